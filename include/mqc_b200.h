@@ -1,0 +1,109 @@
+/* mqc_b200.h — C ABI of the B200-native UCCSD state-vector fragment solver.
+ *
+ * This is the drop-in boundary for the hot path of mahuan-git/MultiscaleQuantumComputing's
+ * VQE fragment solver.  The reference is pure Python and reaches the arithmetic through
+ * VQEChem / OpenFermion / SciPy objects; each entry point below names the reference
+ * interface it stands in for (paths relative to the reference checkout).  A Python host
+ * binds these with ctypes (multiscalequantumcomputing_b200/_lib.py).
+ *
+ * Conventions
+ *   - state vector: complex128[2^N], amplitude index = OpenFermion's
+ *     (qubit q <-> index bit N-1-q; test/testlog_vqe:56-94).
+ *   - Pauli terms: masks over INDEX bits, operator X^xmask Z^zmask (X left of Z per qubit):
+ *       <i ^ xmask| P |i> = (-1)^popcount(i & zmask).
+ *     OpenFermion's label has Y where xmask&zmask and label coefficient
+ *     coeff * (-i)^popcount(xmask & zmask).
+ *   - ansatz factor k: exp(theta[theta_index[k]] * (T_k - T_k^+)), factor 0 acts first;
+ *     kind 1: T = a_a^+ a_i        idx = {i, a, -1, -1}
+ *     kind 2: T = a_a^+ a_b^+ a_j a_i   idx = {i, j, a, b}      (spin orbitals = qubits)
+ *   - every function returns 0 on success, non-zero on failure; mqc_last_error() then holds
+ *     a message (the reference has no exception contract: print+exit(),
+ *     mqc/solver/dmet_solver_vqechem.py:59-61).  There is NO CPU fallback: without a CUDA
+ *     device every compute entry point fails.
+ *   - a handle is bound to one GPU and one stream; handles are not thread safe; calls
+ *     return after results are in host memory.
+ */
+#ifndef MQC_B200_H
+#define MQC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mqc_solver mqc_solver_t;
+
+const char* mqc_last_error(void);
+int mqc_version(void);
+int mqc_device_count(int* count);
+
+/* Replaces: construction of the VQEChem problem object for one fragment,
+ * `DMET(...)` mqc/solver/dmet_solver_vqechem.py:43-51 (state of 2^n_qubits amplitudes). */
+int mqc_create(int n_qubits, int device, mqc_solver_t** out);
+int mqc_destroy(mqc_solver_t* s);
+
+/* Options (before mqc_set_ansatz): "tile_bits" (default 12), "low_bits" (3),
+ * "grad_tile_bits" (11), "mode" (1 = fused tile sweep, 0 = one factor per pass),
+ * "sector" (1 = exploit particle-number/S_z conservation of the ansatz in H|psi>). */
+int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value);
+
+/* Replaces: `mapping(fermi_ham,'JW',...)` + `get_sparse_operator(qubit_ham)`,
+ * mqc/solver/dmet_interface.py:116-123 (the 2^N x 2^N sparse matrix is never formed). */
+int mqc_set_hamiltonian(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask,
+                        const uint64_t* zmask, const double* coeff_re, const double* coeff_im);
+
+/* Replaces: `reference(imp, options)` + `ADAPT(options['ansatz'], imp, pool, ref)`,
+ * mqc/solver/dmet_solver_vqechem.py:63-65, for a fixed factor list. */
+int mqc_set_ansatz(mqc_solver_t* s, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
+                   const int32_t* theta_index, int32_t n_theta, uint64_t ref_index);
+
+/* Replaces: `ansatz.energy(params)`, called by scipy.optimize.minimize at
+ * mqc/solver/dmet_interface.py:295. */
+int mqc_energy(mqc_solver_t* s, const double* theta, double* energy);
+
+/* Replaces: `ansatz.energy` + `ansatz.gradient` (jac=), mqc/solver/dmet_interface.py:295.
+ * Adjoint method: forward sweep, lambda = H psi, reverse sweep over (psi, lambda). */
+int mqc_energy_grad(mqc_solver_t* s, const double* theta, double* energy, double* grad);
+
+/* Replaces: `ansatz.state(params)`, mqc/solver/dmet_solver_vqechem.py:71.  Writes
+ * 2^N interleaved (re, im) pairs in OpenFermion index order.  theta == NULL: state of the
+ * last mqc_energy / mqc_prepare call. */
+int mqc_prepare(mqc_solver_t* s, const double* theta);
+int mqc_state(mqc_solver_t* s, const double* theta, double* re_im, int64_t n_amplitudes);
+
+/* <psi| sum_t c_t P_t |psi> for another operator on the prepared state (e.g. S^2,
+ * mqc/solver/dmet_interface.py:248, or the impurity-energy operator of
+ * mqc/solver/dmet_solver_vqechem.py:75-81). */
+int mqc_expectation(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask, const uint64_t* zmask,
+                    const double* coeff_re, const double* coeff_im, double* value_re, double* value_im);
+
+/* Replaces: `get_rdm12(wfn, n_elec, n_orb, Sz)` = make_strings_qubit + qubit_inverse gather +
+ * make_rdm1 / make_rdm12 + reorder_rdm, mqc/solver/dmet_solver_vqechem.py:109-116 and
+ * mqc/tools/rdm.py:18-30,131-172, in float64 (the reference's float32 is a defect).
+ *   rdm1[p*n+q]              = sum_s <q_s^+ p_s>
+ *   rdm2[((p*n+q)*n+r)*n+s]  = sum_{s,t} <p_s^+ r_t^+ s_t q_s>      (pyscf order)
+ * on the prepared state, restricted to the (n_alpha, n_beta) sector.  rdm2 may be NULL. */
+int mqc_rdm12(mqc_solver_t* s, int32_t n_orb, int32_t n_alpha, int32_t n_beta,
+              double* rdm1, double* rdm2);
+
+/* Device-side timing of the last energy / energy_grad call (CUDA events on the solver's
+ * stream): ms[0] forward sweep, ms[1] H apply, ms[2] reverse sweep, ms[3] total;
+ * counters[0] kernel launches, counters[1] forward passes, counters[2] reverse passes. */
+int mqc_last_timing(mqc_solver_t* s, double* ms4, int64_t* counters3);
+
+/* Host-only introspection of the sweep schedule (works without a GPU). */
+int mqc_schedule_info(mqc_solver_t* s, int32_t which /*0 energy, 1 gradient*/, int32_t* n_passes,
+                      int32_t* tile_bits, int32_t* n_tile_factors);
+int mqc_schedule_pass(mqc_solver_t* s, int32_t which, int32_t pass, int32_t* first_factor,
+                      int32_t* n_factors, uint64_t* act_mask, int32_t* pos16, int32_t* perm16,
+                      int32_t* has_perm);
+int mqc_schedule_factor(mqc_solver_t* s, int32_t which, int32_t tile_factor, uint32_t* m, uint32_t* v,
+                        uint32_t* z, uint64_t* z_out, int32_t* sign0, int32_t* slot);
+int mqc_schedule_final_layout(mqc_solver_t* s, int32_t which, int32_t* phys_of_logical);
+int mqc_schedule_initial_layout(mqc_solver_t* s, int32_t which, int32_t* phys_of_logical);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,213 @@
+"""ctypes binding of the C ABI in include/mqc_b200.h.
+
+The library is the only compute path: if ``libmqc_b200.so`` is missing, or no CUDA device is
+visible when a compute entry point is called, this raises — there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_lib = None
+
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_H = C.c_void_p
+
+# name -> (argtypes); every function returns int except mqc_last_error
+SIGNATURES = {
+    "mqc_version": [],
+    "mqc_device_count": [_i32p],
+    "mqc_create": [C.c_int, C.c_int, C.POINTER(_H)],
+    "mqc_destroy": [_H],
+    "mqc_set_option": [_H, C.c_char_p, C.c_int64],
+    "mqc_set_hamiltonian": [_H, C.c_int64, _u64p, _u64p, _f64p, _f64p],
+    "mqc_set_ansatz": [_H, C.c_int32, _i32p, _i32p, _i32p, C.c_int32, C.c_uint64],
+    "mqc_energy": [_H, _f64p, _f64p],
+    "mqc_energy_grad": [_H, _f64p, _f64p, _f64p],
+    "mqc_prepare": [_H, _f64p],
+    "mqc_state": [_H, _f64p, _f64p, C.c_int64],
+    "mqc_expectation": [_H, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p],
+    "mqc_rdm12": [_H, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p],
+    "mqc_last_timing": [_H, _f64p, _i64p],
+    "mqc_schedule_info": [_H, C.c_int32, _i32p, _i32p, _i32p],
+    "mqc_schedule_pass": [_H, C.c_int32, C.c_int32, _i32p, _i32p, _u64p, _i32p, _i32p, _i32p],
+    "mqc_schedule_factor": [_H, C.c_int32, C.c_int32, _u32p, _u32p, _u32p, _u64p, _i32p, _i32p],
+    "mqc_schedule_final_layout": [_H, C.c_int32, _i32p],
+    "mqc_schedule_initial_layout": [_H, C.c_int32, _i32p],
+}
+
+
+class MqcError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building in-tree first if the sources are newer) and type the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on the box and no prebuilt library
+            if not os.path.exists(path):
+                raise MqcError("CUDA extension libmqc_b200.so is missing and could not be built: %s" % exc)
+    lib = C.CDLL(path)
+    lib.mqc_last_error.restype = C.c_char_p
+    lib.mqc_last_error.argtypes = []
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise MqcError(load().mqc_last_error().decode())
+
+
+def ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    check(load().mqc_device_count(C.byref(n)))
+    return n.value
+
+
+class Handle:
+    """Thin RAII wrapper over ``mqc_solver_t*``."""
+
+    def __init__(self, n_qubits: int, device: int = 0):
+        self.lib = load()
+        self.n_qubits = n_qubits
+        self.h = _H()
+        check(self.lib.mqc_create(n_qubits, device, C.byref(self.h)))
+        self.n_theta = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mqc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        check(self.lib.mqc_set_option(self.h, key.encode(), int(value)))
+
+    def set_hamiltonian(self, xmask, zmask, coeff):
+        x = np.ascontiguousarray(xmask, dtype=np.uint64)
+        z = np.ascontiguousarray(zmask, dtype=np.uint64)
+        c = np.asarray(coeff, dtype=np.complex128)
+        cr = np.ascontiguousarray(c.real)
+        ci = np.ascontiguousarray(c.imag)
+        check(self.lib.mqc_set_hamiltonian(self.h, len(x), ptr(x, _u64p), ptr(z, _u64p), ptr(cr, _f64p), ptr(ci, _f64p)))
+
+    def set_ansatz(self, kind, idx, theta_index, n_theta, ref_index):
+        k = np.ascontiguousarray(kind, dtype=np.int32)
+        ix = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, 4)
+        ti = np.ascontiguousarray(theta_index, dtype=np.int32)
+        check(self.lib.mqc_set_ansatz(self.h, len(k), ptr(k, _i32p), ptr(ix, _i32p), ptr(ti, _i32p), int(n_theta), int(ref_index)))
+        self.n_theta = int(n_theta)
+
+    def _theta(self, theta):
+        t = np.ascontiguousarray(theta, dtype=np.float64)
+        if t.shape != (self.n_theta,):
+            raise ValueError("theta must have shape (%d,)" % self.n_theta)
+        return t
+
+    def energy(self, theta) -> float:
+        t = self._theta(theta)
+        e = C.c_double(0.0)
+        check(self.lib.mqc_energy(self.h, ptr(t, _f64p), C.byref(e)))
+        return e.value
+
+    def energy_grad(self, theta):
+        t = self._theta(theta)
+        e = C.c_double(0.0)
+        g = np.zeros(max(1, self.n_theta))
+        check(self.lib.mqc_energy_grad(self.h, ptr(t, _f64p), C.byref(e), ptr(g, _f64p)))
+        return e.value, g[:self.n_theta]
+
+    def prepare(self, theta):
+        t = self._theta(theta)
+        check(self.lib.mqc_prepare(self.h, ptr(t, _f64p)))
+
+    def state(self, theta=None) -> np.ndarray:
+        out = np.empty(1 << self.n_qubits, dtype=np.complex128)
+        tp = ptr(self._theta(theta), _f64p) if theta is not None else None
+        check(self.lib.mqc_state(self.h, tp, C.cast(out.ctypes.data, _f64p), out.shape[0]))
+        return out
+
+    def expectation(self, xmask, zmask, coeff) -> complex:
+        x = np.ascontiguousarray(xmask, dtype=np.uint64)
+        z = np.ascontiguousarray(zmask, dtype=np.uint64)
+        c = np.asarray(coeff, dtype=np.complex128)
+        cr = np.ascontiguousarray(c.real)
+        ci = np.ascontiguousarray(c.imag)
+        vr, vi = C.c_double(0.0), C.c_double(0.0)
+        check(self.lib.mqc_expectation(self.h, len(x), ptr(x, _u64p), ptr(z, _u64p), ptr(cr, _f64p), ptr(ci, _f64p),
+                                       C.byref(vr), C.byref(vi)))
+        return complex(vr.value, vi.value)
+
+    def rdm12(self, n_orb, n_alpha, n_beta, want_rdm2=True):
+        r1 = np.zeros((n_orb, n_orb))
+        r2 = np.zeros((n_orb,) * 4) if want_rdm2 else None
+        check(self.lib.mqc_rdm12(self.h, n_orb, n_alpha, n_beta, ptr(r1, _f64p),
+                                 ptr(r2, _f64p) if want_rdm2 else None))
+        return r1, r2
+
+    def last_timing(self):
+        ms = np.zeros(4)
+        cnt = np.zeros(3, dtype=np.int64)
+        check(self.lib.mqc_last_timing(self.h, ptr(ms, _f64p), ptr(cnt, _i64p)))
+        return dict(forward_ms=ms[0], hamiltonian_ms=ms[1], reverse_ms=ms[2], total_ms=ms[3],
+                    launches=int(cnt[0]), forward_passes=int(cnt[1]), reverse_passes=int(cnt[2]))
+
+    # ---- host-only schedule introspection -------------------------------------------
+    def schedule(self, which=0):
+        npass, kb, ntf = C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.lib.mqc_schedule_info(self.h, which, C.byref(npass), C.byref(kb), C.byref(ntf)))
+        passes = []
+        for p in range(npass.value):
+            f0, nf, hp = C.c_int32(), C.c_int32(), C.c_int32()
+            act = C.c_uint64()
+            pos = np.zeros(16, dtype=np.int32)
+            perm = np.zeros(16, dtype=np.int32)
+            check(self.lib.mqc_schedule_pass(self.h, which, p, C.byref(f0), C.byref(nf), C.byref(act),
+                                             ptr(pos, _i32p), ptr(perm, _i32p), C.byref(hp)))
+            facs = []
+            for t in range(f0.value, f0.value + nf.value):
+                m, v, z = C.c_uint32(), C.c_uint32(), C.c_uint32()
+                zo = C.c_uint64()
+                s0, slot = C.c_int32(), C.c_int32()
+                check(self.lib.mqc_schedule_factor(self.h, which, t, C.byref(m), C.byref(v), C.byref(z),
+                                                   C.byref(zo), C.byref(s0), C.byref(slot)))
+                facs.append(dict(m=m.value, v=v.value, z=z.value, z_out=zo.value, sign0=s0.value, slot=slot.value))
+            passes.append(dict(act_mask=act.value, pos=pos[:kb.value].copy(), perm=perm[:kb.value].copy(),
+                               has_perm=bool(hp.value), factors=facs))
+        lay = np.zeros(self.n_qubits, dtype=np.int32)
+        check(self.lib.mqc_schedule_final_layout(self.h, which, ptr(lay, _i32p)))
+        lay0 = np.zeros(self.n_qubits, dtype=np.int32)
+        check(self.lib.mqc_schedule_initial_layout(self.h, which, ptr(lay0, _i32p)))
+        return dict(tile_bits=kb.value, passes=passes, final_layout=lay, initial_layout=lay0)

@@ -1,0 +1,168 @@
+"""Jordan-Wigner term table of the fragment Hamiltonian, closed form (host side, numpy).
+
+Replaces, for the hot path, the symbolic chain of the reference
+(`mqc/solver/dmet_interface.py:10-39` get_1e_2e_integral, `:200-241` DMET.hamiltonian,
+`:112-123` S^2 penalty + ``mapping(...,'JW')``), which goes through OpenFermion
+``FermionOperator`` / ``normal_ordered`` / ``jordan_wigner`` one Python term at a time.
+Here every ladder-operator product is expanded directly into Pauli strings kept as integer
+masks, vectorised over all terms:
+
+    a_P   = 1/2 X_P (1 - Z_P) Z_0..Z_{P-1}          a_P^+ = 1/2 X_P (1 + Z_P) Z_0..Z_{P-1}
+    (X^x1 Z^z1)(X^x2 Z^z2) = (-1)^{popc(z1 & x2)} X^{x1^x2} Z^{z1^z2}
+
+Output convention (the C ABI's, include/mqc_b200.h): masks over amplitude-INDEX bits
+(qubit q <-> index bit N-1-q, OpenFermion's ``get_sparse_operator`` order), operator
+X^xmask Z^zmask, i.e. <i ^ xmask| P |i> = (-1)^{popc(i & zmask)}.  The OpenFermion label
+of a term has Y where xmask & zmask and label coefficient coeff * (-i)^{popc(x&z)}.
+
+tests/test_jw_table.py checks this against the literal restatement in oracle/ (identical
+key sets; coefficients to a few ulp - summation order differs from OpenFermion's).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _popc64(v):
+    v = v.astype(np.uint64)
+    m1 = np.uint64(0x5555555555555555)
+    m2 = np.uint64(0x3333333333333333)
+    m4 = np.uint64(0x0F0F0F0F0F0F0F0F)
+    v = v - ((v >> np.uint64(1)) & m1)
+    v = (v & m2) + ((v >> np.uint64(2)) & m2)
+    v = (v + (v >> np.uint64(4))) & m4
+    return ((v * np.uint64(0x0101010101010101)) >> np.uint64(56)).astype(np.int64)
+
+
+def _expand_products(ops_idx, ops_act, coeff):
+    """JW-expand T ladder products of equal length L.
+    ops_idx int64[T,L] qubit numbers, ops_act int64[T,L] (1 = creation), coeff complex[T].
+    Returns (x, z, c) arrays of T * 2^L Pauli rows in qubit-number bits."""
+    T, L = ops_idx.shape
+    one = np.uint64(1)
+    x = np.zeros((T, 1), dtype=np.uint64)
+    z = np.zeros((T, 1), dtype=np.uint64)
+    c = coeff.astype(np.complex128).reshape(T, 1)
+    for l in range(L):
+        p = ops_idx[:, l].astype(np.uint64)
+        bit = (one << p)
+        chain = bit - one
+        act = ops_act[:, l]
+        # two choices per ladder operator: (bit, chain, +1/2) and (bit, chain|bit, +-1/2)
+        lx = np.stack([bit, bit], axis=1)                                  # (T,2)
+        lz = np.stack([chain, chain | bit], axis=1)
+        lc = np.stack([np.full(T, 0.5), np.where(act == 1, 0.5, -0.5)], axis=1)
+        sgn = 1.0 - 2.0 * (_popc64(z[:, :, None] & lx[:, None, :]) & 1)    # (T,R,2)
+        x = (x[:, :, None] ^ lx[:, None, :]).reshape(T, -1)
+        z = (z[:, :, None] ^ lz[:, None, :]).reshape(T, -1)
+        c = (c[:, :, None] * lc[:, None, :] * sgn).reshape(T, -1)
+    return x.reshape(-1), z.reshape(-1), c.reshape(-1)
+
+
+def _reverse_bits(mask, n):
+    out = np.zeros_like(mask)
+    one = np.uint64(1)
+    for q in range(n):
+        out |= ((mask >> np.uint64(q)) & one) << np.uint64(n - 1 - q)
+    return out
+
+
+def _combine(xs, zs, cs, n_qubits, tol):
+    x = np.concatenate(xs)
+    z = np.concatenate(zs)
+    c = np.concatenate(cs)
+    x = _reverse_bits(x, n_qubits)
+    z = _reverse_bits(z, n_qubits)
+    key = (x.astype(object) << 64) | z.astype(object) if n_qubits > 32 else \
+        (x << np.uint64(32)) | z
+    uniq, inv = np.unique(key, return_inverse=True)
+    cre = np.bincount(inv, weights=c.real, minlength=len(uniq))
+    cim = np.bincount(inv, weights=c.imag, minlength=len(uniq))
+    csum = cre + 1j * cim
+    if n_qubits > 32:
+        ux = np.array([int(k) >> 64 for k in uniq], dtype=np.uint64)
+        uz = np.array([int(k) & ((1 << 64) - 1) for k in uniq], dtype=np.uint64)
+    else:
+        ux = uniq >> np.uint64(32)
+        uz = uniq & np.uint64(0xFFFFFFFF)
+    keep = np.abs(csum) > tol
+    return ux[keep], uz[keep], csum[keep]
+
+
+def s2_ladder_terms(n_orb):
+    """S^2 = S_- S_+ + S_z^2 + S_z as explicit ladder products (vqechem.tools.s2_operator,
+    `dmet_interface.py:112`), alpha = 2p, beta = 2p+1."""
+    four_i, four_a, four_c = [], [], []
+    two_i, two_a, two_c = [], [], []
+    for p in range(n_orb):
+        a, b = 2 * p, 2 * p + 1
+        two_i += [(a, a), (b, b)]
+        two_a += [(1, 0), (1, 0)]
+        two_c += [0.5, -0.5]
+        for q in range(n_orb):
+            c, d = 2 * q, 2 * q + 1
+            four_i.append((b, a, c, d)); four_a.append((1, 0, 1, 0)); four_c.append(1.0)      # S_- S_+
+            for (u, su) in ((a, 0.5), (b, -0.5)):
+                for (v, sv) in ((c, 0.5), (d, -0.5)):
+                    four_i.append((u, u, v, v)); four_a.append((1, 0, 1, 0)); four_c.append(su * sv)
+    return (np.array(two_i), np.array(two_a), np.array(two_c, dtype=np.complex128),
+            np.array(four_i), np.array(four_a), np.array(four_c, dtype=np.complex128))
+
+
+def fragment_term_table(one_body_mo, two_body_mo, n_imp_orbs=0, chempot_imp=0.0, s2_shift=0.0,
+                        tol=1e-14):
+    """(xmask, zmask, coeff) sorted by (xmask, zmask) for
+         H = sum_PQ h1[P,Q] P^+ Q + 1/2 sum_PQRS h2[P,Q,R,S] P^+ Q^+ R S  (+ s2_shift * S^2)
+    with h1/h2 the interleaved spin-orbital integrals of get_1e_2e_integral and the
+    chemical potential subtracted on the impurity diagonal (`dmet_interface.py:226-233`)."""
+    fock = np.asarray(one_body_mo, dtype=np.float64)
+    tei = np.asarray(two_body_mo, dtype=np.float64)
+    n = fock.shape[0]
+    nq = 2 * n
+    h = fock.copy()
+    if chempot_imp != 0.0:
+        d = np.arange(n_imp_orbs)
+        h[d, d] -= chempot_imp
+    xs, zs, cs = [], [], []
+    # one-body: both spins
+    p, q = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    p, q = p.reshape(-1), q.reshape(-1)
+    for s in (0, 1):
+        idx = np.stack([2 * p + s, 2 * q + s], axis=1)
+        act = np.tile(np.array([1, 0]), (len(p), 1))
+        x, z, c = _expand_products(idx, act, h[p, q].astype(np.complex128))
+        xs.append(x); zs.append(z); cs.append(c)
+    # two-body: h2[P,Q,R,S] = tei[p,s,q,r] for spins (sP,sQ,sR,sS) = (s,t,t,s)
+    p, q, r, s_ = np.meshgrid(*(np.arange(n),) * 4, indexing="ij")
+    p, q, r, s_ = (v.reshape(-1) for v in (p, q, r, s_))
+    val = 0.5 * tei[p, s_, q, r]
+    for sg in (0, 1):
+        for tu in (0, 1):
+            P, Q, R, S = 2 * p + sg, 2 * q + tu, 2 * r + tu, 2 * s_ + sg
+            ok = (P != Q) & (R != S) & (val != 0.0)
+            idx = np.stack([P[ok], Q[ok], R[ok], S[ok]], axis=1)
+            act = np.tile(np.array([1, 1, 0, 0]), (idx.shape[0], 1))
+            # chunk to bound memory at large n
+            step = 1 << 18
+            for a0 in range(0, idx.shape[0], step):
+                x, z, c = _expand_products(idx[a0:a0 + step], act[a0:a0 + step],
+                                           val[ok][a0:a0 + step].astype(np.complex128))
+                xs.append(x); zs.append(z); cs.append(c)
+    if s2_shift != 0.0:
+        ti, ta, tc, fi, fa, fc = s2_ladder_terms(n)
+        x, z, c = _expand_products(ti, ta, tc * s2_shift)
+        xs.append(x); zs.append(z); cs.append(c)
+        x, z, c = _expand_products(fi, fa, fc * s2_shift)
+        xs.append(x); zs.append(z); cs.append(c)
+    return _combine(xs, zs, cs, nq, tol)
+
+
+def s2_term_table(n_orb, tol=1e-14):
+    ti, ta, tc, fi, fa, fc = s2_ladder_terms(n_orb)
+    x1, z1, c1 = _expand_products(ti, ta, tc)
+    x2, z2, c2 = _expand_products(fi, fa, fc)
+    return _combine([x1, x2], [z1, z2], [c1, c2], 2 * n_orb, tol)
+
+
+def number_of_x_groups(xmask):
+    return len(np.unique(xmask))

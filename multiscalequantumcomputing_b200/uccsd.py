@@ -1,0 +1,124 @@
+"""UCCSD factor lists (host side).
+
+The reference builds its ansatz inside VQEChem (`mqc/solver/dmet_solver_vqechem.py:54-65`:
+``FermionOps`` pool + ``ADAPT``); BASELINE.json's north star fixes the ansatz to
+Jordan-Wigner UCCSD in disentangled (factorised) form
+
+    |psi(theta)> = prod_k exp(theta_k (T_k - T_k^+)) |ref>,      factor 0 acts first
+
+with T_k = a_a^+ a_i (single) or a_a^+ a_b^+ a_j a_i (double) over spin orbitals
+(alpha = even, beta = odd, `mqc/solver/dmet_interface.py:27-37`).  Factor order is part of
+the ansatz (SURVEY.md §7 "hard parts"); two orders are provided:
+
+``lex``      singles then doubles, lexicographic in (i,a) / (i,j,a,b)
+``blocked``  the same factor SET, ordered block by block over (occupied-orbital subset,
+             virtual-orbital subset) pairs so that consecutive factors move few distinct
+             qubits - this is what lets the GPU sweep fuse ~50-100 factors per HBM pass.
+
+A factor list is plain data: ``kind`` int32[n], ``idx`` int32[n,4] (single: i,a,-1,-1;
+double: i,j,a,b), ``theta_index`` int32[n].
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from itertools import combinations
+
+import numpy as np
+
+
+@dataclass
+class FactorList:
+    n_qubits: int
+    kind: np.ndarray         # int32[n]
+    idx: np.ndarray          # int32[n,4]
+    theta_index: np.ndarray  # int32[n]
+    n_theta: int
+    ref_index: int           # amplitude index of the reference determinant
+
+    def __len__(self):
+        return len(self.kind)
+
+    def as_tuples(self):
+        out = []
+        for k, ix in zip(self.kind, self.idx):
+            out.append((int(k), tuple(int(v) for v in (ix[:2] if k == 1 else ix))))
+        return out
+
+
+def reference_index(n_qubits: int, n_elec: int) -> int:
+    """Qubits 0..n_elec-1 occupied; qubit 0 is the most significant index bit
+    (`test/testlog_vqe:25`: index 240 for N=8, N_e=4)."""
+    return (1 << n_qubits) - (1 << (n_qubits - n_elec))
+
+
+def _all_excitations(n_orb: int, n_elec: int):
+    assert n_elec % 2 == 0, "closed-shell reference expected (noa = nob, dmet_interface.py:84-85)"
+    nq = 2 * n_orb
+    occ = list(range(n_elec))
+    vir = list(range(n_elec, nq))
+    singles = [(i, a) for i in occ for a in vir if i % 2 == a % 2]
+    doubles = []
+    for i, j in combinations(occ, 2):
+        for a, b in combinations(vir, 2):
+            if sorted((i % 2, j % 2)) == sorted((a % 2, b % 2)):
+                doubles.append((i, j, a, b))
+    return singles, doubles
+
+
+def _pair_cover(items, size):
+    """Greedy family of ``size``-subsets of ``items`` covering every pair (and every item)."""
+    items = list(items)
+    if len(items) <= size:
+        return [tuple(items)]
+    need = set(combinations(items, 2))
+    fam = []
+    while need:
+        best, gain = None, -1
+        for c in combinations(items, size):
+            g = sum(1 for p in combinations(c, 2) if p in need)
+            if g > gain:
+                best, gain = c, g
+        fam.append(best)
+        need -= set(combinations(best, 2))
+    return fam
+
+
+def uccsd_factors(n_orb: int, n_elec: int, order: str = "blocked", block_orbs: int = 6) -> FactorList:
+    """All spin-conserving singles and doubles from the closed-shell reference.
+
+    ``block_orbs``: spatial orbitals per block (occupied + virtual); 6 spatial = 12 qubits
+    matches the 12-bit shared-memory tile of the sweep kernel."""
+    nq = 2 * n_orb
+    singles, doubles = _all_excitations(n_orb, n_elec)
+    if order == "lex":
+        seq = [(1, s + (-1, -1)) for s in singles] + [(2, d) for d in doubles]
+    elif order == "blocked":
+        nocc, nvir = n_elec // 2, n_orb - n_elec // 2
+        so = min(nocc, block_orbs // 2)
+        sv = min(nvir, block_orbs - so)
+        so = min(nocc, block_orbs - sv)
+        occ_blocks = _pair_cover(range(nocc), so)
+        vir_blocks = _pair_cover(range(nocc, n_orb), sv)
+        seq = []
+        done = set()
+        flip = False
+        for ob in occ_blocks:
+            vbs = vir_blocks[::-1] if flip else vir_blocks
+            flip = not flip
+            for vb in vbs:
+                orbs = set(ob) | set(vb)
+                for s in singles:
+                    if s not in done and all((q // 2) in orbs for q in s):
+                        done.add(s)
+                        seq.append((1, s + (-1, -1)))
+                for d in doubles:
+                    if d not in done and all((q // 2) in orbs for q in d):
+                        done.add(d)
+                        seq.append((2, d))
+        assert len(done) == len(singles) + len(doubles)
+    else:
+        raise ValueError("unknown order %r" % order)
+    kind = np.array([k for k, _ in seq], dtype=np.int32)
+    idx = np.array([ix for _, ix in seq], dtype=np.int32).reshape(-1, 4)
+    theta_index = np.arange(len(seq), dtype=np.int32)
+    return FactorList(nq, kind, idx, theta_index, len(seq), reference_index(nq, n_elec))

@@ -1,0 +1,58 @@
+"""Host-side sweep scheduler (C++ in the CUDA library, reached through the C ABI without a
+GPU): executing its passes with the numpy interpreter reproduces the oracle state."""
+import numpy as np
+import pytest
+
+import schedule_interp as SI
+from multiscalequantumcomputing_b200 import _lib
+from multiscalequantumcomputing_b200.uccsd import uccsd_factors
+from oracle.statevector import UCCSDOracle
+
+EMPTY = (np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.complex128))
+
+
+@pytest.mark.parametrize("n,ne,kb,lb,order", [
+    (4, 4, 12, 3, "blocked"),     # whole register in one tile
+    (4, 4, 6, 2, "lex"),
+    (5, 4, 7, 3, "lex"),
+    (6, 6, 8, 2, "blocked"),
+    (6, 6, 7, 3, "lex"),
+    (6, 4, 9, 4, "blocked"),
+    (7, 6, 10, 3, "blocked"),
+])
+def test_schedule_reproduces_oracle_state(n, ne, kb, lb, order):
+    F = uccsd_factors(n, ne, order)
+    h = _lib.Handle(2 * n)
+    h.set_option("tile_bits", kb)
+    h.set_option("low_bits", lb)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    S = h.schedule(0)
+    th = np.random.default_rng(5).normal(0, 0.2, F.n_theta)
+    cs = [(np.cos(th[t]), np.sin(th[t])) for t in F.theta_index]
+    psi = SI.to_logical(SI.run_forward(S, 2 * n, F.ref_index, cs), S["final_layout"])
+    ref = UCCSDOracle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, EMPTY).state(th)
+    assert abs(psi - ref).max() < 1e-14
+    # every factor scheduled exactly once, in order
+    slots = [f["slot"] for p in S["passes"] for f in p["factors"]]
+    assert slots == list(range(len(F)))
+    for p in S["passes"]:
+        assert bin(p["act_mask"]).count("1") == S["tile_bits"]
+        if S["tile_bits"] < 2 * n:
+            assert p["act_mask"] & ((1 << lb) - 1) == (1 << lb) - 1     # low bits always active
+
+
+def test_blocked_order_fuses_24_qubit_uccsd():
+    F = uccsd_factors(12, 12, "blocked")
+    assert len(F) == 1818
+    h = _lib.Handle(24)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    S = h.schedule(0)
+    assert len(S["passes"]) <= 48                           # ~40 factors per HBM pass on average
+    F2 = uccsd_factors(12, 12, "lex")
+    assert sorted(map(tuple, F.idx.tolist())) == sorted(map(tuple, F2.idx.tolist()))
+
+
+def test_factor_counts():
+    # n_theta = 2ov + 2C(o,2)C(v,2) + (ov)^2
+    for n, cnt in ((4, 26), (8, 360)):
+        assert len(uccsd_factors(n, n)) == cnt

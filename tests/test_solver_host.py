@@ -1,0 +1,38 @@
+"""Host logic of the drop-in solve() with the oracle plugged in behind the ansatz surface
+(CPU only; the product path itself always runs the CUDA library)."""
+import numpy as np
+
+from oracle_ansatz import OracleAnsatz
+from multiscalequantumcomputing_b200.solver import solve, prepare_problem
+from multiscalequantumcomputing_b200.synth.hydrogen import hydrogen_ring, hydrogen_chain, local_integrals
+from multiscalequantumcomputing_b200.synth.dmet_loop import DMETRun, atom_clusters, fragment_problems
+from oracle.fci import solve_fci
+
+ORACLE = dict(_ansatz_factory=lambda nq, tab, fac: OracleAnsatz(nq, tab, fac), warm_start=False)
+
+
+def test_uccsd_fragment_close_to_fci(golden):
+    ints = local_integrals(hydrogen_ring(10, 1.0))
+    p = fragment_problems(ints, atom_clusters(10, 2), 0.0, True)[0]
+    e_imp, rdm1, det = solve(p.oei, p.fock, p.tei, p.nelec, p.n_imp_orbs, 0.0, return_details=True, **ORACLE)
+    assert det.n_theta == 26
+    assert 0.0 <= det.e_uccsd - golden["ring_fci"]["e_fci"][0] < 1e-4      # variational, near-exact
+    assert abs(e_imp - golden["ring_fci"]["e_imp"][0]) < 1e-4
+    assert abs(np.trace(rdm1) - 4.0) < 1e-10
+    assert abs(rdm1 - rdm1.T).max() < 1e-10
+
+
+def test_chemical_potential_enters_hamiltonian():
+    ints = local_integrals(hydrogen_chain(10, 0.8))
+    p = fragment_problems(ints, atom_clusters(10, 2), 0.0, False)[1]
+    a = prepare_problem(p.fock, p.tei, p.nelec, p.n_imp_orbs, 0.0)
+    b = prepare_problem(p.fock, p.tei, p.nelec, p.n_imp_orbs, 0.05)
+    assert len(a["table"][0]) == len(b["table"][0])
+    assert abs(a["table"][2] - b["table"][2]).max() > 1e-3
+
+
+def test_dmet_with_uccsd_solver_close_to_fci_logs(golden):
+    ints = local_integrals(hydrogen_ring(10, 1.0))
+    run = DMETRun(ints, atom_clusters(10, 2), solver=lambda *a: solve(*a, **ORACLE), trans_inv=True)
+    e = run.run()
+    assert abs(e - golden["ring_fci"]["dmet_energy"]) < 2e-4
