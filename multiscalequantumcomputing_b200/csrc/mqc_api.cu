@@ -69,17 +69,30 @@ struct HamTables {                  // one Hamiltonian mapped to one physical la
     void reset() { gmask.release(); tz.release(); goff.release(); tc.release(); n_groups = 0; }
 };
 
+struct SecHamTables {               // Hamiltonian in sector form for one layout and (na, nb)
+    DevBuf<unsigned> ma_list, gmb;
+    DevBuf<int> ma_goff, goff;
+    DevBuf<u64> tz;
+    DevBuf<double2> tc;
+    int n_ma = 0;
+    void reset() { ma_list.release(); gmb.release(); ma_goff.release(); goff.release(); tz.release(); tc.release(); n_ma = 0; }
+};
+
 struct LayoutTables {
     std::vector<int> phys;          // logical bit -> physical position
     HamTables ham;
+    SecHamTables sham;
+    bool sham_ready = false;
     DevBuf<u64> astr, bstr, qbit, below;
+    DevBuf<unsigned> aorb, borb, rank_a, rank_b;
     DevBuf<int> phys_dev;
     u64 amask = 0, bmask = 0;
     int na = -1, nb = -1;           // sector the strings were built for
     bool ham_ready = false;
     void reset() {
-        phys.clear(); ham.reset(); astr.release(); bstr.release(); qbit.release(); below.release();
-        phys_dev.release(); amask = bmask = 0; na = nb = -1; ham_ready = false;
+        phys.clear(); ham.reset(); sham.reset(); astr.release(); bstr.release(); qbit.release(); below.release();
+        aorb.release(); borb.release(); rank_a.release(); rank_b.release();
+        phys_dev.release(); amask = bmask = 0; na = nb = -1; ham_ready = false; sham_ready = false;
     }
 };
 
@@ -91,9 +104,9 @@ struct mqc_solver {
     bool gpu_ready = false;
 
     // options
-    int tile_bits = 12, low_bits = 3, grad_tile_bits = 11, mode = 1, use_sector = 1, tile_threads = 256;
+    int tile_bits = 12, low_bits = 3, grad_tile_bits = 12, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
 
-    DevBuf<double2> psi, lam, cs, scratch_state;
+    DevBuf<double2> psi, lam, cs, scratch_state, csec, lsec;
     DevBuf<double> theta, grad, scalars, rdm_acc;
     DevBuf<int> theta_index;
     DevBuf<MqcTileFactor> tf[2];
@@ -204,6 +217,8 @@ static void require_gpu(mqc_solver* s) {
     for (auto& e2 : s->ev) CK(cudaEventCreate(&e2));
     CK(cudaFuncSetAttribute(k_tile_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_tile_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_tile_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     s->gpu_ready = true;
 }
 
@@ -232,17 +247,21 @@ static void build_ham_tables(mqc_solver* s, const HamHost& H, const std::vector<
     CK(cudaStreamSynchronize(s->stream));
 }
 
-static void enum_strings(int n_orb, int k, int spin, int n, const std::vector<int>& phys, std::vector<u64>& out) {
-    out.clear();
+static void enum_strings(int n_orb, int k, int spin, int n, const std::vector<int>& phys, std::vector<u64>& out,
+                         std::vector<unsigned>& orb, std::vector<unsigned>& rank) {
+    out.clear(); orb.clear();
+    rank.assign((size_t)1 << n_orb, 0xffffffffu);
     if (k < 0 || k > n_orb) return;
-    if (k == 0) { out.push_back(0); return; }
+    if (k == 0) { out.push_back(0); orb.push_back(0); rank[0] = 0; return; }
     u64 v = (1ull << k) - 1ull;
     const u64 limit = 1ull << n_orb;
     while (v < limit) {
         u64 img = 0;
         for (int p = 0; p < n_orb; ++p)
             if ((v >> p) & 1ull) img |= 1ull << phys[n - 1 - (2 * p + spin)];
+        rank[v] = (unsigned)out.size();
         out.push_back(img);
+        orb.push_back((unsigned)v);
         const u64 c = v & (~v + 1ull), r = v + c;
         v = (((r ^ v) >> 2) / c) | r;
     }
@@ -252,10 +271,16 @@ static void build_sector_tables(mqc_solver* s, LayoutTables& L, int na, int nb) 
     if (L.na == na && L.nb == nb && L.astr.p) return;
     const int n = s->n, n_orb = n / 2;
     std::vector<u64> a, b;
-    enum_strings(n_orb, na, 0, n, L.phys, a);
-    enum_strings(n_orb, nb, 1, n, L.phys, b);
+    std::vector<unsigned> ao, bo, ra, rb;
+    enum_strings(n_orb, na, 0, n, L.phys, a, ao, ra);
+    enum_strings(n_orb, nb, 1, n, L.phys, b, bo, rb);
     L.astr.upload(a, s->stream);
     L.bstr.upload(b, s->stream);
+    L.aorb.upload(ao, s->stream);
+    L.borb.upload(bo, s->stream);
+    L.rank_a.upload(ra, s->stream);
+    L.rank_b.upload(rb, s->stream);
+    L.sham_ready = false;
     L.amask = L.bmask = 0;
     std::vector<u64> qbit(n), below(n);
     u64 acc = 0;
@@ -272,6 +297,66 @@ static void build_sector_tables(mqc_solver* s, LayoutTables& L, int na, int nb) 
     L.na = na; L.nb = nb;
 }
 
+static void build_sec_ham(mqc_solver* s, const HamHost& H, const std::vector<int>& phys, SecHamTables& T) {
+    const int n = s->n;
+    std::vector<int> orb_of(n), spin_of(n);
+    for (int q = 0; q < n; ++q) { orb_of[phys[n - 1 - q]] = q / 2; spin_of[phys[n - 1 - q]] = q & 1; }
+    struct Row { unsigned ma, mb; u64 z; double2 c; };
+    std::vector<Row> rows;
+    rows.reserve(H.x.size());
+    for (size_t t = 0; t < H.x.size(); ++t) {
+        u64 px = mqc_map_mask(H.x[t], phys);
+        unsigned ma = 0, mb = 0;
+        while (px) {
+            const int b = __builtin_ctzll(px); px &= px - 1;
+            if (spin_of[b]) mb |= 1u << orb_of[b]; else ma |= 1u << orb_of[b];
+        }
+        if ((__builtin_popcount(ma) | __builtin_popcount(mb)) & 1) continue;   // leaves the sector
+        rows.push_back(Row{ma, mb, mqc_map_mask(H.z[t], phys), H.c[t]});
+    }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) {
+        return a.ma != b.ma ? a.ma < b.ma : a.mb < b.mb; });
+    std::vector<unsigned> ma_list, gmb;
+    std::vector<int> ma_goff, goff;
+    std::vector<u64> tz(rows.size());
+    std::vector<double2> tc(rows.size());
+    for (size_t k = 0; k < rows.size(); ++k) {
+        const bool new_ma = (k == 0) || rows[k].ma != rows[k - 1].ma;
+        const bool new_g = new_ma || rows[k].mb != rows[k - 1].mb;
+        if (new_g) {
+            if (new_ma) { ma_list.push_back(rows[k].ma); ma_goff.push_back((int)gmb.size()); }
+            gmb.push_back(rows[k].mb);
+            goff.push_back((int)k);
+        }
+        tz[k] = rows[k].z;
+        tc[k] = rows[k].c;
+    }
+    ma_goff.push_back((int)gmb.size());
+    goff.push_back((int)rows.size());
+    if (gmb.empty()) gmb.push_back(0);
+    if (ma_list.empty()) ma_list.push_back(0);
+    if (tz.empty()) { tz.push_back(0); tc.push_back(make_double2(0, 0)); }
+    T.n_ma = (int)ma_goff.size() - 1;
+    T.ma_list.upload(ma_list, s->stream);
+    T.ma_goff.upload(ma_goff, s->stream);
+    T.gmb.upload(gmb, s->stream);
+    T.goff.upload(goff, s->stream);
+    T.tz.upload(tz, s->stream);
+    T.tc.upload(tc, s->stream);
+    CK(cudaStreamSynchronize(s->stream));
+}
+
+static MqcSecHamDev sec_ham_dev(const LayoutTables& L, const SecHamTables& T) {
+    MqcSecHamDev D{};
+    D.n_ma = T.n_ma;
+    D.ma_list = T.ma_list.p; D.ma_goff = T.ma_goff.p; D.gmb = T.gmb.p; D.goff = T.goff.p;
+    D.tz = T.tz.p; D.tc = T.tc.p;
+    D.aorb = L.aorb.p; D.borb = L.borb.p; D.astr = L.astr.p; D.bstr = L.bstr.p;
+    D.rank_a = L.rank_a.p; D.rank_b = L.rank_b.p;
+    D.n_a = (unsigned)L.astr.n; D.n_b = (unsigned)L.bstr.n;
+    return D;
+}
+
 static MqcSectorDev sector_dev(const LayoutTables& L, bool enabled) {
     MqcSectorDev S{};
     S.enabled = enabled ? 1 : 0;
@@ -284,27 +369,65 @@ static MqcSectorDev sector_dev(const LayoutTables& L, bool enabled) {
 
 static void ensure_layout_ready(mqc_solver* s, int which) {
     LayoutTables& L = s->lay[which];
-    if (!L.ham_ready) {
-        if (!s->have_ham) throw MqcError("mqc_set_hamiltonian has not been called");
+    if (!s->have_ham) throw MqcError("mqc_set_hamiltonian has not been called");
+    if (!L.ham_ready && !(s->conserving && s->use_sector)) {
         build_ham_tables(s, s->ham, L.phys, L.ham);
         L.ham_ready = true;
     }
-    if (s->conserving && s->use_sector) build_sector_tables(s, L, s->na, s->nb);
+    if (s->conserving && s->use_sector) {
+        build_sector_tables(s, L, s->na, s->nb);
+        if (!L.sham_ready) { build_sec_ham(s, s->ham, L.phys, L.sham); L.sham_ready = true; }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
 // launch sequences
 // ---------------------------------------------------------------------------------------
+static double binom(int n, int k) {
+    if (k < 0 || k > n) return 0.0;
+    double r = 1.0;
+    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+    return r;
+}
+
 static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int reverse) {
     const MqcSchedule& S = s->sched[which];
     const MqcPass& P = S.passes[pass];
     const int nf = P.f1 - P.f0;
+    const unsigned grid = (unsigned)(s->dim >> P.k);
+    const bool sparse = s->conserving && s->use_sector && s->sparse_tiles;
+    if (sparse) {
+        // alpha = even qubits, beta = odd qubits.  Tile-local coordinates are those of the
+        // forward pass's LOAD layout in both directions (the reverse pass un-permutes while
+        // loading), and a pass never moves the inactive bits, so one set of masks serves both.
+        MqcSparse SP{};
+        const std::vector<int>& ph = S.pass_phys_before[pass];
+        for (int q = 0; q < s->n; ++q) {
+            const u64 bit = 1ull << ph[s->n - 1 - q];
+            if (q & 1) SP.bmask |= bit; else SP.amask |= bit;
+        }
+        SP.na = s->na; SP.nb = s->nb;
+        const int n_orb_a = (s->n + 1) / 2, n_orb_b = s->n / 2;
+        const int a_act = __builtin_popcountll(SP.amask & P.act_mask), b_act = __builtin_popcountll(SP.bmask & P.act_mask);
+        double ca = 0, cb = 0;
+        for (int k = 0; k <= a_act; ++k) if (k <= s->na && s->na - k <= n_orb_a - a_act) ca = std::max(ca, binom(a_act, k));
+        for (int k = 0; k <= b_act; ++k) if (k <= s->nb && s->nb - k <= n_orb_b - b_act) cb = std::max(cb, binom(b_act, k));
+        SP.cap = std::max(1, (int)(ca * cb + 0.5));
+        int nthr = s->sparse_threads;
+        while (nthr > 32 && nthr / 2 >= SP.cap) nthr >>= 1;
+        const size_t smem = mqc_sparse_smem_bytes(P.k, SP.cap, adj);
+        if (smem <= 232448) {
+            if (adj) k_tile_sparse<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n, reverse, SP);
+            else k_tile_sparse<false><<<grid, nthr, smem, s->stream>>>(s->psi.p, nullptr, P, s->tf[which].p, s->cs.p, nullptr, s->n, reverse, SP);
+            s->counters[0]++;
+            return;
+        }
+    }
     int nthr = s->tile_threads;
     const int T = 1 << P.k;
     while (nthr > 32 && nthr > T / 2) nthr >>= 1;
     const size_t smem = mqc_tile_smem_bytes(P.k, nf, adj, nthr);
     if (smem > 232448) throw MqcError("tile does not fit shared memory; lower tile_bits / grad_tile_bits");
-    const unsigned grid = (unsigned)(s->dim >> P.k);
     if (adj)
         k_tile_sweep<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n, reverse);
     else
@@ -339,16 +462,34 @@ static void forward(mqc_solver* s, int which, const double* theta) {
     s->state_layout = which;
 }
 
-static void happly(mqc_solver* s, int which, const HamTables& T, double2* lam_out, double* host_val2) {
+static void happly(mqc_solver* s, int which, const HamTables& T, const SecHamTables* ST, double2* lam_out,
+                   double* host_val2) {
     LayoutTables& L = s->lay[which];
-    const bool sec = s->conserving && s->use_sector;
-    MqcSectorDev S = sector_dev(L, sec);
-    const u64 count = sec ? (u64)L.astr.n * (u64)L.bstr.n : s->dim;
+    const bool sec = s->conserving && s->use_sector && ST;
     CK(cudaMemsetAsync(s->scalars.p, 0, 2 * sizeof(double), s->stream));
-    if (lam_out && sec) CK(cudaMemsetAsync(lam_out, 0, sizeof(double2) * s->dim, s->stream));
-    const unsigned grid = (unsigned)((count + 255) / 256);
-    k_happly<<<grid, 256, 0, s->stream>>>(s->psi.p, lam_out, T.dev(), S, count, s->scalars.p);
-    s->counters[0]++;
+    if (sec) {
+        const unsigned nA = (unsigned)L.astr.n, nB = (unsigned)L.bstr.n;
+        const u64 cnt = (u64)nA * nB;
+        if (s->csec.n < cnt) { s->csec.alloc(cnt); s->lsec.alloc(cnt); }
+        const unsigned gl = (unsigned)((cnt + 255) / 256);
+        k_sector_gather<<<gl, 256, 0, s->stream>>>(s->psi.p, s->csec.p, L.astr.p, L.bstr.p, nA, nB);
+        unsigned bd = 256;
+        while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
+        dim3 grid(nA, (nB + bd * MQC_HS_R - 1) / (bd * MQC_HS_R));
+        k_happly_sector<<<grid, bd, 0, s->stream>>>(s->csec.p, lam_out ? s->lsec.p : nullptr, sec_ham_dev(L, *ST), s->scalars.p);
+        s->counters[0] += 2;
+        if (lam_out) {
+            CK(cudaMemsetAsync(lam_out, 0, sizeof(double2) * s->dim, s->stream));
+            k_sector_scatter<<<gl, 256, 0, s->stream>>>(lam_out, s->lsec.p, L.astr.p, L.bstr.p, nA, nB);
+            s->counters[0]++;
+        }
+    } else {
+        MqcSectorDev S = sector_dev(L, false);
+        const u64 count = s->dim;
+        const unsigned grid = (unsigned)((count + 255) / 256);
+        k_happly<<<grid, 256, 0, s->stream>>>(s->psi.p, lam_out, T.dev(), S, count, s->scalars.p);
+        s->counters[0]++;
+    }
     if (host_val2) {
         CK(cudaMemcpyAsync(host_val2, s->scalars.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     }
@@ -441,12 +582,16 @@ int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value) {
     else if (k == "mode") s->mode = (int)value;
     else if (k == "sector") s->use_sector = (int)value;
     else if (k == "tile_threads") s->tile_threads = (int)value;
+    else if (k == "sparse_tiles") s->sparse_tiles = (int)value;
+    else if (k == "sparse_threads") s->sparse_threads = (int)value;
     else throw MqcError("unknown option: " + k);
     if (s->tile_bits < 5 || s->tile_bits > MQC_MAX_TILE_BITS || s->grad_tile_bits < 5 || s->grad_tile_bits > MQC_MAX_TILE_BITS - 1)
         throw MqcError("tile_bits must be in [5,13], grad_tile_bits in [5,12]");
     if (s->low_bits < 0 || s->low_bits > 6) throw MqcError("low_bits must be in [0,6]");
     if (s->tile_threads < 32 || s->tile_threads > 512 || (s->tile_threads & (s->tile_threads - 1)))
         throw MqcError("tile_threads must be a power of two in [32,512]");
+    if (s->sparse_threads < 32 || s->sparse_threads > 256 || (s->sparse_threads & (s->sparse_threads - 1)))
+        throw MqcError("sparse_threads must be a power of two in [32,256]");
     MQC_CATCH
 }
 
@@ -464,6 +609,7 @@ int mqc_set_hamiltonian(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask,
     }
     s->have_ham = true;
     s->lay[0].ham_ready = s->lay[1].ham_ready = false;
+    s->lay[0].sham_ready = s->lay[1].sham_ready = false;
     MQC_CATCH
 }
 
@@ -555,7 +701,7 @@ int mqc_energy(mqc_solver_t* s, const double* theta, double* energy) {
     CK(cudaEventRecord(s->ev[0], s->stream));
     forward(s, 0, theta);
     CK(cudaEventRecord(s->ev[1], s->stream));
-    happly(s, 0, s->lay[0].ham, nullptr, val);
+    happly(s, 0, s->lay[0].ham, &s->lay[0].sham, nullptr, val);
     CK(cudaEventRecord(s->ev[2], s->stream));
     CK(cudaStreamSynchronize(s->stream));
     finish_timing(s, false);
@@ -576,7 +722,7 @@ int mqc_energy_grad(mqc_solver_t* s, const double* theta, double* energy, double
     CK(cudaEventRecord(s->ev[0], s->stream));
     forward(s, 1, theta);
     CK(cudaEventRecord(s->ev[1], s->stream));
-    happly(s, 1, s->lay[1].ham, s->lam.p, val);
+    happly(s, 1, s->lay[1].ham, &s->lay[1].sham, s->lam.p, val);
     CK(cudaEventRecord(s->ev[2], s->stream));
     reverse_sweep(s, 1);
     CK(cudaEventRecord(s->ev[3], s->stream));
@@ -624,10 +770,12 @@ int mqc_expectation(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask, con
     H.c.resize(n_terms);
     for (int64_t t = 0; t < n_terms; ++t) H.c[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
     HamTables T;
-    build_ham_tables(s, H, s->lay[w].phys, T);
-    if (s->conserving && s->use_sector) build_sector_tables(s, s->lay[w], s->na, s->nb);
+    SecHamTables ST;
+    const bool sec = s->conserving && s->use_sector;
+    if (sec) { build_sector_tables(s, s->lay[w], s->na, s->nb); build_sec_ham(s, H, s->lay[w].phys, ST); }
+    else build_ham_tables(s, H, s->lay[w].phys, T);
     double val[2] = {0, 0};
-    happly(s, w, T, nullptr, val);
+    happly(s, w, T, sec ? &ST : nullptr, nullptr, val);
     CK(cudaStreamSynchronize(s->stream));
     *value_re = val[0];
     if (value_im) *value_im = val[1];

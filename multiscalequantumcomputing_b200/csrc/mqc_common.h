@@ -43,8 +43,8 @@ struct MqcTileFactor {      // factor in tile-local coordinates (k <= 16 bits)
     u64 z_out;              // physical parity mask over the tile's fixed (inactive) bits
     uint16_t m, v, z;       // local masks
     uint8_t npos;
-    uint8_t pos[4];         // local positions of m, ascending
     uint8_t sign0;
+    uint8_t pos[4];         // local positions of m, ascending (4-byte aligned: read as one word)
     int32_t slot;
     int32_t theta;
 };

@@ -1,8 +1,9 @@
 // sm_100a kernels of the UCCSD state-vector path.  All HBM-bandwidth-bound complex128
 // streaming work: no tensor cores (nothing here is a dense contraction).
 //
-//   k_tile_sweep<ADJ>   K1/K3  fused excitation sweep over a 2^K shared-memory tile
+//   k_tile_sweep<ADJ>   K1/K3  fused excitation sweep over a dense 2^K shared-memory tile
 //                              (ADJ: psi and lambda together + per-factor gradient partials)
+//   k_tile_sparse<ADJ>  K1/K3  same sweep on the compressed (N_alpha, N_beta)-sector tile
 //   k_excite_direct     K1     one factor per HBM pass (unfused baseline / fallback)
 //   k_adjoint_direct    K3     one factor per pass on (psi, lambda) + gradient
 //   k_happly            K2     lambda = H psi and E = <psi|H|psi>, X-mask-grouped terms,
@@ -84,6 +85,249 @@ __global__ void k_gather_logical(const double2* __restrict__ psi, double2* __res
 //   uint16  prm_lo[128], prm_hi[128]  re-layout LUTs
 //   MqcTileFactor sf[nf]; double2 scs[nf]
 //   double  gpart[nwarps][nf]                                     (ADJ only)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+// Bank swizzle of the dense tile: a 16-byte element lives in bank group (index & 7).  Factors
+// move arbitrary tile bits, so a quarter-warp's eight lanes may differ in ANY three index bits;
+// the three low address bits are XORed with a GF(2)-linear image of the high bits whose
+// columns are successive powers of a primitive element of GF(8) (1,2,4,3,6,7,5,...): any
+// three consecutive bit positions - and most other triples - map to independent vectors,
+// i.e. eight distinct bank groups.  Linear, so swz(x ^ m) = swz(x) ^ swz(m).
+#define MQC_SWZ_M0 0x74E8u
+#define MQC_SWZ_M1 0x9D38u
+#define MQC_SWZ_M2 0x3A70u
+__device__ __forceinline__ uint32_t swz(uint32_t t) {
+    return t ^ ((uint32_t)__popc(t & MQC_SWZ_M0) & 1u) ^ (((uint32_t)__popc(t & MQC_SWZ_M1) & 1u) << 1) ^
+           (((uint32_t)__popc(t & MQC_SWZ_M2) & 1u) << 2);
+}
+__device__ __forceinline__ uint32_t ins0(uint32_t x, uint32_t p) {
+    return ((x >> p) << (p + 1)) | (x & ((1u << p) - 1u));
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 / K3, sector form : compressed tile
+// ------------------------------------------------------------------------------------------
+// When every ansatz factor conserves (N_alpha, N_beta), a tile with a_act alpha and b_act beta
+// active bits can only hold C(a_act, ka) * C(b_act, kb) non-zero amplitudes (ka, kb fixed by the
+// tile's inactive bits): <= 400 of 4096 for a 6+6-bit tile.  This kernel keeps only those in
+// shared memory (<= 6.4 KB per state instead of 64 KB), so ~10 CTAs per SM overlap their
+// per-factor latency chains instead of 3, touches only those amplitudes in HBM/L2 (the zeros
+// outside the sector are never read or written), and skips tiles that cannot hold any.
+//
+//   slist[e]  : slot -> tile-local index (ascending)         smap[t] : tile-local index -> slot
+// A factor scans the list; element xl is the lower partner iff (xl & m) == v; its partner
+// xl ^ m is in the same sector, slot = smap[xl ^ m].
+struct MqcSparse {
+    u64 amask, bmask;          // physical masks of the alpha / beta qubits
+    int na, nb;
+    int cap;                   // slots reserved per state (max elements of any tile of this pass)
+};
+
+#define MQC_FCHUNK 32
+
+template <bool ADJ>
+__global__ void __launch_bounds__(256)
+k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass P,
+              const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
+              double* __restrict__ grad, const int n_bits, const int reverse, const MqcSparse SP) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = P.k;
+    const uint32_t T = 1u << K;
+    const int nf = P.f1 - P.f0;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int h0 = K >> 1, h1 = K - h0;
+    const uint32_t lo_mask = (1u << h0) - 1u;
+    const int cap = SP.cap;
+
+    double2* sp = reinterpret_cast<double2*>(smem_raw);
+    double2* sl = sp + (ADJ ? cap : 0);
+    unsigned char* q = smem_raw + (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2);
+    u64* dep_lo = reinterpret_cast<u64*>(q);            q += 128 * sizeof(u64);
+    u64* dep_hi = reinterpret_cast<u64*>(q);            q += 128 * sizeof(u64);
+    double2* scs = reinterpret_cast<double2*>(q);       q += MQC_FCHUNK * sizeof(double2);
+    double* gpart = reinterpret_cast<double*>(q);       q += (ADJ ? 8 * MQC_FCHUNK : 0) * sizeof(double);
+    int* stheta = reinterpret_cast<int*>(q);            q += MQC_FCHUNK * sizeof(int);
+    uint32_t* smz = reinterpret_cast<uint32_t*>(q);     q += MQC_FCHUNK * sizeof(uint32_t);     // m | z << 16
+    uint32_t* svs = reinterpret_cast<uint32_t*>(q);     q += MQC_FCHUNK * sizeof(uint32_t);     // v | sign << 16
+    int* spos = reinterpret_cast<int*>(q);              q += 16 * sizeof(int);
+    int* sperm = reinterpret_cast<int*>(q);             q += 16 * sizeof(int);
+    int* scount = reinterpret_cast<int*>(q);            q += 4 * sizeof(int);
+    uint16_t* inv_lo = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);
+    uint16_t* inv_hi = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);
+    uint16_t* slist = reinterpret_cast<uint16_t*>(q);   q += (size_t)cap * sizeof(uint16_t);
+    uint16_t* smap = reinterpret_cast<uint16_t*>(q);
+
+    if (tid < 16) {
+        int pv = 0, qv = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (j == tid) { pv = P.pos[j]; qv = P.perm[j]; }
+        spos[tid] = pv; sperm[tid] = qv;
+        if (tid == 0) scount[0] = 0;
+    }
+    __syncthreads();
+    const u64 base = mqc_deposit_complement((u64)blockIdx.x, P.act_mask, n_bits);
+    uint32_t aloc = 0, bloc = 0;
+    for (int j = 0; j < K; ++j) {
+        aloc |= (uint32_t)((SP.amask >> spos[j]) & 1ull) << j;
+        bloc |= (uint32_t)((SP.bmask >> spos[j]) & 1ull) << j;
+    }
+    const int ka = SP.na - __popcll(base & SP.amask);
+    const int kb = SP.nb - __popcll(base & SP.bmask);
+    if (ka < 0 || kb < 0 || ka > __popc(aloc) || kb > __popc(bloc)) return;      // tile holds only zeros
+
+    // physical offset of a tile-local index, and the local index an element has in the OTHER
+    // layout of a re-layout pass: t' with bit j' = bit perm[j'] of t
+    for (int t = tid; t < (1 << h0); t += nthr) {
+        u64 d = 0;
+        for (int j = 0; j < h0; ++j) d |= (((u64)t >> j) & 1ull) << spos[j];
+        dep_lo[t] = d;
+    }
+    for (int t = tid; t < (1 << h1); t += nthr) {
+        u64 d = 0;
+        for (int j = 0; j < h1; ++j) d |= (((u64)t >> j) & 1ull) << spos[h0 + j];
+        dep_hi[t] = d;
+    }
+    // inverse permutation as two gathers: contribution of the low / high half of t to t'
+    for (int t = tid; t < (1 << h0); t += nthr) {
+        uint32_t o = 0;
+        for (int jp = 0; jp < K; ++jp) { const int src = sperm[jp]; if (src < h0) o |= (((uint32_t)t >> src) & 1u) << jp; }
+        inv_lo[t] = (uint16_t)o;
+    }
+    for (int t = tid; t < (1 << h1); t += nthr) {
+        uint32_t o = 0;
+        for (int jp = 0; jp < K; ++jp) { const int src = sperm[jp]; if (src >= h0) o |= (((uint32_t)t >> (src - h0)) & 1u) << jp; }
+        inv_hi[t] = (uint16_t)o;
+    }
+    // sector elements of this tile, ascending (block-wide ordered compaction)
+    {
+        __shared__ int wcount[8];
+        const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+        int running = 0;
+        for (uint32_t t0 = 0; t0 < T; t0 += nthr) {
+            const uint32_t t = t0 + tid;
+            const bool ok = (t < T) && (__popc(t & aloc) == ka) && (__popc(t & bloc) == kb);
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) wcount[warp] = __popc(bal);
+            __syncthreads();
+            int off = running, tot = 0;
+            for (int w = 0; w < nw; ++w) { const int c = wcount[w]; if (w < warp) off += c; tot += c; }
+            if (ok) {
+                const int o = off + __popc(bal & ((1u << lane) - 1u));
+                if (o < cap) { slist[o] = (uint16_t)t; smap[t] = (uint16_t)o; }
+            }
+            running += tot;
+            __syncthreads();
+        }
+        if (tid == 0) scount[0] = min(running, cap);
+    }
+    __syncthreads();
+    const int cnt = scount[0];
+
+    // ---- load -----------------------------------------------------------------------
+    const bool other_layout_load = reverse && P.has_perm;
+    const bool other_layout_store = (!reverse) && P.has_perm;
+    for (int e = tid; e < cnt; e += nthr) {
+        uint32_t t = slist[e];
+        if (other_layout_load) t = (uint32_t)(inv_lo[t & lo_mask] | inv_hi[t >> h0]);
+        const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
+        cp_async16(sp + e, psi + g);
+        if (ADJ) cp_async16(sl + e, lam + g);
+    }
+
+    // ---- factors, in chunks ---------------------------------------------------------
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nw = nthr >> 5;
+    for (int c0 = 0; c0 < nf; c0 += MQC_FCHUNK) {
+        const int nc = min(MQC_FCHUNK, nf - c0);
+        for (int fc = tid; fc < nc; fc += nthr) {
+            const int f = reverse ? (nf - 1 - (c0 + fc)) : (c0 + fc);
+            const MqcTileFactor* Fp = tf + P.f0 + f;
+            const double2 v = cs[Fp->slot];
+            scs[fc] = make_double2(v.x, reverse ? -v.y : v.y);
+            stheta[fc] = Fp->theta;
+            const uint32_t sg = ((uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
+            smz[fc] = (uint32_t)Fp->m | ((uint32_t)Fp->z << 16);
+            svs[fc] = (uint32_t)Fp->v | (sg << 16);
+        }
+        if (c0 == 0) cp_async_wait_all();
+        __syncthreads();
+        for (int fc = 0; fc < nc; ++fc) {
+            const uint32_t mz = smz[fc], vs = svs[fc];
+            const uint32_t fm = mz & 0xffffu, fz = mz >> 16, fv = vs & 0xffffu, sg = vs >> 16;
+            const double2 csv = scs[fc];
+            const double c = csv.x, sn = csv.y;
+            double gacc = 0.0;
+            for (int e = tid; e < cnt; e += nthr) {
+                const uint32_t xl = slist[e];
+                if ((xl & fm) != fv) continue;
+                const uint32_t e1 = smap[xl ^ fm];
+                const bool neg = (((uint32_t)__popc(xl & fz) + sg) & 1u) != 0u;
+                const double ssn = neg ? -sn : sn;
+                const double2 a = sp[e], b = sp[e1];
+                if (ADJ) {
+                    const double2 la = sl[e], lb = sl[e1];
+                    const double gv = lb.x * a.x + lb.y * a.y - la.x * b.x - la.y * b.y;
+                    gacc += neg ? -gv : gv;
+                    sl[e] = make_double2(c * la.x - ssn * lb.x, c * la.y - ssn * lb.y);
+                    sl[e1] = make_double2(c * lb.x + ssn * la.x, c * lb.y + ssn * la.y);
+                }
+                sp[e] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
+                sp[e1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
+            }
+            if (ADJ) {
+                gacc = warp_sum(gacc);
+                if (lane == 0) gpart[warp * MQC_FCHUNK + fc] = gacc;
+            }
+            __syncthreads();
+        }
+        if (ADJ) {
+            for (int fc = tid; fc < nc; fc += nthr) {
+                double g = 0.0;
+                for (int w = 0; w < nw; ++w) g += gpart[w * MQC_FCHUNK + fc];
+                if (g != 0.0) atomicAdd(grad + stheta[fc], 2.0 * g);
+            }
+            __syncthreads();
+        }
+    }
+    if (nf == 0) { cp_async_wait_all(); __syncthreads(); }
+
+    // ---- store ----------------------------------------------------------------------
+    for (int e = tid; e < cnt; e += nthr) {
+        uint32_t t = slist[e];
+        if (other_layout_store) t = (uint32_t)(inv_lo[t & lo_mask] | inv_hi[t >> h0]);
+        const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
+        psi[g] = sp[e];
+        if (ADJ) lam[g] = sl[e];
+    }
+}
+
+static inline size_t mqc_sparse_smem_bytes(int K, int cap, bool adj) {
+    size_t b = (size_t)(adj ? 2 : 1) * cap * sizeof(double2);
+    b += 2 * 128 * sizeof(u64);
+    b += MQC_FCHUNK * sizeof(double2);
+    if (adj) b += 8 * MQC_FCHUNK * sizeof(double);
+    b += MQC_FCHUNK * sizeof(int) + 2 * MQC_FCHUNK * sizeof(uint32_t);
+    b += 32 * sizeof(int) + 4 * sizeof(int);
+    b += 2 * 128 * sizeof(uint16_t);
+    b += (size_t)cap * sizeof(uint16_t);
+    b += ((size_t)1 << K) * sizeof(uint16_t);
+    return b;
+}
+
+// Per-factor pair addressing.  For a factor with flip mask m the lower partner of pair u is
+//   xl(u) = ins(u) | v      (u with zero bits inserted at the positions of m)
+// and both ins() and the bank swizzle are GF(2)-linear, as is the parity popc(xl & z).  So
+//   [ swz(xl(u)) | sign(u) << 15 ] = A[u & 31] ^ B[(u >> 5) & 7] ^ C[u >> 8]
+// with three tiny tables per factor (48 x u16) that fold in v and the per-tile sign.  They are
+// rebuilt per chunk of MQC_FCHUNK factors, which costs ~6 instructions per factor and thread
+// and replaces ~100 instructions of per-pair bit arithmetic.
+#define MQC_LUT_PER_FACTOR 48
+
 template <bool ADJ>
 __global__ void __launch_bounds__(512)
 k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass P,
@@ -102,94 +346,158 @@ k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass
     unsigned char* q = smem_raw + (size_t)(ADJ ? 2 : 1) * T * sizeof(double2);
     u64* dep_lo = reinterpret_cast<u64*>(q);            q += 128 * sizeof(u64);
     u64* dep_hi = reinterpret_cast<u64*>(q);            q += 128 * sizeof(u64);
+    double2* scs = reinterpret_cast<double2*>(q);       q += MQC_FCHUNK * sizeof(double2);
+    double* gpart = reinterpret_cast<double*>(q);       q += (ADJ ? 16 * MQC_FCHUNK : 0) * sizeof(double);
+    int* stheta = reinterpret_cast<int*>(q);            q += MQC_FCHUNK * sizeof(int);
+    uint16_t* slut = reinterpret_cast<uint16_t*>(q);    q += MQC_FCHUNK * MQC_LUT_PER_FACTOR * sizeof(uint16_t);
+    uint16_t* sswm = reinterpret_cast<uint16_t*>(q);    q += MQC_FCHUNK * sizeof(uint16_t);
+    uint16_t* slg = reinterpret_cast<uint16_t*>(q);     q += MQC_FCHUNK * sizeof(uint16_t);
     uint16_t* prm_lo = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);
     uint16_t* prm_hi = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);
-    MqcTileFactor* sf = reinterpret_cast<MqcTileFactor*>(q);  q += (size_t)nf * sizeof(MqcTileFactor);
-    double2* scs = reinterpret_cast<double2*>(q);       q += (size_t)nf * sizeof(double2);
-    double* gpart = reinterpret_cast<double*>(q);
+    int* spos = reinterpret_cast<int*>(q);              q += 16 * sizeof(int);
+    int* sperm = reinterpret_cast<int*>(q);             q += 16 * sizeof(int);
 
     // ---- per-CTA tables -------------------------------------------------------------
+    if (tid < 16) {                      // static indices only: no local-memory copy of P
+        int pv = 0, qv = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (j == tid) { pv = P.pos[j]; qv = P.perm[j]; }
+        spos[tid] = pv; sperm[tid] = qv;
+    }
+    __syncthreads();
     for (int t = tid; t < (1 << h0); t += nthr) {
-        dep_lo[t] = mqc_deposit((u64)t, P.pos, h0);
-        prm_lo[t] = (uint16_t)mqc_permute_bits((uint32_t)t, P.perm, h0);
+        u64 d = 0; uint32_t pm = 0;
+        for (int j = 0; j < h0; ++j) { const u64 b = ((u64)t >> j) & 1ull; d |= b << spos[j]; pm |= (uint32_t)b << sperm[j]; }
+        dep_lo[t] = d; prm_lo[t] = (uint16_t)pm;
     }
     for (int t = tid; t < (1 << h1); t += nthr) {
-        dep_hi[t] = mqc_deposit((u64)t, P.pos + h0, h1);
-        prm_hi[t] = (uint16_t)mqc_permute_bits((uint32_t)t, P.perm + h0, h1);
-    }
-    for (int f = tid; f < nf; f += nthr) {
-        const MqcTileFactor F = tf[P.f0 + f];
-        sf[f] = F;
-        scs[f] = cs[F.slot];
+        u64 d = 0; uint32_t pm = 0;
+        for (int j = 0; j < h1; ++j) { const u64 b = ((u64)t >> j) & 1ull; d |= b << spos[h0 + j]; pm |= (uint32_t)b << sperm[h0 + j]; }
+        dep_hi[t] = d; prm_hi[t] = (uint16_t)pm;
     }
     const u64 base = mqc_deposit_complement((u64)blockIdx.x, P.act_mask, n_bits);
     __syncthreads();
 
-    // ---- load -----------------------------------------------------------------------
+    // ---- load (cp.async: whole tile in flight, no register staging) -------------------
     const bool perm_load = reverse && P.has_perm;
     const bool perm_store = (!reverse) && P.has_perm;
     for (uint32_t t = tid; t < T; t += nthr) {
         const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
         const uint32_t st = perm_load ? (uint32_t)(prm_lo[t & lo_mask] | prm_hi[t >> h0]) : t;
-        sp[st] = ld_stream(psi + g);
-        if (ADJ) sl[st] = ld_stream(lam + g);
+        const uint32_t sw = swz(st);
+        cp_async16(sp + sw, psi + g);
+        if (ADJ) cp_async16(sl + sw, lam + g);
     }
-    __syncthreads();
 
-    // ---- factors --------------------------------------------------------------------
+    // ---- factors, in chunks ---------------------------------------------------------
     const int warp = tid >> 5, lane = tid & 31;
-    for (int fi = 0; fi < nf; ++fi) {
-        const int f = reverse ? (nf - 1 - fi) : fi;
-        const MqcTileFactor F = sf[f];
-        const double c = scs[f].x;
-        const double sn = reverse ? -scs[f].y : scs[f].y;
-        const int sgn_tile = (__popcll(base & F.z_out) + F.sign0) & 1;
-        const uint32_t npairs = T >> F.npos;
-        double gacc = 0.0;
-        for (uint32_t u = tid; u < npairs; u += nthr) {
-            const uint32_t x0 = mqc_insert_zeros8(u, F.pos, F.npos) | F.v;
-            const uint32_t x1 = x0 ^ F.m;
-            const double s = ((__popc(x0 & F.z) + sgn_tile) & 1) ? -1.0 : 1.0;
-            const double ssn = s * sn;
-            const double2 a = sp[x0], b = sp[x1];
-            if (ADJ) {
-                const double2 la = sl[x0], lb = sl[x1];
-                gacc += s * (lb.x * a.x + lb.y * a.y - la.x * b.x - la.y * b.y);
-                sl[x0] = make_double2(c * la.x - ssn * lb.x, c * la.y - ssn * lb.y);
-                sl[x1] = make_double2(c * lb.x + ssn * la.x, c * lb.y + ssn * la.y);
+    const int nw = nthr >> 5;
+    for (int c0 = 0; c0 < nf; c0 += MQC_FCHUNK) {
+        const int nc = min(MQC_FCHUNK, nf - c0);
+        // chunk tables: entry e of factor fc;  e < 32: A, 32..39: B, 40..47: C
+        for (int w = tid; w < nc * MQC_LUT_PER_FACTOR; w += nthr) {
+            const int fc = w / MQC_LUT_PER_FACTOR, e = w - fc * MQC_LUT_PER_FACTOR;
+            const int f = reverse ? (nf - 1 - (c0 + fc)) : (c0 + fc);
+            const MqcTileFactor* Fp = tf + P.f0 + f;
+            const uint32_t npos = Fp->npos;
+            const uint32_t pos4 = *reinterpret_cast<const uint32_t*>(Fp->pos);
+            const uint32_t up = (e < 32) ? (uint32_t)e : (e < 40 ? (uint32_t)(e - 32) << 5 : (uint32_t)(e - 40) << 8);
+            uint32_t xl = ins0(ins0(up, pos4 & 0xffu), (pos4 >> 8) & 0xffu);
+            if (npos == 4) xl = ins0(ins0(xl, (pos4 >> 16) & 0xffu), pos4 >> 24);
+            const uint32_t fz = Fp->z;
+            uint32_t val = 0;
+            if (xl < T) val = swz(xl) | (((uint32_t)__popc(xl & fz) & 1u) << 15);
+            if (e < 32) {                                       // v and the per-tile sign ride on table A
+                const uint32_t fv = Fp->v;
+                const uint32_t sg = ((uint32_t)__popc(fv & fz) + (uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
+                val ^= swz(fv) | (sg << 15);
             }
-            sp[x0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
-            sp[x1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
+            slut[w] = (uint16_t)val;
+        }
+        for (int fc = tid; fc < nc; fc += nthr) {
+            const int f = reverse ? (nf - 1 - (c0 + fc)) : (c0 + fc);
+            const MqcTileFactor* Fp = tf + P.f0 + f;
+            const double2 v = cs[Fp->slot];
+            scs[fc] = make_double2(v.x, reverse ? -v.y : v.y);
+            sswm[fc] = (uint16_t)swz(Fp->m);
+            slg[fc] = (uint16_t)(K - Fp->npos);
+            stheta[fc] = Fp->theta;
+        }
+        if (c0 == 0) cp_async_wait_all();
+        __syncthreads();
+
+        for (int fc = 0; fc < nc; ++fc) {
+            const uint16_t* lut = slut + fc * MQC_LUT_PER_FACTOR;
+            const uint32_t swm = sswm[fc];
+            const uint32_t npairs = 1u << slg[fc];
+            const double2 csv = scs[fc];
+            const double c = csv.x, sn = csv.y;
+            double gacc = 0.0;
+            for (uint32_t u = tid; u < npairs; u += nthr) {
+                const uint32_t val = (uint32_t)lut[u & 31u] ^ (uint32_t)lut[32u + ((u >> 5) & 7u)] ^ (uint32_t)lut[40u + (u >> 8)];
+                const uint32_t x0 = val & 0x7fffu;
+                const uint32_t x1 = x0 ^ swm;
+                const bool neg = (val & 0x8000u) != 0u;
+                const double2 a = sp[x0], b = sp[x1];
+                if (ADJ) {
+                    const double2 la = sl[x0], lb = sl[x1];
+                    const bool nz = (a.x != 0.0) | (a.y != 0.0) | (b.x != 0.0) | (b.y != 0.0) |
+                                    (la.x != 0.0) | (la.y != 0.0) | (lb.x != 0.0) | (lb.y != 0.0);
+                    if (nz) {
+                        const double ssn = neg ? -sn : sn;
+                        const double gv = lb.x * a.x + lb.y * a.y - la.x * b.x - la.y * b.y;
+                        gacc += neg ? -gv : gv;
+                        sl[x0] = make_double2(c * la.x - ssn * lb.x, c * la.y - ssn * lb.y);
+                        sl[x1] = make_double2(c * lb.x + ssn * la.x, c * lb.y + ssn * la.y);
+                        sp[x0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
+                        sp[x1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
+                    }
+                } else {
+                    const bool nz = (a.x != 0.0) | (a.y != 0.0) | (b.x != 0.0) | (b.y != 0.0);
+                    if (nz) {
+                        const double ssn = neg ? -sn : sn;
+                        sp[x0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
+                        sp[x1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
+                    }
+                }
+            }
+            if (ADJ) {
+                gacc = warp_sum(gacc);
+                if (lane == 0) gpart[warp * MQC_FCHUNK + fc] = gacc;
+            }
+            __syncthreads();
         }
         if (ADJ) {
-            gacc = warp_sum(gacc);
-            if (lane == 0) gpart[warp * nf + f] = gacc;
-        }
-        __syncthreads();
-    }
-    if (ADJ) {
-        const int nw = nthr >> 5;
-        for (int f = tid; f < nf; f += nthr) {
-            double g = 0.0;
-            for (int w = 0; w < nw; ++w) g += gpart[w * nf + f];
-            if (g != 0.0) atomicAdd(grad + sf[f].theta, 2.0 * g);
+            for (int fc = tid; fc < nc; fc += nthr) {
+                double g = 0.0;
+                for (int w = 0; w < nw; ++w) g += gpart[w * MQC_FCHUNK + fc];
+                if (g != 0.0) atomicAdd(grad + stheta[fc], 2.0 * g);
+            }
+            __syncthreads();
         }
     }
+    if (nf == 0) { cp_async_wait_all(); __syncthreads(); }
 
     // ---- store ----------------------------------------------------------------------
     for (uint32_t t = tid; t < T; t += nthr) {
         const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
         const uint32_t st = perm_store ? (uint32_t)(prm_lo[t & lo_mask] | prm_hi[t >> h0]) : t;
-        st_stream(psi + g, sp[st]);
-        if (ADJ) st_stream(lam + g, sl[st]);
+        const uint32_t sw = swz(st);
+        st_stream(psi + g, sp[sw]);
+        if (ADJ) st_stream(lam + g, sl[sw]);
     }
 }
 
 static inline size_t mqc_tile_smem_bytes(int K, int nf, bool adj, int nthreads) {
+    (void)nf; (void)nthreads;
     size_t b = (size_t)(adj ? 2 : 1) * ((size_t)1 << K) * sizeof(double2);
-    b += 2 * 128 * sizeof(u64) + 2 * 128 * sizeof(uint16_t);
-    b += (size_t)nf * (sizeof(MqcTileFactor) + sizeof(double2));
-    if (adj) b += (size_t)(nthreads / 32) * nf * sizeof(double);
+    b += 2 * 128 * sizeof(u64);
+    b += MQC_FCHUNK * sizeof(double2);
+    if (adj) b += 16 * MQC_FCHUNK * sizeof(double);
+    b += MQC_FCHUNK * sizeof(int);
+    b += MQC_FCHUNK * MQC_LUT_PER_FACTOR * sizeof(uint16_t);
+    b += 2 * MQC_FCHUNK * sizeof(uint16_t);
+    b += 2 * 128 * sizeof(uint16_t) + 32 * sizeof(int);
     return b;
 }
 
@@ -283,6 +591,141 @@ k_happly(const double2* __restrict__ psi, double2* __restrict__ lam, const MqcHa
         const double2 py = psi[y];
         er = py.x * ar + py.y * ai;       // conj(psi[y]) * acc
         ei = py.x * ai - py.y * ar;
+    }
+    er = warp_sum(er);
+    ei = warp_sum(ei);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = er; red[1][warp] = ei; }
+    __syncthreads();
+    if (warp == 0) {
+        double vr = (lane < (blockDim.x >> 5)) ? red[0][lane] : 0.0;
+        double vi = (lane < (blockDim.x >> 5)) ? red[1][lane] : 0.0;
+        vr = warp_sum(vr);
+        vi = warp_sum(vi);
+        if (lane == 0) {
+            if (vr != 0.0) atomicAdd(e_out, vr);
+            if (vi != 0.0) atomicAdd(e_out + 1, vi);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 (sector form): C = psi restricted to alpha-string x beta-string, Lambda = H C
+// ------------------------------------------------------------------------------------------
+// The UCCSD state only populates one (N_alpha, N_beta) sector.  It is gathered into a dense
+// matrix C[ia][ib]; X-mask groups are sorted by their alpha part so that a CTA, which owns one
+// output alpha string, tests alpha validity once per distinct alpha mask (uniform branch) and
+// reads whole rows of C; threads own output beta strings.
+struct MqcSecHamDev {
+    int n_ma;                  // distinct alpha x-masks (orbital space)
+    const unsigned* ma_list;   // [n_ma]
+    const int* ma_goff;        // [n_ma+1] group range per alpha mask
+    const unsigned* gmb;       // [G] beta x-mask (orbital space)
+    const int* goff;           // [G+1] term range per group
+    const u64* tz;             // [T] physical z-mask
+    const double2* tc;         // [T]
+    const unsigned* aorb;      // [nA] alpha strings, orbital space
+    const unsigned* borb;      // [nB]
+    const u64* astr;           // [nA] physical images
+    const u64* bstr;           // [nB]
+    const unsigned* rank_a;    // [2^n_orb] string -> index (0xffffffff: not in sector)
+    const unsigned* rank_b;
+    unsigned n_a, n_b;
+};
+
+__global__ void k_sector_gather(const double2* __restrict__ psi, double2* __restrict__ C,
+                                const u64* __restrict__ astr, const u64* __restrict__ bstr,
+                                const unsigned n_a, const unsigned n_b) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (u64)n_a * n_b) return;
+    const unsigned ia = (unsigned)(tid / n_b), ib = (unsigned)(tid - (u64)ia * n_b);
+    C[tid] = psi[astr[ia] | bstr[ib]];
+}
+
+__global__ void k_sector_scatter(double2* __restrict__ lam, const double2* __restrict__ L,
+                                 const u64* __restrict__ astr, const u64* __restrict__ bstr,
+                                 const unsigned n_a, const unsigned n_b) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (u64)n_a * n_b) return;
+    const unsigned ia = (unsigned)(tid / n_b), ib = (unsigned)(tid - (u64)ia * n_b);
+    lam[astr[ia] | bstr[ib]] = L[tid];
+}
+
+#define MQC_HS_R 4
+__global__ void __launch_bounds__(256)
+k_happly_sector(const double2* __restrict__ C, double2* __restrict__ L, const MqcSecHamDev H,
+                double* __restrict__ e_out) {
+    __shared__ double red[2][8];
+    const unsigned iap = blockIdx.x;
+    const unsigned ap = H.aorb[iap];
+    unsigned bp[MQC_HS_R];
+    unsigned ibp[MQC_HS_R];
+    double ar[MQC_HS_R], ai[MQC_HS_R];
+#pragma unroll
+    for (int r = 0; r < MQC_HS_R; ++r) {
+        ibp[r] = (blockIdx.y * MQC_HS_R + r) * blockDim.x + threadIdx.x;
+        bp[r] = (ibp[r] < H.n_b) ? H.borb[ibp[r]] : 0xffffffffu;
+        ar[r] = 0.0; ai[r] = 0.0;
+    }
+    for (int im = 0; im < H.n_ma; ++im) {
+        const unsigned ma = __ldg(H.ma_list + im);
+        if (2 * __popc(ap & ma) != __popc(ma)) continue;          // uniform over the CTA
+        const unsigned ia = __ldg(H.rank_a + (ap ^ ma));
+        const u64 xa = __ldg(H.astr + ia);
+        const double2* __restrict__ Crow = C + (size_t)ia * H.n_b;
+        const int g0 = __ldg(H.ma_goff + im), g1 = __ldg(H.ma_goff + im + 1);
+        for (int g = g0; g < g1; ++g) {
+            const unsigned mb = __ldg(H.gmb + g);
+            const int pmb = __popc(mb);
+            u64 x[MQC_HS_R];
+            double2 amp[MQC_HS_R];
+            double cr[MQC_HS_R], ci[MQC_HS_R];
+            bool ok[MQC_HS_R];
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < MQC_HS_R; ++r) {
+                ok[r] = (bp[r] != 0xffffffffu) && (2 * __popc(bp[r] & mb) == pmb);
+                cr[r] = 0.0; ci[r] = 0.0;
+                if (ok[r]) {
+                    const unsigned ib = __ldg(H.rank_b + (bp[r] ^ mb));
+                    amp[r] = Crow[ib];
+                    x[r] = xa | __ldg(H.bstr + ib);
+                    ok[r] = (amp[r].x != 0.0) || (amp[r].y != 0.0);
+                }
+                any |= ok[r];
+            }
+            if (!any) continue;
+            const int t0 = __ldg(H.goff + g), t1 = __ldg(H.goff + g + 1);
+            for (int t = t0; t < t1; ++t) {
+                const u64 z = __ldg(H.tz + t);
+                const double2 cc = __ldg(H.tc + t);
+#pragma unroll
+                for (int r = 0; r < MQC_HS_R; ++r) {
+                    if (ok[r]) {
+                        if (__popcll(x[r] & z) & 1) { cr[r] -= cc.x; ci[r] -= cc.y; }
+                        else { cr[r] += cc.x; ci[r] += cc.y; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < MQC_HS_R; ++r) {
+                if (ok[r]) {
+                    ar[r] += cr[r] * amp[r].x - ci[r] * amp[r].y;
+                    ai[r] += cr[r] * amp[r].y + ci[r] * amp[r].x;
+                }
+            }
+        }
+    }
+    double er = 0.0, ei = 0.0;
+#pragma unroll
+    for (int r = 0; r < MQC_HS_R; ++r) {
+        if (ibp[r] < H.n_b) {
+            const size_t o = (size_t)iap * H.n_b + ibp[r];
+            if (L) L[o] = make_double2(ar[r], ai[r]);
+            const double2 py = C[o];
+            er += py.x * ar[r] + py.y * ai[r];
+            ei += py.x * ai[r] - py.y * ar[r];
+        }
     }
     er = warp_sum(er);
     ei = warp_sum(ei);

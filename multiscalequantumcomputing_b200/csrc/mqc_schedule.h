@@ -23,6 +23,7 @@ struct MqcSchedule {
     int n_bits = 0, k = 0, low = 0;
     std::vector<MqcPass> passes;
     std::vector<MqcTileFactor> tf;
+    std::vector<std::vector<int>> pass_phys_before, pass_phys_after;   // layout around each pass
     std::vector<int> phys_init;    // logical bit -> physical position before the first pass
     std::vector<int> phys_final;   // logical bit -> physical position after the last pass
 };
@@ -91,6 +92,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
         MqcPass P{};
         P.k = K;
         P.f0 = (int)S.tf.size();
+        S.pass_phys_before.push_back(phys);
         std::vector<int> pos;                       // physical positions of A, ascending
         for (int p = 0; p < N; ++p) if ((A >> inv[p]) & 1ull) pos.push_back(p);
         u64 act = 0;
@@ -160,6 +162,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
             }
         }
         S.passes.push_back(P);
+        S.pass_phys_after.push_back(phys);
         i = j;
     }
     S.phys_final = phys;

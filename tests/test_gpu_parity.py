@@ -68,6 +68,17 @@ def test_state_energy_gradient(n, ne, order, opts):
     h.close()
 
 
+def test_gradient_at_zero_angles():
+    """theta = 0 is where every optimisation starts: sin = 0 must not lose the JW sign."""
+    h, orc, F, tab, th = _setup(6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 8})
+    z = np.zeros(F.n_theta)
+    e_ref, g_ref = orc.energy_grad(z)
+    e, g = h.energy_grad(z)
+    assert abs(e - e_ref) < E_TOL and abs(g - g_ref).max() < G_TOL
+    assert np.abs(g_ref).max() > 1e-3
+    h.close()
+
+
 @pytest.mark.parametrize("n,ne", [(4, 4), (5, 4), (6, 6)])
 def test_rdm12(n, ne):
     h, orc, F, tab, th = _setup(n, ne, "blocked", {"tile_bits": 9, "grad_tile_bits": 8})
