@@ -217,8 +217,8 @@ static void require_gpu(mqc_solver* s) {
     for (auto& e2 : s->ev) CK(cudaEventCreate(&e2));
     CK(cudaFuncSetAttribute(k_tile_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_tile_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_tile_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_tile_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_tile_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     s->gpu_ready = true;
 }
 
@@ -416,7 +416,7 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
         int nthr = s->sparse_threads;
         while (nthr > 32 && nthr / 2 >= SP.cap) nthr >>= 1;
         const size_t smem = mqc_sparse_smem_bytes(P.k, SP.cap, adj);
-        if (smem <= 232448) {
+        if (smem <= 200000) {
             if (adj) k_tile_sparse<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n, reverse, SP);
             else k_tile_sparse<false><<<grid, nthr, smem, s->stream>>>(s->psi.p, nullptr, P, s->tf[which].p, s->cs.p, nullptr, s->n, reverse, SP);
             s->counters[0]++;

@@ -297,6 +297,19 @@ k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPas
     if (nf == 0) { cp_async_wait_all(); __syncthreads(); }
 
     // ---- store ----------------------------------------------------------------------
+    // A re-layout pass moves the sector elements to other addresses of the same tile: clear
+    // the addresses they were loaded from first, so that everything outside the sector stays
+    // exactly zero in HBM (the dense kernels and mqc_state read it).
+    if (P.has_perm) {
+        for (int e = tid; e < cnt; e += nthr) {
+            uint32_t t = slist[e];
+            if (other_layout_load) t = (uint32_t)(inv_lo[t & lo_mask] | inv_hi[t >> h0]);
+            const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
+            psi[g] = make_double2(0.0, 0.0);
+            if (ADJ) lam[g] = make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+    }
     for (int e = tid; e < cnt; e += nthr) {
         uint32_t t = slist[e];
         if (other_layout_store) t = (uint32_t)(inv_lo[t & lo_mask] | inv_hi[t >> h0]);
