@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the UCCSD fragment-solver hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository (CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+
+One "step" = one energy + adjoint-gradient evaluation of a 24-qubit JW-UCCSD state vector
+(BASELINE.json configs[2]: 12 orbitals, 12 electrons, 1 818 parameters) on a synthetic
+H12-chain / STO-3G Hamiltonian.  With N > 1 ranks every rank evaluates its own fragment
+(fragment-parallel DMET mode, SURVEY.md §8e: independent units, no data-path collective):
+weak scaling, value = total evaluations / s.
+
+value   : evaluations/s with Hamiltonian, ansatz and parameters resident in HBM, timed with
+          CUDA events on the solver's stream, max over ranks.
+e2e     : the same through the public API with HOST buffers (pinned): parameters host->device
+          and (energy, gradient) device->host inside the timed region, every step.
+roofline: dominant kernel of the step (see DESIGN.md §5 for the byte accounting).
+cpu_baseline: oracle/c (a C/OpenMP port of the same path; the reference itself cannot run
+          here) on a bounded sample, scaled to one evaluation.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ORB = 12
+N_ELEC = 12
+BOND = 1.0
+THETA_SEED = 4321
+THETA_SIGMA = 0.05
+
+
+def workload():
+    from multiscalequantumcomputing_b200.jw import fragment_term_table, number_of_x_groups
+    from multiscalequantumcomputing_b200.synth.hydrogen import hydrogen_chain, mo_integrals
+    from multiscalequantumcomputing_b200.uccsd import uccsd_factors
+    h_mo, eri_mo, e_nuc, e_rhf = mo_integrals(hydrogen_chain(N_ORB, BOND), N_ELEC)
+    table = fragment_term_table(h_mo, eri_mo, 0, 0.0, 0.25)
+    factors = uccsd_factors(N_ORB, N_ELEC, "blocked")
+    theta = np.random.default_rng(THETA_SEED).normal(0.0, THETA_SIGMA, factors.n_theta)
+    return table, factors, theta, number_of_x_groups(table[0])
+
+
+CONFIG = {"workload": "uccsd_statevector_24q_H12chain_sto3g_energy+adjoint_gradient",
+          "n_qubits": 2 * N_ORB, "n_orb": N_ORB, "n_elec": N_ELEC, "bond_angstrom": BOND,
+          "ansatz": "JW-UCCSD, blocked order", "fragments_per_gpu": 1,
+          "l2_policy": "state (268 MB) and its adjoint are larger than L2 (126 MB); no flush needed"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [v.strip() for v in s.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+_CPU_REF = None
+_SEC = None
+
+
+def cpu_sample(table, factors, theta, n_fac=32, n_terms=1500):
+    global _CPU_REF, _SEC
+    from oracle.cref import CRefUCCSD, num_threads
+    if _CPU_REF is None:
+        _CPU_REF = CRefUCCSD(factors.n_qubits, factors.kind, factors.idx, factors.theta_index, factors.n_theta,
+                             factors.ref_index, table)
+    ref = _CPU_REF
+    if _SEC is None:
+        from oracle.fci import sector_indices
+        _SEC = sector_indices(N_ORB, N_ELEC)[1]
+    sec = _SEC
+    tf, th, tr, nf, nt = ref.time_sample(theta, n_fac, n_terms, sector_index=sec)
+    n_all, t_all = len(factors), len(table[0])
+    t_eval = tf / nf * n_all + th / nt * t_all + tr / nf * n_all
+    sample = ("forward over %d of %d factors (%.2fs), H apply over %d of %d Pauli terms (%.2fs), adjoint reverse "
+              "over %d factors (%.2fs); scaled linearly to one full evaluation = %.1fs" %
+              (nf, n_all, tf, nt, t_all, th, nf, tr, t_eval))
+    return 1.0 / t_eval, num_threads(), sample
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    table, factors, theta, n_groups = workload()
+    vals = []
+    info = None
+    for it in range(args.warmup + args.steps):
+        v, cores, sample = cpu_sample(table, factors, theta, n_fac=16, n_terms=600)
+        if it >= args.warmup:
+            vals.append(v)
+            info = (cores, sample)
+    value = float(np.mean(vals))
+    out = {"impl": "reference", "metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)",
+           "data": "synthetic", "config": dict(CONFIG),
+           "cpu_baseline": {"value": value, "unit": "evals/s", "cores": info[0], "kind": "port", "sample": info[1]},
+           "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "the reference's own path (OpenFermion/SciPy 2^N x 2^N sparse operators) cannot be built or run "
+                   "here and is infeasible at 24 qubits (SURVEY.md §5); this arm times oracle/c, a matrix-free "
+                   "C/OpenMP port of the same mathematics, on a bounded sample per step"}
+    print(json.dumps(out))
+
+
+def run_ours(args):
+    import torch
+    from multiscalequantumcomputing_b200 import _lib
+    rank, world, local = dist_env()
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    table, factors, theta, n_groups = workload()
+    t0 = time.perf_counter()
+    h = _lib.Handle(factors.n_qubits, local)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        h.set_option(k, int(v))
+    h.set_hamiltonian(*table)
+    h.set_ansatz(factors.kind, factors.idx, factors.theta_index, factors.n_theta, factors.ref_index)
+    setup_s = time.perf_counter() - t0
+
+    theta_pin = torch.from_numpy(theta.copy()).pin_memory()
+    grad_pin = torch.empty(factors.n_theta, dtype=torch.float64).pin_memory()
+    th_np, g_np = theta_pin.numpy(), grad_pin.numpy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also makes the parameters resident) ----------------------------------
+    e = None
+    for _ in range(max(args.warmup, 1)):
+        e = h.energy_grad_into(th_np, g_np)
+    e_ref, g_ref = e, g_np.copy()
+
+    # ---- value: inputs resident, CUDA events on the solver's stream ---------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    phase = np.zeros(3)
+    launches = 0
+    h.event_record(0)
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        e = h.energy_grad_resident()
+        t = h.last_timing()
+        phase += (t["forward_ms"], t["hamiltonian_ms"], t["reverse_ms"])
+        launches += t["launches"]
+    h.event_record(1)
+    dev_ms = h.event_elapsed_ms()
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    assert abs(e - e_ref) < 1e-9, "resident evaluation drifted"
+    tim = h.last_timing()
+
+    # ---- e2e: host buffers through the public call --------------------------------------
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2 = h.energy_grad_into(th_np, g_np)
+    barrier()
+    e2e_ms = (time.perf_counter() - w0) * 1e3
+    assert abs(e2 - e_ref) < 1e-9 and np.abs(g_np - g_ref).max() < 1e-9
+
+    if use_dist:
+        tt = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, wall_ms = (float(v) for v in tt.cpu())
+    ms_step = dev_ms / args.steps
+    value = world * 1e3 / ms_step
+    e2e_val = world * 1e3 / (e2e_ms / args.steps)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        S = 16.0 * (1 << factors.n_qubits)
+        from math import comb
+        n_det = comb(N_ORB, N_ELEC // 2) ** 2
+        sector_bytes = 16.0 * n_det
+        phase /= args.steps
+        names = ("k_tile_sparse<false> (forward sweep)", "k_happly_sector (H|psi>)", "k_tile_sparse<true> (adjoint reverse sweep)")
+        sparse = tim["forward_passes"] > 0 and "sparse_tiles=0" not in args.opt and "sector=0" not in args.opt
+        if not sparse:
+            names = ("k_tile_sweep<false> (forward sweep)", "k_happly (H|psi>)", "k_tile_sweep<true> (adjoint reverse sweep)")
+        # algorithmic bytes per LAUNCH of each kernel
+        if sparse:
+            per_launch = (2 * sector_bytes, 2 * sector_bytes, 4 * sector_bytes)
+        else:
+            per_launch = (2 * S, 2 * sector_bytes, 4 * S)
+        n_launch = (tim["forward_passes"], 1, tim["reverse_passes"])
+        dom = int(np.argmax(phase))
+        avg_ms = phase[dom] / n_launch[dom]
+        achieved = per_launch[dom] / (avg_ms * 1e-3) / 1e9
+        roof = {"kernel": names[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_launch[dom], "avg_launch_ms": avg_ms,
+                "launches_per_step": n_launch[dom], "share_of_step": float(phase[dom] / phase.sum()),
+                "phase_ms": {"forward": phase[0], "hamiltonian": phase[1], "reverse": phase[2]},
+                "unfused_equivalent": {
+                    "B_alg_bytes": S * (6 * len(factors) + 2), "note": "SURVEY.md §8d: one HBM pass per factor",
+                    "effective_GBps": S * (6 * len(factors) + 2) / (ms_step * 1e-3) / 1e9}}
+        cpu = None
+        try:
+            v, cores, sample = cpu_sample(table, factors, theta)
+            cpu = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample}
+        except Exception as exc:  # the checker could not be built on this box
+            cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % exc}
+        out = {"metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
+               "config": dict(CONFIG, n_theta=factors.n_theta, n_factors=len(factors), n_pauli_terms=len(table[0]),
+                              n_x_groups=n_groups, passes_per_sweep=tim["forward_passes"],
+                              parallelism="fragment-parallel x%d" % world, options=args.opt),
+               "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(theta_pin.numel() * 8),
+                       "d2h_bytes_per_step": int(grad_pin.numel() * 8 + 16), "ms_per_step": e2e_ms / args.steps},
+               "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
+               "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "energy": e_ref, "setup_s": setup_s}
+        print(json.dumps(out))
+    h.close()
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. sparse_tiles=0)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,8 +44,10 @@ int mqc_create(int n_qubits, int device, mqc_solver_t** out);
 int mqc_destroy(mqc_solver_t* s);
 
 /* Options (before mqc_set_ansatz): "tile_bits" (default 12), "low_bits" (3),
- * "grad_tile_bits" (11), "mode" (1 = fused tile sweep, 0 = one factor per pass),
- * "sector" (1 = exploit particle-number/S_z conservation of the ansatz in H|psi>). */
+ * "grad_tile_bits" (12), "mode" (1 = fused tile sweep, 0 = one factor per pass),
+ * "sector" (1 = exploit particle-number/S_z conservation of the ansatz in H|psi>),
+ * "sparse_tiles" (1 = compressed-sector tiles when the ansatz conserves N_alpha, N_beta),
+ * "tile_threads" (256), "sparse_threads" (128). */
 int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value);
 
 /* Replaces: `mapping(fermi_ham,'JW',...)` + `get_sparse_operator(qubit_ham)`,
@@ -65,6 +67,15 @@ int mqc_energy(mqc_solver_t* s, const double* theta, double* energy);
 /* Replaces: `ansatz.energy` + `ansatz.gradient` (jac=), mqc/solver/dmet_interface.py:295.
  * Adjoint method: forward sweep, lambda = H psi, reverse sweep over (psi, lambda). */
 int mqc_energy_grad(mqc_solver_t* s, const double* theta, double* energy, double* grad);
+
+/* Same evaluation with the parameters of the previous mqc_energy_grad call, which are still
+ * resident in HBM; the gradient stays on the device (benchmarks: no per-step host traffic). */
+int mqc_energy_grad_resident(mqc_solver_t* s, double* energy);
+
+/* CUDA events on the solver's stream, for device-side timing of a run of calls:
+ * mqc_event_record(s, 0) ... calls ... mqc_event_record(s, 1); mqc_event_elapsed_ms(s, &ms). */
+int mqc_event_record(mqc_solver_t* s, int32_t which);
+int mqc_event_elapsed_ms(mqc_solver_t* s, double* ms);
 
 /* Replaces: `ansatz.state(params)`, mqc/solver/dmet_solver_vqechem.py:71.  Writes
  * 2^N interleaved (re, im) pairs in OpenFermion index order.  theta == NULL: state of the

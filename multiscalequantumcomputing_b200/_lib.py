@@ -31,6 +31,9 @@ SIGNATURES = {
     "mqc_set_ansatz": [_H, C.c_int32, _i32p, _i32p, _i32p, C.c_int32, C.c_uint64],
     "mqc_energy": [_H, _f64p, _f64p],
     "mqc_energy_grad": [_H, _f64p, _f64p, _f64p],
+    "mqc_energy_grad_resident": [_H, _f64p],
+    "mqc_event_record": [_H, C.c_int32],
+    "mqc_event_elapsed_ms": [_H, _f64p],
     "mqc_prepare": [_H, _f64p],
     "mqc_state": [_H, _f64p, _f64p, C.c_int64],
     "mqc_expectation": [_H, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p],
@@ -148,6 +151,25 @@ class Handle:
         g = np.zeros(max(1, self.n_theta))
         check(self.lib.mqc_energy_grad(self.h, ptr(t, _f64p), C.byref(e), ptr(g, _f64p)))
         return e.value, g[:self.n_theta]
+
+    def energy_grad_resident(self) -> float:
+        e = C.c_double(0.0)
+        check(self.lib.mqc_energy_grad_resident(self.h, C.byref(e)))
+        return e.value
+
+    def energy_grad_into(self, theta: np.ndarray, grad_out: np.ndarray) -> float:
+        """Host buffers supplied by the caller (e.g. pinned memory): no allocation per call."""
+        e = C.c_double(0.0)
+        check(self.lib.mqc_energy_grad(self.h, ptr(theta, _f64p), C.byref(e), ptr(grad_out, _f64p)))
+        return e.value
+
+    def event_record(self, which: int):
+        check(self.lib.mqc_event_record(self.h, which))
+
+    def event_elapsed_ms(self) -> float:
+        ms = C.c_double(0.0)
+        check(self.lib.mqc_event_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def prepare(self, theta):
         t = self._theta(theta)

@@ -70,12 +70,15 @@ struct HamTables {                  // one Hamiltonian mapped to one physical la
 };
 
 struct SecHamTables {               // Hamiltonian in sector form for one layout and (na, nb)
-    DevBuf<unsigned> ma_list, gmb;
+    DevBuf<unsigned> ma_list, gmb, ginfo, gzca, gzcb;
     DevBuf<int> ma_goff, goff;
     DevBuf<u64> tz;
-    DevBuf<double2> tc;
+    DevBuf<double2> tc, gw;
     int n_ma = 0;
-    void reset() { ma_list.release(); gmb.release(); ma_goff.release(); goff.release(); tz.release(); tc.release(); n_ma = 0; }
+    void reset() {
+        ma_list.release(); gmb.release(); ma_goff.release(); goff.release(); tz.release(); tc.release();
+        ginfo.release(); gzca.release(); gzcb.release(); gw.release(); n_ma = 0;
+    }
 };
 
 struct LayoutTables {
@@ -101,6 +104,7 @@ struct mqc_solver {
     u64 dim = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t user_ev[2] = {nullptr, nullptr};
     bool gpu_ready = false;
 
     // options
@@ -301,7 +305,9 @@ static void build_sec_ham(mqc_solver* s, const HamHost& H, const std::vector<int
     const int n = s->n;
     std::vector<int> orb_of(n), spin_of(n);
     for (int q = 0; q < n; ++q) { orb_of[phys[n - 1 - q]] = q / 2; spin_of[phys[n - 1 - q]] = q & 1; }
-    struct Row { unsigned ma, mb; u64 z; double2 c; };
+    struct Row { unsigned ma, mb; u64 z; double2 c; u64 px; };
+    std::vector<u64> abit(n / 2 + 1, 0), bbit(n / 2 + 1, 0);           // physical bit of alpha / beta orbital p
+    for (int q = 0; q < n; ++q) { if (q & 1) bbit[q / 2] = 1ull << phys[n - 1 - q]; else abit[q / 2] = 1ull << phys[n - 1 - q]; }
     std::vector<Row> rows;
     rows.reserve(H.x.size());
     for (size_t t = 0; t < H.x.size(); ++t) {
@@ -312,7 +318,7 @@ static void build_sec_ham(mqc_solver* s, const HamHost& H, const std::vector<int
             if (spin_of[b]) mb |= 1u << orb_of[b]; else ma |= 1u << orb_of[b];
         }
         if ((__builtin_popcount(ma) | __builtin_popcount(mb)) & 1) continue;   // leaves the sector
-        rows.push_back(Row{ma, mb, mqc_map_mask(H.z[t], phys), H.c[t]});
+        rows.push_back(Row{ma, mb, mqc_map_mask(H.z[t], phys), H.c[t], mqc_map_mask(H.x[t], phys)});
     }
     std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) {
         return a.ma != b.ma ? a.ma < b.ma : a.mb < b.mb; });
@@ -333,6 +339,43 @@ static void build_sec_ham(mqc_solver* s, const HamHost& H, const std::vector<int
     }
     ma_goff.push_back((int)gmb.size());
     goff.push_back((int)rows.size());
+    // LUT form of the "simple" groups
+    const size_t G = gmb.size();
+    std::vector<unsigned> ginfo(std::max<size_t>(G, 1), 0), gzca(std::max<size_t>(G, 1), 0), gzcb(std::max<size_t>(G, 1), 0);
+    std::vector<double2> gw(std::max<size_t>(G, 1) * 16, make_double2(0, 0));
+    for (size_t g = 0; g < G; ++g) {
+        const int t0 = goff[g], t1 = goff[g + 1];
+        const unsigned ma = rows[t0].ma, mb = rows[t0].mb;
+        const int na_bits = __builtin_popcount(ma), nb_bits = __builtin_popcount(mb);
+        if (na_bits + nb_bits > 4) continue;
+        const u64 mphys = rows[t0].px;
+        const u64 zc = rows[t0].z & ~mphys;
+        bool simple = true;
+        for (int t = t0; t < t1; ++t) if ((rows[t].z & ~mphys) != zc) { simple = false; break; }
+        if (!simple) continue;
+        // physical bit of every pattern position: alpha orbitals ascending, then beta
+        u64 pbit[4]; int np = 0;
+        for (int p = 0; p < n / 2 + 1; ++p) if ((ma >> p) & 1u) pbit[np++] = abit[p];
+        for (int p = 0; p < n / 2 + 1; ++p) if ((mb >> p) & 1u) pbit[np++] = bbit[p];
+        for (int pat = 0; pat < (1 << np); ++pat) {
+            u64 xm = 0;
+            for (int k = 0; k < np; ++k) if ((pat >> k) & 1) xm |= pbit[k];
+            double wr = 0, wi = 0;
+            for (int t = t0; t < t1; ++t) {
+                const double sgn = (__builtin_popcountll(xm & rows[t].z) & 1) ? -1.0 : 1.0;
+                wr += sgn * rows[t].c.x; wi += sgn * rows[t].c.y;
+            }
+            gw[g * 16 + pat] = make_double2(wr, wi);
+        }
+        unsigned za = 0, zb = 0;
+        for (int p = 0; p < n / 2 + 1; ++p) { if (zc & abit[p]) za |= 1u << p; if (zc & bbit[p]) zb |= 1u << p; }
+        gzca[g] = za; gzcb[g] = zb;
+        ginfo[g] = 1u | ((unsigned)na_bits << 4);
+    }
+    T.ginfo.upload(ginfo, s->stream);
+    T.gzca.upload(gzca, s->stream);
+    T.gzcb.upload(gzcb, s->stream);
+    T.gw.upload(gw, s->stream);
     if (gmb.empty()) gmb.push_back(0);
     if (ma_list.empty()) ma_list.push_back(0);
     if (tz.empty()) { tz.push_back(0); tc.push_back(make_double2(0, 0)); }
@@ -351,6 +394,7 @@ static MqcSecHamDev sec_ham_dev(const LayoutTables& L, const SecHamTables& T) {
     D.n_ma = T.n_ma;
     D.ma_list = T.ma_list.p; D.ma_goff = T.ma_goff.p; D.gmb = T.gmb.p; D.goff = T.goff.p;
     D.tz = T.tz.p; D.tc = T.tc.p;
+    D.ginfo = T.ginfo.p; D.gzca = T.gzca.p; D.gzcb = T.gzcb.p; D.gw = T.gw.p;
     D.aorb = L.aorb.p; D.borb = L.borb.p; D.astr = L.astr.p; D.bstr = L.bstr.p;
     D.rank_a = L.rank_a.p; D.rank_b = L.rank_b.p;
     D.n_a = (unsigned)L.astr.n; D.n_b = (unsigned)L.bstr.n;
@@ -437,8 +481,10 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
 
 static void forward(mqc_solver* s, int which, const double* theta) {
     if (!s->have_ansatz) throw MqcError("mqc_set_ansatz has not been called");
-    s->theta_host.assign(theta, theta + s->n_theta);
-    CK(cudaMemcpyAsync(s->theta.p, theta, sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
+    if (theta) {
+        s->theta_host.assign(theta, theta + s->n_theta);
+        CK(cudaMemcpyAsync(s->theta.p, theta, sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
+    }
     const int nfac = (int)s->fac.size();
     if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->cs.p, nfac); s->counters[0]++; }
     CK(cudaMemsetAsync(s->psi.p, 0, sizeof(double2) * s->dim, s->stream));
@@ -709,15 +755,10 @@ int mqc_energy(mqc_solver_t* s, const double* theta, double* energy) {
     MQC_CATCH
 }
 
-int mqc_energy_grad(mqc_solver_t* s, const double* theta, double* energy, double* grad) {
-    MQC_TRY
-    require_gpu(s);
-    if (!theta || !energy || !grad) throw MqcError("null argument");
+static void run_energy_grad(mqc_solver* s, const double* theta, double* energy, double* grad) {
     reset_counters(s);
     ensure_layout_ready(s, 1);
     if (!s->lam.p) s->lam.alloc(s->dim);
-    const bool sec = s->conserving && s->use_sector;
-    (void)sec;
     double val[2] = {0, 0};
     CK(cudaEventRecord(s->ev[0], s->stream));
     forward(s, 1, theta);
@@ -726,11 +767,48 @@ int mqc_energy_grad(mqc_solver_t* s, const double* theta, double* energy, double
     CK(cudaEventRecord(s->ev[2], s->stream));
     reverse_sweep(s, 1);
     CK(cudaEventRecord(s->ev[3], s->stream));
-    if (s->n_theta)
+    if (grad && s->n_theta)
         CK(cudaMemcpyAsync(grad, s->grad.p, sizeof(double) * s->n_theta, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     finish_timing(s, true);
     *energy = val[0];
+}
+
+int mqc_energy_grad(mqc_solver_t* s, const double* theta, double* energy, double* grad) {
+    MQC_TRY
+    require_gpu(s);
+    if (!theta || !energy || !grad) throw MqcError("null argument");
+    run_energy_grad(s, theta, energy, grad);
+    MQC_CATCH
+}
+
+int mqc_energy_grad_resident(mqc_solver_t* s, double* energy) {
+    MQC_TRY
+    require_gpu(s);
+    if (!energy) throw MqcError("null argument");
+    if ((int)s->theta_host.size() != s->n_theta || !s->have_ansatz)
+        throw MqcError("no resident parameters: call mqc_energy_grad once first");
+    run_energy_grad(s, nullptr, energy, nullptr);
+    MQC_CATCH
+}
+
+int mqc_event_record(mqc_solver_t* s, int32_t which) {
+    MQC_TRY
+    require_gpu(s);
+    if (which < 0 || which > 1) throw MqcError("event index must be 0 or 1");
+    if (!s->user_ev[which]) CK(cudaEventCreate(&s->user_ev[which]));
+    CK(cudaEventRecord(s->user_ev[which], s->stream));
+    MQC_CATCH
+}
+
+int mqc_event_elapsed_ms(mqc_solver_t* s, double* ms) {
+    MQC_TRY
+    require_gpu(s);
+    if (!ms || !s->user_ev[0] || !s->user_ev[1]) throw MqcError("record both events first");
+    CK(cudaEventSynchronize(s->user_ev[1]));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, s->user_ev[0], s->user_ev[1]));
+    *ms = t;
     MQC_CATCH
 }
 

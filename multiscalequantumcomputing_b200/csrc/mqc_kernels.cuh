@@ -637,6 +637,12 @@ struct MqcSecHamDev {
     const int* goff;           // [G+1] term range per group
     const u64* tz;             // [T] physical z-mask
     const double2* tc;         // [T]
+    // "simple" groups (<= 4 flipped bits, all terms share the parity mask outside them):
+    //   coefficient(x) = (-1)^popc(x & zc) * W[pattern of x on the flipped bits]
+    const unsigned* ginfo;     // [G] bit0 simple, bits 4..7 = # flipped alpha bits
+    const unsigned* gzca;      // [G] common parity mask, alpha orbitals
+    const unsigned* gzcb;      // [G] common parity mask, beta orbitals
+    const double2* gw;         // [G][16] pattern = alpha bits (ascending) then beta bits
     const unsigned* aorb;      // [nA] alpha strings, orbital space
     const unsigned* borb;      // [nB]
     const u64* astr;           // [nA] physical images
@@ -665,6 +671,12 @@ __global__ void k_sector_scatter(double2* __restrict__ lam, const double2* __res
 }
 
 #define MQC_HS_R 4
+__device__ __forceinline__ unsigned pext_small(unsigned x, unsigned m) {   // gather the bits of x under m (<= 4 set bits)
+    unsigned out = 0, k = 0;
+    while (m) { const unsigned b = __ffs(m) - 1; m &= m - 1; out |= ((x >> b) & 1u) << k; ++k; }
+    return out;
+}
+
 __global__ void __launch_bounds__(256)
 k_happly_sector(const double2* __restrict__ C, double2* __restrict__ L, const MqcSecHamDev H,
                 double* __restrict__ e_out) {
@@ -683,13 +695,67 @@ k_happly_sector(const double2* __restrict__ C, double2* __restrict__ L, const Mq
     for (int im = 0; im < H.n_ma; ++im) {
         const unsigned ma = __ldg(H.ma_list + im);
         if (2 * __popc(ap & ma) != __popc(ma)) continue;          // uniform over the CTA
-        const unsigned ia = __ldg(H.rank_a + (ap ^ ma));
-        const u64 xa = __ldg(H.astr + ia);
+        const unsigned a = ap ^ ma;                               // source alpha string
+        const unsigned ia = __ldg(H.rank_a + a);
+        const unsigned pata = pext_small(a, ma);
+        const int nbits_a = __popc(ma);
         const double2* __restrict__ Crow = C + (size_t)ia * H.n_b;
         const int g0 = __ldg(H.ma_goff + im), g1 = __ldg(H.ma_goff + im + 1);
         for (int g = g0; g < g1; ++g) {
             const unsigned mb = __ldg(H.gmb + g);
             const int pmb = __popc(mb);
+            const unsigned info = __ldg(H.ginfo + g);
+            if (info & 1u) {
+                // ---- LUT path ---------------------------------------------------------
+                const unsigned sa = __popc(a & __ldg(H.gzca + g)) & 1u;
+                const unsigned zcb = __ldg(H.gzcb + g);
+                const double2* __restrict__ Wg = H.gw + (size_t)g * 16 + pata;
+                if (pmb == 2) {
+                    // exactly one of the two beta bits is set in a valid source string
+                    const unsigned q0 = __ffs(mb) - 1;
+                    const double2 w1 = __ldg(Wg + (1u << nbits_a)), w2 = __ldg(Wg + (2u << nbits_a));
+#pragma unroll
+                    for (int r = 0; r < MQC_HS_R; ++r) {
+                        if (bp[r] != 0xffffffffu && __popc(bp[r] & mb) == 1) {
+                            const unsigned b = bp[r] ^ mb;
+                            const double2 amp = Crow[__ldg(H.rank_b + b)];
+                            const bool first = (b >> q0) & 1u;
+                            double wr = first ? w1.x : w2.x, wi = first ? w1.y : w2.y;
+                            if ((__popc(b & zcb) + sa) & 1u) { wr = -wr; wi = -wi; }
+                            ar[r] += wr * amp.x - wi * amp.y;
+                            ai[r] += wr * amp.y + wi * amp.x;
+                        }
+                    }
+                } else if (pmb == 0) {
+                    const double2 w = __ldg(Wg);
+#pragma unroll
+                    for (int r = 0; r < MQC_HS_R; ++r) {
+                        if (bp[r] != 0xffffffffu) {
+                            const double2 amp = Crow[ibp[r]];
+                            double wr = w.x, wi = w.y;
+                            if ((__popc(bp[r] & zcb) + sa) & 1u) { wr = -wr; wi = -wi; }
+                            ar[r] += wr * amp.x - wi * amp.y;
+                            ai[r] += wr * amp.y + wi * amp.x;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < MQC_HS_R; ++r) {
+                        if (bp[r] != 0xffffffffu && 2 * __popc(bp[r] & mb) == pmb) {
+                            const unsigned b = bp[r] ^ mb;
+                            const double2 amp = Crow[__ldg(H.rank_b + b)];
+                            const double2 w = __ldg(Wg + (pext_small(b, mb) << nbits_a));
+                            double wr = w.x, wi = w.y;
+                            if ((__popc(b & zcb) + sa) & 1u) { wr = -wr; wi = -wi; }
+                            ar[r] += wr * amp.x - wi * amp.y;
+                            ai[r] += wr * amp.y + wi * amp.x;
+                        }
+                    }
+                }
+                continue;
+            }
+            // ---- general path: explicit term loop -------------------------------------
+            const u64 xa = __ldg(H.astr + ia);
             u64 x[MQC_HS_R];
             double2 amp[MQC_HS_R];
             double cr[MQC_HS_R], ci[MQC_HS_R];

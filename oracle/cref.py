@@ -95,7 +95,7 @@ class CRefUCCSD:
         return self.psi.copy()
 
     # pieces, for bounded-sample timing
-    def time_sample(self, theta, n_factors_sample, n_terms_sample):
+    def time_sample(self, theta, n_factors_sample, n_terms_sample, sector_index=None):
         """Time a bounded sample: forward over the first ``n_factors_sample`` factors, H apply
         over the first ``n_terms_sample`` terms, reverse over the same factors.
         Returns (t_forward, t_happly, t_reverse) seconds."""
@@ -108,6 +108,15 @@ class CRefUCCSD:
         for k in range(nf):
             self.lib.orc_apply_excitation(self.psi.ctypes.data, self.n, int(self.kind[k]),
                                           self.idx[k].ctypes.data_as(_i32p), float(th[self.ti[k]]))
+        t1 = time.perf_counter()
+        # after a few factors the state is still almost a single determinant; fill the whole
+        # (N_alpha, N_beta) sector so that H apply and the reverse sweep see the populated state
+        # of a full evaluation (untimed)
+        if sector_index is not None:
+            rng = np.random.default_rng(7)
+            v = rng.standard_normal(len(sector_index))
+            self.psi[:] = 0.0
+            self.psi[sector_index] = v / np.linalg.norm(v)
         t1 = time.perf_counter()
         self.lib.orc_happly(self.psi.ctypes.data, self.lam.ctypes.data, self.n, len(self.xm), self._p(self.xm, _u64p),
                             self._p(self.zm, _u64p), self._p(self.cre, _f64p), self._p(self.cim, _f64p), 0, nt)
