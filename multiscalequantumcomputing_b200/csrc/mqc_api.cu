@@ -101,7 +101,9 @@ struct LayoutTables {
 
 struct mqc_solver {
     int n = 0, device = 0;
-    u64 dim = 0;
+    u64 dim = 0;                    // amplitudes held by THIS handle (2^n_local)
+    int n_global = 0, rank = 0;     // sharded state: top n_global physical bits = rank id
+    int n_local = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t user_ev[2] = {nullptr, nullptr};
@@ -439,6 +441,7 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
     const MqcPass& P = S.passes[pass];
     const int nf = P.f1 - P.f0;
     const unsigned grid = (unsigned)(s->dim >> P.k);
+    const u64 rank_bits = (u64)s->rank << s->n_local;
     const bool sparse = s->conserving && s->use_sector && s->sparse_tiles;
     if (sparse) {
         // alpha = even qubits, beta = odd qubits.  Tile-local coordinates are those of the
@@ -461,8 +464,8 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
         while (nthr > 32 && nthr / 2 >= SP.cap) nthr >>= 1;
         const size_t smem = mqc_sparse_smem_bytes(P.k, SP.cap, adj);
         if (smem <= 200000) {
-            if (adj) k_tile_sparse<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n, reverse, SP);
-            else k_tile_sparse<false><<<grid, nthr, smem, s->stream>>>(s->psi.p, nullptr, P, s->tf[which].p, s->cs.p, nullptr, s->n, reverse, SP);
+            if (adj) k_tile_sparse<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n_local, reverse, SP, rank_bits);
+            else k_tile_sparse<false><<<grid, nthr, smem, s->stream>>>(s->psi.p, nullptr, P, s->tf[which].p, s->cs.p, nullptr, s->n_local, reverse, SP, rank_bits);
             s->counters[0]++;
             return;
         }
@@ -473,14 +476,15 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
     const size_t smem = mqc_tile_smem_bytes(P.k, nf, adj, nthr);
     if (smem > 232448) throw MqcError("tile does not fit shared memory; lower tile_bits / grad_tile_bits");
     if (adj)
-        k_tile_sweep<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n, reverse);
+        k_tile_sweep<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n_local, reverse, rank_bits);
     else
-        k_tile_sweep<false><<<grid, nthr, smem, s->stream>>>(s->psi.p, nullptr, P, s->tf[which].p, s->cs.p, nullptr, s->n, reverse);
+        k_tile_sweep<false><<<grid, nthr, smem, s->stream>>>(s->psi.p, nullptr, P, s->tf[which].p, s->cs.p, nullptr, s->n_local, reverse, rank_bits);
     s->counters[0]++;
 }
 
 static void forward(mqc_solver* s, int which, const double* theta) {
     if (!s->have_ansatz) throw MqcError("mqc_set_ansatz has not been called");
+    if (s->n_global) throw MqcError("sharded handle: drive it through the mqc_shard_* entry points");
     if (theta) {
         s->theta_host.assign(theta, theta + s->n_theta);
         CK(cudaMemcpyAsync(s->theta.p, theta, sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
@@ -597,6 +601,7 @@ int mqc_create(int n_qubits, int device, mqc_solver_t** out) {
     if (n_qubits < 2 || n_qubits > 40) throw MqcError("n_qubits must be in [2, 40]");
     mqc_solver* s = new mqc_solver();
     s->n = n_qubits;
+    s->n_local = n_qubits;
     s->device = device;
     s->dim = 1ull << n_qubits;
     *out = s;
@@ -645,7 +650,7 @@ int mqc_set_hamiltonian(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask,
                         const double* coeff_re, const double* coeff_im) {
     MQC_TRY
     if (!s || n_terms < 0 || (n_terms && (!xmask || !zmask || !coeff_re))) throw MqcError("bad arguments");
-    const u64 lim = s->dim - 1ull;
+    const u64 lim = (s->n >= 64) ? ~0ull : ((1ull << s->n) - 1ull);
     s->ham.x.assign(xmask, xmask + n_terms);
     s->ham.z.assign(zmask, zmask + n_terms);
     s->ham.c.resize(n_terms);
@@ -664,7 +669,8 @@ int mqc_set_ansatz(mqc_solver_t* s, int32_t n_factors, const int32_t* kind, cons
     MQC_TRY
     if (!s || n_factors < 0 || n_theta < 0 || (n_factors && (!kind || !idx4 || !theta_index)))
         throw MqcError("bad arguments");
-    if (ref_index >= s->dim) throw MqcError("reference index outside the register");
+    if (ref_index >> s->n) throw MqcError("reference index outside the register");
+    if (s->n_global && s->mode != 1) throw MqcError("a sharded state needs mode = 1 (tile sweep)");
     const int n = s->n;
     std::vector<MqcFactor> fac;
     fac.reserve(n_factors);
@@ -690,7 +696,7 @@ int mqc_set_ansatz(mqc_solver_t* s, int32_t n_factors, const int32_t* kind, cons
     for (int w = 0; w < 2; ++w) {
         const int kb = (w == 0) ? s->tile_bits : s->grad_tile_bits;
         if (s->mode == 1) {
-            s->sched[w] = mqc_build_schedule(n, kb, s->low_bits, fac);
+            s->sched[w] = mqc_build_schedule(n, kb, s->low_bits, fac, MQC_MAX_PASS_FACTORS, s->n_global);
         } else {
             s->sched[w] = MqcSchedule();
             s->sched[w].n_bits = n;

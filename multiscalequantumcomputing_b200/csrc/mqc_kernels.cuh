@@ -134,7 +134,8 @@ template <bool ADJ>
 __global__ void __launch_bounds__(256)
 k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass P,
               const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
-              double* __restrict__ grad, const int n_bits, const int reverse, const MqcSparse SP) {
+              double* __restrict__ grad, const int n_bits, const int reverse, const MqcSparse SP,
+              const u64 rank_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = P.k;
     const uint32_t T = 1u << K;
@@ -170,14 +171,17 @@ k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPas
         if (tid == 0) scount[0] = 0;
     }
     __syncthreads();
+    // n_bits counts the LOCAL address bits; rank_bits are the shard's global bits (already
+    // shifted above them): they enter parities and electron counts, never addresses.
     const u64 base = mqc_deposit_complement((u64)blockIdx.x, P.act_mask, n_bits);
+    const u64 sbase = base | rank_bits;
     uint32_t aloc = 0, bloc = 0;
     for (int j = 0; j < K; ++j) {
         aloc |= (uint32_t)((SP.amask >> spos[j]) & 1ull) << j;
         bloc |= (uint32_t)((SP.bmask >> spos[j]) & 1ull) << j;
     }
-    const int ka = SP.na - __popcll(base & SP.amask);
-    const int kb = SP.nb - __popcll(base & SP.bmask);
+    const int ka = SP.na - __popcll(sbase & SP.amask);
+    const int kb = SP.nb - __popcll(sbase & SP.bmask);
     if (ka < 0 || kb < 0 || ka > __popc(aloc) || kb > __popc(bloc)) return;      // tile holds only zeros
 
     // physical offset of a tile-local index, and the local index an element has in the OTHER
@@ -250,7 +254,7 @@ k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPas
             const double2 v = cs[Fp->slot];
             scs[fc] = make_double2(v.x, reverse ? -v.y : v.y);
             stheta[fc] = Fp->theta;
-            const uint32_t sg = ((uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
+            const uint32_t sg = ((uint32_t)__popcll(sbase & Fp->z_out) + Fp->sign0) & 1u;
             smz[fc] = (uint32_t)Fp->m | ((uint32_t)Fp->z << 16);
             svs[fc] = (uint32_t)Fp->v | (sg << 16);
         }
@@ -345,7 +349,7 @@ template <bool ADJ>
 __global__ void __launch_bounds__(512)
 k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass P,
              const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
-             double* __restrict__ grad, const int n_bits, const int reverse) {
+             double* __restrict__ grad, const int n_bits, const int reverse, const u64 rank_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = P.k;
     const uint32_t T = 1u << K;
@@ -422,7 +426,7 @@ k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass
             if (xl < T) val = swz(xl) | (((uint32_t)__popc(xl & fz) & 1u) << 15);
             if (e < 32) {                                       // v and the per-tile sign ride on table A
                 const uint32_t fv = Fp->v;
-                const uint32_t sg = ((uint32_t)__popc(fv & fz) + (uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
+                const uint32_t sg = ((uint32_t)__popc(fv & fz) + (uint32_t)__popcll((base | rank_bits) & Fp->z_out) + Fp->sign0) & 1u;
                 val ^= swz(fv) | (sg << 15);
             }
             slut[w] = (uint16_t)val;

@@ -19,8 +19,18 @@
 
 #include "mqc_common.h"
 
+// One step of a (possibly sharded) sweep: a tile pass on the local shard, or the exchange of
+// the amplitudes' global bit (physical position pg >= n_local) with local position pl between
+// rank pairs r <-> r ^ (1 << (pg - n_local)).
+struct MqcStep {
+    int type;      // 0 = tile pass, 1 = exchange
+    int a, b;      // pass index, 0   |   pg, pl
+};
+
 struct MqcSchedule {
     int n_bits = 0, k = 0, low = 0;
+    int n_global = 0;              // top physical positions that live in the rank id
+    std::vector<MqcStep> steps;
     std::vector<MqcPass> passes;
     std::vector<MqcTileFactor> tf;
     std::vector<std::vector<int>> pass_phys_before, pass_phys_after;   // layout around each pass
@@ -37,17 +47,26 @@ static inline u64 mqc_map_mask(u64 mask, const std::vector<int>& phys) {
 
 // factors are given in LOGICAL bit coordinates
 static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
-                                             const std::vector<MqcFactor>& fac, int cap = MQC_MAX_PASS_FACTORS) {
+                                             const std::vector<MqcFactor>& fac, int cap = MQC_MAX_PASS_FACTORS,
+                                             int n_global = 0) {
     MqcSchedule S;
-    const int N = n_bits;
+    const int NT = n_bits;                 // all physical bits
+    const int N = n_bits - n_global;       // local physical bits: positions 0 .. N-1
+    if (N < 1) throw std::runtime_error("too many global bits");
+    S.n_global = n_global;
     const int K = std::min(k_req, N);
     const int L = std::min(low_req, K);
     if (K > 16) throw std::runtime_error("tile bits too large");
     if (K < N && K < L + 4) throw std::runtime_error("tile bits must be >= low bits + 4");
-    S.n_bits = N; S.k = K; S.low = L;
-    std::vector<int> phys(N), inv(N);
-    for (int l = 0; l < N; ++l) phys[l] = inv[l] = l;
+    S.n_bits = NT; S.k = K; S.low = L;
+    std::vector<int> phys(NT), inv(NT);
+    for (int l = 0; l < NT; ++l) phys[l] = inv[l] = l;
     const size_t n = fac.size();
+    // next use of every logical bit after factor t (for the exchange victim choice)
+    auto next_use = [&](int bit, size_t from) -> size_t {
+        for (size_t t = from; t < n; ++t) if ((fac[t].m >> bit) & 1ull) return t;
+        return n + 1;
+    };
     // The reference state is a single determinant, so the initial layout is free: put the
     // bits the first factors move into the low physical positions.
     if (K < N && L > 0) {
@@ -64,14 +83,51 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
             }
         }
     }
+    // ... and the bits whose first use is farthest away into the global (rank) positions
+    if (n_global > 0) {
+        std::vector<int> cand;
+        for (int l = 0; l < NT; ++l) if (!(K < N && phys[l] < L)) cand.push_back(l);
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return next_use(a, 0) > next_use(b, 0); });
+        for (int t = 0; t < n_global && t < (int)cand.size(); ++t) {
+            const int b = cand[t], target = N + t;
+            if (phys[b] == target) continue;
+            const int other = inv[target], p_old = phys[b];
+            phys[b] = target; inv[target] = b;
+            phys[other] = p_old; inv[p_old] = other;
+        }
+    }
     S.phys_init = phys;
     size_t i = 0;
     while (i < n) {
+        // bring the bits the next factor moves into the local shard
+        {
+            u64 need = fac[i].m;
+            while (need) {
+                const int b = __builtin_ctzll(need); need &= need - 1;
+                if (phys[b] < N) continue;
+                // victim: local bit, not moved by this factor, whose next use is farthest away
+                int victim = -1; size_t far = 0;
+                for (int p = N - 1; p >= 0; --p) {
+                    const int lb = inv[p];
+                    if ((fac[i].m >> lb) & 1ull) continue;
+                    const size_t nu = next_use(lb, i);
+                    if (victim < 0 || nu > far) { victim = lb; far = nu; }
+                }
+                if (victim < 0) throw std::runtime_error("no local bit to exchange with");
+                const int pg = phys[b], pl = phys[victim];
+                S.steps.push_back(MqcStep{1, pg, pl});
+                phys[b] = pl; inv[pl] = b;
+                phys[victim] = pg; inv[pg] = victim;
+            }
+        }
         u64 A = 0;                                   // logical active set
         for (int p = 0; p < L; ++p) A |= 1ull << inv[p];
-        if (K == N) A = (N == 64) ? ~0ull : ((1ull << N) - 1ull);
+        if (K == N) { A = 0; for (int p = 0; p < N; ++p) A |= 1ull << inv[p]; }
         size_t j = i;
         while (j < n && (int)(j - i) < cap) {
+            bool local = true;
+            { u64 mm = fac[j].m; while (mm) { const int b = __builtin_ctzll(mm); mm &= mm - 1; if (phys[b] >= N) local = false; } }
+            if (!local) break;
             const u64 U = A | fac[j].m;
             if (MQC_POPC64(U) > K) break;
             A = U; ++j;
@@ -86,7 +142,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
             if ((int)ahead.size() >= 2 * K) break;
         }
         // fill A up to K bits: first with bits needed soonest, then lowest physical positions
-        for (size_t t = 0; t < ahead.size() && MQC_POPC64(A) < K; ++t) A |= 1ull << ahead[t];
+        for (size_t t = 0; t < ahead.size() && MQC_POPC64(A) < K; ++t) if (phys[ahead[t]] < N) A |= 1ull << ahead[t];
         for (int p = 0; p < N && MQC_POPC64(A) < K; ++p) A |= 1ull << inv[p];
 
         MqcPass P{};
@@ -96,7 +152,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
         std::vector<int> pos;                       // physical positions of A, ascending
         for (int p = 0; p < N; ++p) if ((A >> inv[p]) & 1ull) pos.push_back(p);
         u64 act = 0;
-        std::vector<int> local_of_phys(N, -1);
+        std::vector<int> local_of_phys(NT, -1);
         for (int jj = 0; jj < K; ++jj) { P.pos[jj] = pos[jj]; act |= 1ull << pos[jj]; local_of_phys[pos[jj]] = jj; }
         P.act_mask = act;
         for (size_t t = i; t < j; ++t) {
@@ -146,21 +202,22 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
                 }
             }
             bool changed = false;
-            for (int l = 0; l < N; ++l) if (newphys[l] != phys[l]) changed = true;
+            for (int l = 0; l < NT; ++l) if (newphys[l] != phys[l]) changed = true;
             if (changed) {
                 P.has_perm = 1;
                 // new local bit j' (physical pos[j']) holds logical l' = newinv[pos[j']],
                 // which sat at old local position local_of_phys[phys[l']]
-                std::vector<int> newinv(N);
-                for (int l = 0; l < N; ++l) newinv[newphys[l]] = l;
+                std::vector<int> newinv(NT);
+                for (int l = 0; l < NT; ++l) newinv[newphys[l]] = l;
                 for (int jj = 0; jj < K; ++jj) {
                     const int lg = newinv[pos[jj]];
                     P.perm[jj] = (uint8_t)local_of_phys[phys[lg]];
                 }
                 phys = newphys;
-                for (int l = 0; l < N; ++l) inv[phys[l]] = l;
+                for (int l = 0; l < NT; ++l) inv[phys[l]] = l;
             }
         }
+        S.steps.push_back(MqcStep{0, (int)S.passes.size(), 0});
         S.passes.push_back(P);
         S.pass_phys_after.push_back(phys);
         i = j;
