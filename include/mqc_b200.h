@@ -43,6 +43,36 @@ int mqc_device_count(int* count);
 int mqc_create(int n_qubits, int device, mqc_solver_t** out);
 int mqc_destroy(mqc_solver_t* s);
 
+/* Sharded state (BASELINE.json configs[4]; SURVEY.md §8e "sharded state"): the 2^n_qubits
+ * amplitudes are split over n_ranks = 2, 4 or 8 GPUs; the top log2(n_ranks) PHYSICAL index
+ * bits are the rank.  Every other entry point of this header then works on the sharded
+ * state and is COLLECTIVE: all ranks call it with the same arguments.  There is no
+ * counterpart in the reference (its scipy.sparse vectors live in one host address space,
+ * mqc/solver/dmet_interface.py:114-123); this replaces "does not fit" beyond one GPU.
+ *
+ *   mqc_shard_group_create  all ranks are driven by THIS process through one handle
+ *                           (devices[r] may repeat: several ranks on one GPU, for tests).
+ *   mqc_shard_create        one process per GPU (torchrun): after mqc_set_ansatz every rank
+ *                           calls mqc_shard_export, the MQC_SHARD_BLOB_BYTES blobs are
+ *                           all-gathered by the host (torch.distributed), and
+ *                           mqc_shard_connect maps the peers' shards with CUDA IPC.
+ * Tile passes whose active bits include rank bits read and write the peers' HBM directly
+ * over NVLink (the global-qubit exchange is fused into the compute pass); ranks are ordered
+ * by CUDA events (same process) or a system-scope flag barrier kernel (IPC).
+ * mqc_rdm12 on a per-process shard handle returns that rank's partial sums (add them up
+ * with an all-reduce); everything else returns the reduced result on every rank. */
+#define MQC_SHARD_BLOB_BYTES 512
+int mqc_shard_group_create(int n_qubits, int n_ranks, const int* devices, mqc_solver_t** out);
+int mqc_shard_create(int n_qubits, int device, int rank, int n_ranks, mqc_solver_t** out);
+int mqc_shard_export(mqc_solver_t* s, int32_t want_lambda, void* blob, int64_t blob_bytes);
+int mqc_shard_connect(mqc_solver_t* s, const void* blobs, int64_t blobs_bytes);
+int mqc_shard_info(mqc_solver_t* s, int32_t* rank, int32_t* n_ranks, int32_t* n_local_bits, int32_t* members);
+/* Raw PHYSICAL-order amplitudes of one rank's shard (2^n_local complex128) and the layout
+ * phys_of_logical[l] (n_qubits entries) they are stored in; `member` selects the rank of a
+ * same-process group (0 otherwise).  Test / checkpoint access; replaces nothing. */
+int mqc_shard_read(mqc_solver_t* s, const double* theta, int32_t member, double* re_im,
+                   int64_t n_amplitudes, int32_t* phys_of_logical);
+
 /* Options (before mqc_set_ansatz): "tile_bits" (default 12), "low_bits" (3),
  * "grad_tile_bits" (12), "mode" (1 = fused tile sweep, 0 = one factor per pass),
  * "sector" (1 = exploit particle-number/S_z conservation of the ansatz in H|psi>),
@@ -109,6 +139,10 @@ int mqc_schedule_info(mqc_solver_t* s, int32_t which /*0 energy, 1 gradient*/, i
 int mqc_schedule_pass(mqc_solver_t* s, int32_t which, int32_t pass, int32_t* first_factor,
                       int32_t* n_factors, uint64_t* act_mask, int32_t* pos16, int32_t* perm16,
                       int32_t* has_perm);
+/* tiles rank `rank` sweeps in pass `pass`: tile counter t in [0, n_tiles) -> (t | tau_hi) is
+ * deposited into the inactive LOCAL bits, OR fixed_bits (the rank's inactive global bits) */
+int mqc_schedule_tile_map(mqc_solver_t* s, int32_t which, int32_t pass, int32_t rank, uint64_t* tau_hi,
+                          uint64_t* fixed_bits, uint64_t* n_tiles);
 int mqc_schedule_factor(mqc_solver_t* s, int32_t which, int32_t tile_factor, uint32_t* m, uint32_t* v,
                         uint32_t* z, uint64_t* z_out, int32_t* sign0, int32_t* slot);
 int mqc_schedule_final_layout(mqc_solver_t* s, int32_t which, int32_t* phys_of_logical);

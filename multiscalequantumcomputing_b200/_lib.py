@@ -25,6 +25,13 @@ SIGNATURES = {
     "mqc_version": [],
     "mqc_device_count": [_i32p],
     "mqc_create": [C.c_int, C.c_int, C.POINTER(_H)],
+    "mqc_shard_group_create": [C.c_int, C.c_int, _i32p, C.POINTER(_H)],
+    "mqc_shard_create": [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_H)],
+    "mqc_shard_export": [_H, C.c_int32, C.c_void_p, C.c_int64],
+    "mqc_shard_connect": [_H, C.c_void_p, C.c_int64],
+    "mqc_shard_info": [_H, _i32p, _i32p, _i32p, _i32p],
+    "mqc_shard_read": [_H, _f64p, C.c_int32, _f64p, C.c_int64, _i32p],
+    "mqc_schedule_tile_map": [_H, C.c_int32, C.c_int32, C.c_int32, _u64p, _u64p, _u64p],
     "mqc_destroy": [_H],
     "mqc_set_option": [_H, C.c_char_p, C.c_int64],
     "mqc_set_hamiltonian": [_H, C.c_int64, _u64p, _u64p, _f64p, _f64p],
@@ -96,11 +103,12 @@ def device_count() -> int:
 class Handle:
     """Thin RAII wrapper over ``mqc_solver_t*``."""
 
-    def __init__(self, n_qubits: int, device: int = 0):
+    def __init__(self, n_qubits: int, device: int = 0, _create=True):
         self.lib = load()
         self.n_qubits = n_qubits
         self.h = _H()
-        check(self.lib.mqc_create(n_qubits, device, C.byref(self.h)))
+        if _create:
+            check(self.lib.mqc_create(n_qubits, device, C.byref(self.h)))
         self.n_theta = 0
         self._keep = []
 
@@ -226,10 +234,111 @@ class Handle:
                 check(self.lib.mqc_schedule_factor(self.h, which, t, C.byref(m), C.byref(v), C.byref(z),
                                                    C.byref(zo), C.byref(s0), C.byref(slot)))
                 facs.append(dict(m=m.value, v=v.value, z=z.value, z_out=zo.value, sign0=s0.value, slot=slot.value))
-            passes.append(dict(act_mask=act.value, pos=pos[:kb.value].copy(), perm=perm[:kb.value].copy(),
+            tile_map = []
+            for r in range(getattr(self, "n_ranks", 1)):
+                th, fb, nt = C.c_uint64(), C.c_uint64(), C.c_uint64()
+                check(self.lib.mqc_schedule_tile_map(self.h, which, p, r, C.byref(th), C.byref(fb), C.byref(nt)))
+                tile_map.append((th.value, fb.value, nt.value))
+            passes.append(dict(tile_map=tile_map, act_mask=act.value, pos=pos[:kb.value].copy(), perm=perm[:kb.value].copy(),
                                has_perm=bool(hp.value), factors=facs))
         lay = np.zeros(self.n_qubits, dtype=np.int32)
         check(self.lib.mqc_schedule_final_layout(self.h, which, ptr(lay, _i32p)))
         lay0 = np.zeros(self.n_qubits, dtype=np.int32)
         check(self.lib.mqc_schedule_initial_layout(self.h, which, ptr(lay0, _i32p)))
         return dict(tile_bits=kb.value, passes=passes, final_layout=lay, initial_layout=lay0)
+
+
+BLOB_BYTES = 512
+
+
+class _ShardBase(Handle):
+    def shard_info(self):
+        r, n, nl, m = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.lib.mqc_shard_info(self.h, C.byref(r), C.byref(n), C.byref(nl), C.byref(m)))
+        return dict(rank=r.value, n_ranks=n.value, n_local_bits=nl.value, members=m.value)
+
+    def state(self, theta=None):
+        raise MqcError("a sharded state is read shard by shard: use read_shard() / gather_state()")
+
+    def read_shard(self, member=0, theta=None):
+        """(raw physical-order shard, phys_of_logical layout)"""
+        nl = self.shard_info()["n_local_bits"]
+        out = np.empty(1 << nl, dtype=np.complex128)
+        lay = np.zeros(self.n_qubits, dtype=np.int32)
+        tp = ptr(self._theta(theta), _f64p) if theta is not None else None
+        check(self.lib.mqc_shard_read(self.h, tp, member, C.cast(out.ctypes.data, _f64p), out.shape[0], ptr(lay, _i32p)))
+        return out, lay
+
+
+def assemble_state(shards, layout):
+    """Logical-order state vector from the physical-order shards of all ranks (rank = top
+    physical index bits); small registers only (tests, checkpoints)."""
+    phys = np.concatenate(shards)
+    n = len(layout)
+    i = np.arange(1 << n, dtype=np.uint64)
+    p = np.zeros_like(i)
+    for l, pos in enumerate(layout):
+        p |= ((i >> np.uint64(l)) & np.uint64(1)) << np.uint64(int(pos))
+    return phys[p.astype(np.int64)]
+
+
+class ShardGroup(_ShardBase):
+    """All ranks of a sharded state driven by this process (`mqc_shard_group_create`).
+    ``devices[r]`` is the GPU of rank r; repeating a device puts several ranks on one GPU."""
+
+    def __init__(self, n_qubits: int, devices):
+        super().__init__(n_qubits, _create=False)
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        self.n_ranks = len(dv)
+        check(self.lib.mqc_shard_group_create(n_qubits, len(dv), ptr(dv, _i32p), C.byref(self.h)))
+
+    def gather_state(self, theta=None):
+        shards = []
+        lay = None
+        for m in range(self.n_ranks):
+            sh, lay = self.read_shard(m, theta if m == 0 else None)
+            shards.append(sh)
+        return assemble_state(shards, lay)
+
+
+class ShardRank(_ShardBase):
+    """One rank of a sharded state, one process per GPU (`mqc_shard_create`); ``connect``
+    all-gathers the CUDA IPC blobs over ``torch.distributed`` (any backend)."""
+
+    def __init__(self, n_qubits: int, device: int, rank: int, n_ranks: int):
+        super().__init__(n_qubits, _create=False)
+        self.rank, self.n_ranks = rank, n_ranks
+        check(self.lib.mqc_shard_create(n_qubits, device, rank, n_ranks, C.byref(self.h)))
+
+    def export(self, want_lambda=True) -> bytes:
+        buf = C.create_string_buffer(BLOB_BYTES)
+        check(self.lib.mqc_shard_export(self.h, int(bool(want_lambda)), buf, BLOB_BYTES))
+        return buf.raw
+
+    def connect_blobs(self, blobs):
+        raw = b"".join(blobs)
+        check(self.lib.mqc_shard_connect(self.h, raw, len(raw)))
+
+    def connect(self, want_lambda=True, group=None):
+        import torch.distributed as dist
+        mine = self.export(want_lambda)
+        blobs = [None] * self.n_ranks
+        dist.all_gather_object(blobs, mine, group=group)
+        self.connect_blobs(blobs)
+        dist.barrier(group=group)
+
+    def rdm12(self, n_orb, n_alpha, n_beta, want_rdm2=True, group=None):
+        """Partial sums of this rank, all-reduced over the ranks."""
+        import torch
+        import torch.distributed as dist
+        r1, r2 = super().rdm12(n_orb, n_alpha, n_beta, want_rdm2)
+        for a in (r1, r2):
+            if a is not None and self.n_ranks > 1:
+                t = torch.from_numpy(a)
+                if dist.get_backend(group) == "nccl":
+                    t = t.cuda()
+                    dist.all_reduce(t, group=group)
+                    a[...] = t.cpu().numpy()
+                else:
+                    dist.all_reduce(t, group=group)
+        return r1, r2

@@ -99,11 +99,29 @@ struct LayoutTables {
     }
 };
 
+// mail buffer layout (doubles): [0..3] scalars, [8..15] barrier flags (as u64), [16..) gradient.
+// One allocation so that a peer maps it with one CUDA IPC handle.
+#define MQC_MAIL_FLAGS 8
+#define MQC_MAIL_GRAD 16
+#define MQC_BLOB_BYTES 512
+
 struct mqc_solver {
     int n = 0, device = 0;
-    u64 dim = 0;                    // amplitudes held by THIS handle (2^n_local)
-    int n_global = 0, rank = 0;     // sharded state: top n_global physical bits = rank id
+    u64 dim = 0;                    // amplitudes held by THIS rank (2^n_local)
+    int n_global = 0, rank = 0, n_ranks = 1;   // sharded state: top n_global physical bits = rank id
     int n_local = 0;
+    // 0: one rank.  1: all ranks are handles of this process, driven in lockstep by the leader
+    // (members[0]), ordered by CUDA events.  2: one process per GPU, peers mapped with CUDA IPC,
+    // ordered by k_rank_barrier.
+    int comm_mode = 0;
+    std::vector<mqc_solver*> members;          // ranks this handle drives (itself first)
+    bool connected = false;
+    double2* peer_psi[MQC_MAX_RANKS] = {};
+    double2* peer_lam[MQC_MAX_RANKS] = {};
+    double* peer_mail[MQC_MAX_RANKS] = {};
+    std::vector<std::pair<std::string, void*>> ipc_open;   // handle bytes -> mapped base
+    u64 epoch = 0;
+    cudaEvent_t sync_ev = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t user_ev[2] = {nullptr, nullptr};
@@ -113,9 +131,12 @@ struct mqc_solver {
     int tile_bits = 12, low_bits = 3, grad_tile_bits = 12, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
 
     DevBuf<double2> psi, lam, cs, scratch_state, csec, lsec;
-    DevBuf<double> theta, grad, scalars, rdm_acc;
-    DevBuf<int> theta_index;
+    DevBuf<double> theta, mail, red, rdm_acc;
+    DevBuf<int> theta_index, err;
     DevBuf<MqcTileFactor> tf[2];
+    double* scalars_p() const { return mail.p; }
+    double* grad_p() const { return mail.p + MQC_MAIL_GRAD; }
+    unsigned long long* flags_p() const { return reinterpret_cast<unsigned long long*>(mail.p + MQC_MAIL_FLAGS); }
 
     HamHost ham;
     bool have_ham = false, have_ansatz = false;
@@ -200,16 +221,6 @@ static MqcFactor make_factor(int n, int kind, const int32_t* ix, int slot, int t
     return f;
 }
 
-static MqcFactor map_factor(const MqcFactor& f, const std::vector<int>& phys) {
-    MqcFactor g = f;
-    g.m = mqc_map_mask(f.m, phys);
-    g.v = mqc_map_mask(f.v, phys);
-    g.z = mqc_map_mask(f.z, phys);
-    int c = 0;
-    for (int b = 0; b < (int)phys.size(); ++b) if ((g.m >> b) & 1ull) g.pos[c++] = b;
-    return g;
-}
-
 static void require_gpu(mqc_solver* s) {
     if (!s) throw MqcError("null solver handle");
     if (s->gpu_ready) { CK(cudaSetDevice(s->device)); return; }
@@ -221,6 +232,7 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaSetDevice(s->device));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e2 : s->ev) CK(cudaEventCreate(&e2));
+    CK(cudaEventCreateWithFlags(&s->sync_ev, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(k_tile_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
@@ -427,7 +439,10 @@ static void ensure_layout_ready(mqc_solver* s, int which) {
 }
 
 // ---------------------------------------------------------------------------------------
-// launch sequences
+// launch sequences.  Every evaluation is written for a GROUP of ranks: `L` is the handle the
+// caller holds; it drives L->members (all ranks in same-process mode, only itself otherwise).
+// Per-rank work is launched rank by rank on each rank's own stream; group_sync() orders the
+// ranks wherever one reads or writes another's shard.
 // ---------------------------------------------------------------------------------------
 static double binom(int n, int k) {
     if (k < 0 || k > n) return 0.0;
@@ -436,12 +451,53 @@ static double binom(int n, int k) {
     return r;
 }
 
+static void require_connected(mqc_solver* L) {
+    if (L->n_ranks > 1 && !L->connected)
+        throw MqcError("sharded handle is not connected: call mqc_shard_connect (or create it with mqc_shard_group_create)");
+}
+
+static void group_sync(mqc_solver* L) {
+    if (L->n_ranks == 1) return;
+    if (L->comm_mode == 1) {
+        for (mqc_solver* m : L->members) { CK(cudaSetDevice(m->device)); CK(cudaEventRecord(m->sync_ev, m->stream)); }
+        for (mqc_solver* m : L->members) {
+            CK(cudaSetDevice(m->device));
+            for (mqc_solver* q : L->members) if (q != m) CK(cudaStreamWaitEvent(m->stream, q->sync_ev, 0));
+        }
+    } else {
+        MqcFlags F{};
+        F.n_ranks = L->n_ranks; F.rank = L->rank;
+        for (int r = 0; r < L->n_ranks; ++r)
+            F.flags[r] = reinterpret_cast<unsigned long long*>(L->peer_mail[r] + MQC_MAIL_FLAGS);
+        ++L->epoch;
+        CK(cudaSetDevice(L->device));
+        k_rank_barrier<<<1, 32, 0, L->stream>>>(F, (unsigned long long)L->epoch, L->err.p);
+        L->counters[0]++;
+    }
+}
+
+static MqcPeers peers_of(const mqc_solver* s) {
+    MqcPeers R{};
+    for (int r = 0; r < s->n_ranks; ++r) { R.psi[r] = s->peer_psi[r]; R.lam[r] = s->peer_lam[r]; }
+    if (s->n_ranks == 1) { R.psi[0] = s->psi.p; R.lam[0] = s->lam.p; }
+    R.n_local = s->n_local;
+    R.tau_hi = 0; R.fixed_bits = (u64)s->rank << s->n_local;
+    return R;
+}
+
+static bool pass_is_global(const mqc_solver* s, int which, int pass) {
+    return s->n_global > 0 && (s->sched[which].passes[pass].act_mask >> s->n_local) != 0ull;
+}
+
 static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int reverse) {
     const MqcSchedule& S = s->sched[which];
     const MqcPass& P = S.passes[pass];
     const int nf = P.f1 - P.f0;
-    const unsigned grid = (unsigned)(s->dim >> P.k);
-    const u64 rank_bits = (u64)s->rank << s->n_local;
+    const MqcTileMap TM = mqc_tile_map(P, s->n, s->n_global, s->rank);
+    const unsigned grid = (unsigned)TM.n_tiles;
+    MqcPeers PR = peers_of(s);
+    PR.tau_hi = TM.tau_hi; PR.fixed_bits = TM.fixed_bits;
+    CK(cudaSetDevice(s->device));
     const bool sparse = s->conserving && s->use_sector && s->sparse_tiles;
     if (sparse) {
         // alpha = even qubits, beta = odd qubits.  Tile-local coordinates are those of the
@@ -464,8 +520,8 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
         while (nthr > 32 && nthr / 2 >= SP.cap) nthr >>= 1;
         const size_t smem = mqc_sparse_smem_bytes(P.k, SP.cap, adj);
         if (smem <= 200000) {
-            if (adj) k_tile_sparse<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n_local, reverse, SP, rank_bits);
-            else k_tile_sparse<false><<<grid, nthr, smem, s->stream>>>(s->psi.p, nullptr, P, s->tf[which].p, s->cs.p, nullptr, s->n_local, reverse, SP, rank_bits);
+            if (adj) k_tile_sparse<true><<<grid, nthr, smem, s->stream>>>(PR, P, s->tf[which].p, s->cs.p, s->grad_p(), reverse, SP);
+            else k_tile_sparse<false><<<grid, nthr, smem, s->stream>>>(PR, P, s->tf[which].p, s->cs.p, nullptr, reverse, SP);
             s->counters[0]++;
             return;
         }
@@ -476,30 +532,42 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
     const size_t smem = mqc_tile_smem_bytes(P.k, nf, adj, nthr);
     if (smem > 232448) throw MqcError("tile does not fit shared memory; lower tile_bits / grad_tile_bits");
     if (adj)
-        k_tile_sweep<true><<<grid, nthr, smem, s->stream>>>(s->psi.p, s->lam.p, P, s->tf[which].p, s->cs.p, s->grad.p, s->n_local, reverse, rank_bits);
+        k_tile_sweep<true><<<grid, nthr, smem, s->stream>>>(PR, P, s->tf[which].p, s->cs.p, s->grad_p(), reverse);
     else
-        k_tile_sweep<false><<<grid, nthr, smem, s->stream>>>(s->psi.p, nullptr, P, s->tf[which].p, s->cs.p, nullptr, s->n_local, reverse, rank_bits);
+        k_tile_sweep<false><<<grid, nthr, smem, s->stream>>>(PR, P, s->tf[which].p, s->cs.p, nullptr, reverse);
     s->counters[0]++;
 }
 
-static void forward(mqc_solver* s, int which, const double* theta) {
-    if (!s->have_ansatz) throw MqcError("mqc_set_ansatz has not been called");
-    if (s->n_global) throw MqcError("sharded handle: drive it through the mqc_shard_* entry points");
-    if (theta) {
-        s->theta_host.assign(theta, theta + s->n_theta);
-        CK(cudaMemcpyAsync(s->theta.p, theta, sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
+static void forward(mqc_solver* L, int which, const double* theta) {
+    if (!L->have_ansatz) throw MqcError("mqc_set_ansatz has not been called");
+    require_connected(L);
+    const int nfac = (int)L->fac.size();
+    for (mqc_solver* s : L->members) {
+        CK(cudaSetDevice(s->device));
+        if (theta) {
+            s->theta_host.assign(theta, theta + s->n_theta);
+            CK(cudaMemcpyAsync(s->theta.p, s->theta_host.data(), sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
+        }
+        if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->cs.p, nfac); s->counters[0]++; }
+        CK(cudaMemsetAsync(s->psi.p, 0, sizeof(double2) * s->dim, s->stream));
+        const u64 ref_phys = (s->mode == 1) ? mqc_map_mask(s->ref_index, s->sched[which].phys_init) : s->ref_index;
+        if ((int)(ref_phys >> s->n_local) == s->rank) {
+            k_set_amplitude<<<1, 32, 0, s->stream>>>(s->psi.p, ref_phys & (s->dim - 1ull), 1.0, 0.0);
+            s->counters[0]++;
+        }
     }
-    const int nfac = (int)s->fac.size();
-    if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->cs.p, nfac); s->counters[0]++; }
-    CK(cudaMemsetAsync(s->psi.p, 0, sizeof(double2) * s->dim, s->stream));
-    const u64 ref_phys = (s->mode == 1) ? mqc_map_mask(s->ref_index, s->sched[which].phys_init) : s->ref_index;
-    k_set_amplitude<<<1, 32, 0, s->stream>>>(s->psi.p, ref_phys, 1.0, 0.0);
-    s->counters[0]++;
-    if (s->mode == 1) {
-        const int np = (int)s->sched[which].passes.size();
-        for (int p = 0; p < np; ++p) launch_tile(s, which, p, false, 0);
-        s->counters[1] += np;
+    if (L->mode == 1) {
+        const int np = (int)L->sched[which].passes.size();
+        bool prev_g = false;
+        for (int p = 0; p < np; ++p) {
+            const bool g = pass_is_global(L, which, p);
+            if (g || prev_g) group_sync(L);
+            for (mqc_solver* s : L->members) launch_tile(s, which, p, false, 0);
+            prev_g = g;
+        }
+        L->counters[1] += np;
     } else {
+        mqc_solver* s = L;
         for (int k = 0; k < nfac; ++k) {
             const MqcFactor& F = s->fac[k];
             const u64 npairs = s->dim >> F.npos;
@@ -509,65 +577,129 @@ static void forward(mqc_solver* s, int which, const double* theta) {
         }
         s->counters[1] += nfac;
     }
-    s->state_layout = which;
+    group_sync(L);          // every shard complete before anyone reads a peer's
+    for (mqc_solver* s : L->members) s->state_layout = which;
 }
 
-static void happly(mqc_solver* s, int which, const HamTables& T, const SecHamTables* ST, double2* lam_out,
-                   double* host_val2) {
-    LayoutTables& L = s->lay[which];
-    const bool sec = s->conserving && s->use_sector && ST;
-    CK(cudaMemsetAsync(s->scalars.p, 0, 2 * sizeof(double), s->stream));
-    if (sec) {
-        const unsigned nA = (unsigned)L.astr.n, nB = (unsigned)L.bstr.n;
-        const u64 cnt = (u64)nA * nB;
-        if (s->csec.n < cnt) { s->csec.alloc(cnt); s->lsec.alloc(cnt); }
-        const unsigned gl = (unsigned)((cnt + 255) / 256);
-        k_sector_gather<<<gl, 256, 0, s->stream>>>(s->psi.p, s->csec.p, L.astr.p, L.bstr.p, nA, nB);
-        unsigned bd = 256;
-        while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
-        dim3 grid(nA, (nB + bd * MQC_HS_R - 1) / (bd * MQC_HS_R));
-        k_happly_sector<<<grid, bd, 0, s->stream>>>(s->csec.p, lam_out ? s->lsec.p : nullptr, sec_ham_dev(L, *ST), s->scalars.p);
-        s->counters[0] += 2;
-        if (lam_out) {
-            CK(cudaMemsetAsync(lam_out, 0, sizeof(double2) * s->dim, s->stream));
-            k_sector_scatter<<<gl, 256, 0, s->stream>>>(lam_out, s->lsec.p, L.astr.p, L.bstr.p, nA, nB);
+static void row_slice(const mqc_solver* s, unsigned n_rows, unsigned& r0, unsigned& r1) {
+    r0 = (unsigned)(((u64)n_rows * s->rank) / s->n_ranks);
+    r1 = (unsigned)(((u64)n_rows * (s->rank + 1)) / s->n_ranks);
+}
+
+// lambda = H psi (optional) and this group's energy partials in every member's scalars
+struct HamView { const HamTables* T; const SecHamTables* ST; };
+static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, bool want_lam) {
+    const bool sec = L->conserving && L->use_sector && views[0].ST;
+    for (size_t i = 0; i < L->members.size(); ++i) {
+        mqc_solver* s = L->members[i];
+        LayoutTables& Lt = s->lay[which];
+        CK(cudaSetDevice(s->device));
+        CK(cudaMemsetAsync(s->scalars_p(), 0, 4 * sizeof(double), s->stream));
+        const MqcPeers PR = peers_of(s);
+        if (sec) {
+            const unsigned nA = (unsigned)Lt.astr.n, nB = (unsigned)Lt.bstr.n;
+            const u64 cnt = (u64)nA * nB;
+            if (s->csec.n < cnt) { s->csec.alloc(cnt); s->lsec.alloc(cnt); }
+            const unsigned gl = (unsigned)((cnt + 255) / 256);
+            k_sector_gather<<<gl, 256, 0, s->stream>>>(PR, s->csec.p, Lt.astr.p, Lt.bstr.p, 0u, nA, nB);
+            unsigned r0, r1;
+            row_slice(s, nA, r0, r1);
+            if (r1 > r0) {
+                unsigned bd = 256;
+                while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
+                dim3 grid(r1 - r0, (nB + bd * MQC_HS_R - 1) / (bd * MQC_HS_R));
+                k_happly_sector<<<grid, bd, 0, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr,
+                                                            sec_ham_dev(Lt, *views[i].ST), s->scalars_p(), r0);
+            }
+            s->counters[0] += 2;
+            if (want_lam) CK(cudaMemsetAsync(s->lam.p, 0, sizeof(double2) * s->dim, s->stream));
+        } else {
+            MqcSectorDev S = sector_dev(Lt, false);
+            const unsigned grid = (unsigned)((s->dim + 255) / 256);
+            k_happly<<<grid, 256, 0, s->stream>>>(PR, want_lam ? s->lam.p : nullptr, views[i].T->dev(), S, s->dim,
+                                                  (u64)s->rank << s->n_local, s->scalars_p());
             s->counters[0]++;
         }
-    } else {
-        MqcSectorDev S = sector_dev(L, false);
-        const u64 count = s->dim;
-        const unsigned grid = (unsigned)((count + 255) / 256);
-        k_happly<<<grid, 256, 0, s->stream>>>(s->psi.p, lam_out, T.dev(), S, count, s->scalars.p);
-        s->counters[0]++;
     }
-    if (host_val2) {
-        CK(cudaMemcpyAsync(host_val2, s->scalars.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (sec && want_lam) {
+        group_sync(L);      // all shards of lambda cleared before rows are scattered into them
+        for (mqc_solver* s : L->members) {
+            LayoutTables& Lt = s->lay[which];
+            const unsigned nB = (unsigned)Lt.bstr.n;
+            unsigned r0, r1;
+            row_slice(s, (unsigned)Lt.astr.n, r0, r1);
+            if (r1 == r0) continue;
+            CK(cudaSetDevice(s->device));
+            const u64 cnt = (u64)(r1 - r0) * nB;
+            k_sector_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(peers_of(s), s->lsec.p, Lt.astr.p, Lt.bstr.p, r0, r1, nB);
+            s->counters[0]++;
+        }
     }
+    group_sync(L);
 }
 
-static void reverse_sweep(mqc_solver* s, int which) {
-    CK(cudaMemsetAsync(s->grad.p, 0, sizeof(double) * std::max(1, s->n_theta), s->stream));
-    const int nfac = (int)s->fac.size();
-    if (s->mode == 1) {
-        const int np = (int)s->sched[which].passes.size();
-        for (int p = np - 1; p >= 0; --p) launch_tile(s, which, p, true, 1);
-        s->counters[2] += np;
+static void reverse_sweep(mqc_solver* L, int which) {
+    for (mqc_solver* s : L->members) {
+        CK(cudaSetDevice(s->device));
+        CK(cudaMemsetAsync(s->grad_p(), 0, sizeof(double) * std::max(1, s->n_theta), s->stream));
+    }
+    const int nfac = (int)L->fac.size();
+    if (L->mode == 1) {
+        const int np = (int)L->sched[which].passes.size();
+        bool prev_g = false;
+        for (int p = np - 1; p >= 0; --p) {
+            const bool g = pass_is_global(L, which, p);
+            if (g || prev_g) group_sync(L);
+            for (mqc_solver* s : L->members) launch_tile(s, which, p, true, 1);
+            prev_g = g;
+        }
+        L->counters[2] += np;
     } else {
+        mqc_solver* s = L;
         for (int k = nfac - 1; k >= 0; --k) {
             const MqcFactor& F = s->fac[k];
             const u64 npairs = s->dim >> F.npos;
             const unsigned grid = (unsigned)std::min<u64>((npairs + 255) / 256, 148ull * 16);
-            k_adjoint_direct<<<grid, 256, 0, s->stream>>>(s->psi.p, s->lam.p, F, s->cs.p, s->grad.p, npairs);
+            k_adjoint_direct<<<grid, 256, 0, s->stream>>>(s->psi.p, s->lam.p, F, s->cs.p, s->grad_p(), npairs);
             s->counters[0]++;
         }
         s->counters[2] += nfac;
     }
-    s->state_layout = -1;
+    for (mqc_solver* s : L->members) s->state_layout = -1;
 }
 
-static void reset_counters(mqc_solver* s) {
-    s->counters[0] = s->counters[1] = s->counters[2] = 0;
-    s->ms[0] = s->ms[1] = s->ms[2] = s->ms[3] = 0;
+// Sum every rank's mail[0 .. count) into the leader's `red` buffer (all ranks do it for
+// themselves when each is its own process: an all-reduce over peer memory).
+static void reduce_mail(mqc_solver* L, int count) {
+    if (L->n_ranks == 1) return;
+    group_sync(L);
+    MqcSumPeers SP{};
+    SP.n_ranks = L->n_ranks;
+    for (int r = 0; r < L->n_ranks; ++r) SP.src[r] = L->peer_mail[r];
+    CK(cudaSetDevice(L->device));
+    if (L->red.n < (size_t)count) L->red.alloc(count);
+    k_sum_peers<<<(count + 255) / 256, 256, 0, L->stream>>>(SP, L->red.p, count);
+    L->counters[0]++;
+    group_sync(L);          // nobody clears its mail before every peer has read it
+}
+static const double* reduced_scalars(const mqc_solver* L) { return L->n_ranks == 1 ? L->scalars_p() : L->red.p; }
+static const double* reduced_grad(const mqc_solver* L) { return L->n_ranks == 1 ? L->grad_p() : L->red.p + MQC_MAIL_GRAD; }
+
+static void sync_all(mqc_solver* L) {
+    for (mqc_solver* s : L->members) { CK(cudaSetDevice(s->device)); CK(cudaStreamSynchronize(s->stream)); }
+    if (L->comm_mode == 2 && L->err.p) {
+        int e = 0;
+        CK(cudaMemcpy(&e, L->err.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) throw MqcError("rank barrier timed out: a peer rank is not making progress");
+    }
+    CK(cudaSetDevice(L->device));
+}
+
+static void reset_counters(mqc_solver* L) {
+    for (mqc_solver* s : L->members) {
+        s->counters[0] = s->counters[1] = s->counters[2] = 0;
+        s->ms[0] = s->ms[1] = s->ms[2] = s->ms[3] = 0;
+    }
 }
 
 static void finish_timing(mqc_solver* s, bool with_reverse) {
@@ -576,6 +708,46 @@ static void finish_timing(mqc_solver* s, bool with_reverse) {
     CK(cudaEventElapsedTime(&t, s->ev[1], s->ev[2])); s->ms[1] = t;
     if (with_reverse) { CK(cudaEventElapsedTime(&t, s->ev[2], s->ev[3])); s->ms[2] = t; }
     CK(cudaEventElapsedTime(&t, s->ev[0], with_reverse ? s->ev[3] : s->ev[2])); s->ms[3] = t;
+    for (size_t i = 1; i < s->members.size(); ++i) s->counters[0] += s->members[i]->counters[0];
+}
+
+static std::vector<HamView> own_views(mqc_solver* L, int which) {
+    std::vector<HamView> v;
+    for (mqc_solver* s : L->members) v.push_back(HamView{&s->lay[which].ham, &s->lay[which].sham});
+    return v;
+}
+
+static void alloc_state(mqc_solver* s, bool want_lam) {
+    CK(cudaSetDevice(s->device));
+    if (!s->psi.p) s->psi.alloc(s->dim);
+    if (want_lam && !s->lam.p) s->lam.alloc(s->dim);
+    if (s->n_ranks == 1) { s->peer_psi[0] = s->psi.p; s->peer_lam[0] = s->lam.p; }
+}
+
+// same-process group: every member sees every member's buffers (peer access across devices)
+static void connect_group(mqc_solver* L, bool want_lam) {
+    if (L->comm_mode != 1) return;
+    bool need = !L->connected;
+    for (mqc_solver* s : L->members) if (!s->psi.p || (want_lam && !s->lam.p)) need = true;
+    if (!need) return;
+    for (mqc_solver* s : L->members) alloc_state(s, want_lam);
+    for (mqc_solver* s : L->members) {
+        CK(cudaSetDevice(s->device));
+        for (mqc_solver* q : L->members) {
+            if (q->device != s->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, s->device, q->device));
+                if (!can) throw MqcError("GPUs of a shard group cannot access each other's memory");
+                cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cuda_check(e, "cudaDeviceEnablePeerAccess");
+                cudaGetLastError();
+            }
+            s->peer_psi[q->rank] = q->psi.p;
+            s->peer_lam[q->rank] = q->lam.p;
+            s->peer_mail[q->rank] = q->mail.p;
+        }
+        s->connected = true;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -584,7 +756,7 @@ static void finish_timing(mqc_solver* s, bool with_reverse) {
 extern "C" {
 
 const char* mqc_last_error(void) { return g_err.c_str(); }
-int mqc_version(void) { return 100; }
+int mqc_version(void) { return 110; }
 
 int mqc_device_count(int* count) {
     MQC_TRY
@@ -595,38 +767,80 @@ int mqc_device_count(int* count) {
     MQC_CATCH
 }
 
+static mqc_solver* new_rank(int n_qubits, int device, int rank, int n_ranks) {
+    if (n_qubits < 2 || n_qubits > 40) throw MqcError("n_qubits must be in [2, 40]");
+    if (n_ranks < 1 || n_ranks > MQC_MAX_RANKS || (n_ranks & (n_ranks - 1))) throw MqcError("n_ranks must be 1, 2, 4 or 8");
+    if (rank < 0 || rank >= n_ranks) throw MqcError("rank out of range");
+    int g = 0;
+    while ((1 << g) < n_ranks) ++g;
+    if (n_qubits - g < 5) throw MqcError("too few qubits per shard");
+    mqc_solver* s = new mqc_solver();
+    s->n = n_qubits;
+    s->n_global = g;
+    s->n_local = n_qubits - g;
+    s->rank = rank;
+    s->n_ranks = n_ranks;
+    s->device = device;
+    s->dim = 1ull << s->n_local;
+    s->members.push_back(s);
+    return s;
+}
+
 int mqc_create(int n_qubits, int device, mqc_solver_t** out) {
     MQC_TRY
     if (!out) throw MqcError("null argument");
-    if (n_qubits < 2 || n_qubits > 40) throw MqcError("n_qubits must be in [2, 40]");
-    mqc_solver* s = new mqc_solver();
-    s->n = n_qubits;
-    s->n_local = n_qubits;
-    s->device = device;
-    s->dim = 1ull << n_qubits;
+    *out = new_rank(n_qubits, device, 0, 1);
+    MQC_CATCH
+}
+
+int mqc_shard_create(int n_qubits, int device, int rank, int n_ranks, mqc_solver_t** out) {
+    MQC_TRY
+    if (!out) throw MqcError("null argument");
+    mqc_solver* s = new_rank(n_qubits, device, rank, n_ranks);
+    s->comm_mode = n_ranks > 1 ? 2 : 0;
     *out = s;
     MQC_CATCH
+}
+
+int mqc_shard_group_create(int n_qubits, int n_ranks, const int* devices, mqc_solver_t** out) {
+    MQC_TRY
+    if (!out || !devices) throw MqcError("null argument");
+    mqc_solver* L = new_rank(n_qubits, devices[0], 0, n_ranks);
+    L->comm_mode = n_ranks > 1 ? 1 : 0;
+    for (int r = 1; r < n_ranks; ++r) {
+        mqc_solver* m = new_rank(n_qubits, devices[r], r, n_ranks);
+        m->comm_mode = 1;
+        L->members.push_back(m);
+    }
+    *out = L;
+    MQC_CATCH
+}
+
+static void destroy_rank(mqc_solver* s) {
+    if (s->gpu_ready) {
+        cudaSetDevice(s->device);
+        cudaStreamSynchronize(s->stream);
+        for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+        for (auto& e : s->user_ev) if (e) cudaEventDestroy(e);
+        if (s->sync_ev) cudaEventDestroy(s->sync_ev);
+        for (auto& kv : s->ipc_open) cudaIpcCloseMemHandle(kv.second);
+    }
+    cudaStream_t st = s->stream;
+    const bool ready = s->gpu_ready;
+    const int dev = s->device;
+    delete s;
+    if (ready && st) { cudaSetDevice(dev); cudaStreamDestroy(st); }
 }
 
 int mqc_destroy(mqc_solver_t* s) {
     MQC_TRY
     if (!s) return 0;
-    if (s->gpu_ready) {
-        cudaSetDevice(s->device);
-        cudaStreamSynchronize(s->stream);
-        for (auto& e : s->ev) if (e) cudaEventDestroy(e);
-    }
-    cudaStream_t st = s->stream;
-    bool ready = s->gpu_ready;
-    delete s;
-    if (ready && st) cudaStreamDestroy(st);
+    std::vector<mqc_solver*> m = s->members;
+    for (size_t i = m.size(); i-- > 0;) destroy_rank(m[i]);
     MQC_CATCH
 }
 
-int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value) {
-    MQC_TRY
-    if (!s || !key) throw MqcError("null argument");
-    const std::string k(key);
+static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) {
     if (k == "tile_bits") s->tile_bits = (int)value;
     else if (k == "low_bits") s->low_bits = (int)value;
     else if (k == "grad_tile_bits") s->grad_tile_bits = (int)value;
@@ -643,72 +857,82 @@ int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value) {
         throw MqcError("tile_threads must be a power of two in [32,512]");
     if (s->sparse_threads < 32 || s->sparse_threads > 256 || (s->sparse_threads & (s->sparse_threads - 1)))
         throw MqcError("sparse_threads must be a power of two in [32,256]");
+}
+
+int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value) {
+    MQC_TRY
+    if (!s || !key) throw MqcError("null argument");
+    for (mqc_solver* m : s->members) set_option_rank(m, key, value);
     MQC_CATCH
 }
 
-int mqc_set_hamiltonian(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask, const uint64_t* zmask,
+int mqc_set_hamiltonian(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask, const uint64_t* zmask,
                         const double* coeff_re, const double* coeff_im) {
     MQC_TRY
-    if (!s || n_terms < 0 || (n_terms && (!xmask || !zmask || !coeff_re))) throw MqcError("bad arguments");
-    const u64 lim = (s->n >= 64) ? ~0ull : ((1ull << s->n) - 1ull);
-    s->ham.x.assign(xmask, xmask + n_terms);
-    s->ham.z.assign(zmask, zmask + n_terms);
-    s->ham.c.resize(n_terms);
-    for (int64_t t = 0; t < n_terms; ++t) {
+    if (!L || n_terms < 0 || (n_terms && (!xmask || !zmask || !coeff_re))) throw MqcError("bad arguments");
+    const u64 lim = (1ull << L->n) - 1ull;
+    for (int64_t t = 0; t < n_terms; ++t)
         if ((xmask[t] | zmask[t]) & ~lim) throw MqcError("Pauli mask outside the register");
-        s->ham.c[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
+    for (mqc_solver* s : L->members) {
+        s->ham.x.assign(xmask, xmask + n_terms);
+        s->ham.z.assign(zmask, zmask + n_terms);
+        s->ham.c.resize(n_terms);
+        for (int64_t t = 0; t < n_terms; ++t) s->ham.c[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
+        s->have_ham = true;
+        s->lay[0].ham_ready = s->lay[1].ham_ready = false;
+        s->lay[0].sham_ready = s->lay[1].sham_ready = false;
     }
-    s->have_ham = true;
-    s->lay[0].ham_ready = s->lay[1].ham_ready = false;
-    s->lay[0].sham_ready = s->lay[1].sham_ready = false;
     MQC_CATCH
 }
 
-int mqc_set_ansatz(mqc_solver_t* s, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
-                   const int32_t* theta_index, int32_t n_theta, uint64_t ref_index) {
-    MQC_TRY
-    if (!s || n_factors < 0 || n_theta < 0 || (n_factors && (!kind || !idx4 || !theta_index)))
-        throw MqcError("bad arguments");
-    if (ref_index >> s->n) throw MqcError("reference index outside the register");
-    if (s->n_global && s->mode != 1) throw MqcError("a sharded state needs mode = 1 (tile sweep)");
+static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
+                            const int32_t* theta_index, int32_t n_theta, uint64_t ref_index, const mqc_solver* copy_from) {
     const int n = s->n;
-    std::vector<MqcFactor> fac;
-    fac.reserve(n_factors);
-    bool conserving = (n % 2 == 0);
-    for (int k = 0; k < n_factors; ++k) {
-        if (theta_index[k] < 0 || theta_index[k] >= n_theta) throw MqcError("theta_index out of range");
-        fac.push_back(make_factor(n, kind[k], idx4 + 4 * k, k, theta_index[k]));
-        const int32_t* ix = idx4 + 4 * k;
-        if (kind[k] == 1) { if ((ix[0] ^ ix[1]) & 1) conserving = false; }
-        else {
-            const int sa = (ix[0] & 1) + (ix[1] & 1), sc = (ix[2] & 1) + (ix[3] & 1);
-            if (sa != sc) conserving = false;
+    if (copy_from) {
+        s->fac = copy_from->fac; s->conserving = copy_from->conserving;
+        s->sched[0] = copy_from->sched[0]; s->sched[1] = copy_from->sched[1];
+    } else {
+        std::vector<MqcFactor> fac;
+        fac.reserve(n_factors);
+        bool conserving = (n % 2 == 0);
+        for (int k = 0; k < n_factors; ++k) {
+            if (theta_index[k] < 0 || theta_index[k] >= n_theta) throw MqcError("theta_index out of range");
+            fac.push_back(make_factor(n, kind[k], idx4 + 4 * k, k, theta_index[k]));
+            const int32_t* ix = idx4 + 4 * k;
+            if (kind[k] == 1) { if ((ix[0] ^ ix[1]) & 1) conserving = false; }
+            else {
+                const int sa = (ix[0] & 1) + (ix[1] & 1), sc = (ix[2] & 1) + (ix[3] & 1);
+                if (sa != sc) conserving = false;
+            }
+        }
+        s->fac = fac;
+        s->conserving = conserving;
+        // schedules: 0 = energy-only, 1 = energy + gradient
+        for (int w = 0; w < 2; ++w) {
+            const int kb = (w == 0) ? s->tile_bits : s->grad_tile_bits;
+            if (s->mode == 1) {
+                s->sched[w] = mqc_build_schedule(n, kb, s->low_bits, s->fac, MQC_MAX_PASS_FACTORS, s->n_global);
+            } else {
+                s->sched[w] = MqcSchedule();
+                s->sched[w].n_bits = n;
+                s->sched[w].phys_final.resize(n);
+                std::iota(s->sched[w].phys_final.begin(), s->sched[w].phys_final.end(), 0);
+                s->sched[w].phys_init = s->sched[w].phys_final;
+            }
         }
     }
-    s->fac = fac;
     s->n_theta = n_theta;
     s->ref_index = ref_index;
-    s->conserving = conserving;
     s->na = s->nb = 0;
     for (int q = 0; q < n; ++q)
         if ((ref_index >> (n - 1 - q)) & 1ull) { if (q & 1) s->nb++; else s->na++; }
-    // schedules: 0 = energy-only, 1 = energy + gradient
     for (int w = 0; w < 2; ++w) {
-        const int kb = (w == 0) ? s->tile_bits : s->grad_tile_bits;
-        if (s->mode == 1) {
-            s->sched[w] = mqc_build_schedule(n, kb, s->low_bits, fac, MQC_MAX_PASS_FACTORS, s->n_global);
-        } else {
-            s->sched[w] = MqcSchedule();
-            s->sched[w].n_bits = n;
-            s->sched[w].phys_final.resize(n);
-            std::iota(s->sched[w].phys_final.begin(), s->sched[w].phys_final.end(), 0);
-            s->sched[w].phys_init = s->sched[w].phys_final;
-        }
         s->lay[w].reset();
         s->lay[w].phys = s->sched[w].phys_final;
     }
     s->have_ansatz = true;
     s->state_layout = -1;
+    s->connected = (s->n_ranks == 1);
     // device side is set up lazily so that schedules can be inspected without a GPU
     int cnt = 0;
     if (cudaGetDeviceCount(&cnt) == cudaSuccess && cnt > 0) {
@@ -717,19 +941,113 @@ int mqc_set_ansatz(mqc_solver_t* s, int32_t n_factors, const int32_t* kind, cons
         for (int k = 0; k < n_factors; ++k) ti[k] = theta_index[k];
         s->theta_index.upload(ti, s->stream);
         s->theta.alloc(std::max(1, n_theta));
-        s->grad.alloc(std::max(1, n_theta));
+        s->mail.alloc(MQC_MAIL_GRAD + std::max(1, n_theta));
+        CK(cudaMemsetAsync(s->mail.p, 0, sizeof(double) * s->mail.n, s->stream));
+        s->err.alloc(1);
+        CK(cudaMemsetAsync(s->err.p, 0, sizeof(int), s->stream));
+        s->epoch = 0;
         s->cs.alloc(std::max(1, n_factors));
-        s->scalars.alloc(4);
         for (int w = 0; w < 2; ++w) {
             s->tf[w].upload(s->sched[w].tf, s->stream);
             std::vector<int> ph = s->lay[w].phys;
             s->lay[w].phys_dev.upload(ph, s->stream);
         }
-        if (!s->psi.p) s->psi.alloc(s->dim);
+        if (s->n_ranks == 1) alloc_state(s, false);
         CK(cudaStreamSynchronize(s->stream));
     } else {
         cudaGetLastError();
     }
+}
+
+int mqc_set_ansatz(mqc_solver_t* L, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
+                   const int32_t* theta_index, int32_t n_theta, uint64_t ref_index) {
+    MQC_TRY
+    if (!L || n_factors < 0 || n_theta < 0 || (n_factors && (!kind || !idx4 || !theta_index)))
+        throw MqcError("bad arguments");
+    if (ref_index >> L->n) throw MqcError("reference index outside the register");
+    if (L->n_ranks > 1 && L->mode != 1) throw MqcError("a sharded state needs mode = 1 (tile sweep)");
+    for (size_t i = 0; i < L->members.size(); ++i)
+        set_ansatz_rank(L->members[i], n_factors, kind, idx4, theta_index, n_theta, ref_index, i ? L : nullptr);
+    MQC_CATCH
+}
+
+// ---- one process per GPU: CUDA IPC exchange of the shard buffers --------------------------
+struct BlobEntry { cudaIpcMemHandle_t h; unsigned long long offset; unsigned long long valid; };
+
+typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
+static void base_of(void* p, void** base, size_t* off) {
+    static cuMemGetAddressRange_t fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &qr));
+        if (!f) throw MqcError("cuMemGetAddressRange is not available");
+        fn = (cuMemGetAddressRange_t)f;
+    }
+    unsigned long long b = 0; size_t sz = 0;
+    if (fn(&b, &sz, (unsigned long long)(uintptr_t)p) != 0) throw MqcError("cuMemGetAddressRange failed");
+    *base = (void*)(uintptr_t)b;
+    *off = (size_t)((uintptr_t)p - (uintptr_t)b);
+}
+
+int mqc_shard_export(mqc_solver_t* s, int32_t want_lambda, void* blob, int64_t blob_bytes) {
+    MQC_TRY
+    require_gpu(s);
+    if (!blob || blob_bytes < MQC_BLOB_BYTES) throw MqcError("blob must hold MQC_SHARD_BLOB_BYTES bytes");
+    if (s->comm_mode != 2) throw MqcError("not a per-process shard handle (mqc_shard_create with n_ranks > 1)");
+    if (!s->have_ansatz) throw MqcError("call mqc_set_ansatz before mqc_shard_export");
+    alloc_state(s, want_lambda != 0);
+    CK(cudaStreamSynchronize(s->stream));
+    BlobEntry e[3];
+    std::memset(e, 0, sizeof(e));
+    void* ptrs[3] = {s->psi.p, s->lam.p, s->mail.p};
+    for (int i = 0; i < 3; ++i) {
+        if (!ptrs[i]) continue;
+        void* base; size_t off;
+        base_of(ptrs[i], &base, &off);
+        CK(cudaIpcGetMemHandle(&e[i].h, base));
+        e[i].offset = off; e[i].valid = 1;
+    }
+    std::memset(blob, 0, MQC_BLOB_BYTES);
+    std::memcpy(blob, e, sizeof(e));
+    MQC_CATCH
+}
+
+int mqc_shard_connect(mqc_solver_t* s, const void* blobs, int64_t blobs_bytes) {
+    MQC_TRY
+    require_gpu(s);
+    if (s->comm_mode != 2) throw MqcError("not a per-process shard handle");
+    if (!blobs || blobs_bytes < (int64_t)MQC_BLOB_BYTES * s->n_ranks) throw MqcError("need one blob per rank");
+    for (int r = 0; r < s->n_ranks; ++r) {
+        if (r == s->rank) { s->peer_psi[r] = s->psi.p; s->peer_lam[r] = s->lam.p; s->peer_mail[r] = s->mail.p; continue; }
+        BlobEntry e[3];
+        std::memcpy(e, (const char*)blobs + (size_t)r * MQC_BLOB_BYTES, sizeof(e));
+        void* out[3] = {nullptr, nullptr, nullptr};
+        for (int i = 0; i < 3; ++i) {
+            if (!e[i].valid) continue;
+            const std::string key((const char*)&e[i].h, sizeof(cudaIpcMemHandle_t));
+            void* base = nullptr;
+            for (auto& kv : s->ipc_open) if (kv.first == key) base = kv.second;
+            if (!base) {
+                CK(cudaIpcOpenMemHandle(&base, e[i].h, cudaIpcMemLazyEnablePeerAccess));
+                s->ipc_open.emplace_back(key, base);
+            }
+            out[i] = (char*)base + e[i].offset;
+        }
+        s->peer_psi[r] = (double2*)out[0]; s->peer_lam[r] = (double2*)out[1]; s->peer_mail[r] = (double*)out[2];
+        if (!out[0] || !out[2]) throw MqcError("peer blob is incomplete");
+    }
+    s->connected = true;
+    MQC_CATCH
+}
+
+int mqc_shard_info(mqc_solver_t* s, int32_t* rank, int32_t* n_ranks, int32_t* n_local_bits, int32_t* members) {
+    MQC_TRY
+    if (!s) throw MqcError("null solver handle");
+    if (rank) *rank = s->rank;
+    if (n_ranks) *n_ranks = s->n_ranks;
+    if (n_local_bits) *n_local_bits = s->n_local;
+    if (members) *members = (int32_t)s->members.size();
     MQC_CATCH
 }
 
@@ -738,8 +1056,9 @@ int mqc_prepare(mqc_solver_t* s, const double* theta) {
     require_gpu(s);
     if (!theta) throw MqcError("null theta");
     reset_counters(s);
+    connect_group(s, false);
     forward(s, 0, theta);
-    CK(cudaStreamSynchronize(s->stream));
+    sync_all(s);
     MQC_CATCH
 }
 
@@ -748,14 +1067,20 @@ int mqc_energy(mqc_solver_t* s, const double* theta, double* energy) {
     require_gpu(s);
     if (!theta || !energy) throw MqcError("null argument");
     reset_counters(s);
-    ensure_layout_ready(s, 0);
+    connect_group(s, false);
+    for (mqc_solver* m : s->members) ensure_layout_ready(m, 0);
     double val[2] = {0, 0};
+    CK(cudaSetDevice(s->device));
     CK(cudaEventRecord(s->ev[0], s->stream));
     forward(s, 0, theta);
+    CK(cudaSetDevice(s->device));
     CK(cudaEventRecord(s->ev[1], s->stream));
-    happly(s, 0, s->lay[0].ham, &s->lay[0].sham, nullptr, val);
+    happly(s, 0, own_views(s, 0), false);
+    reduce_mail(s, 4);
+    CK(cudaSetDevice(s->device));
     CK(cudaEventRecord(s->ev[2], s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    CK(cudaMemcpyAsync(val, reduced_scalars(s), 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    sync_all(s);
     finish_timing(s, false);
     *energy = val[0];
     MQC_CATCH
@@ -763,19 +1088,25 @@ int mqc_energy(mqc_solver_t* s, const double* theta, double* energy) {
 
 static void run_energy_grad(mqc_solver* s, const double* theta, double* energy, double* grad) {
     reset_counters(s);
-    ensure_layout_ready(s, 1);
-    if (!s->lam.p) s->lam.alloc(s->dim);
+    connect_group(s, true);
+    for (mqc_solver* m : s->members) { ensure_layout_ready(m, 1); if (!m->lam.p) { if (m->n_ranks > 1) throw MqcError("sharded handle was exported without lambda"); alloc_state(m, true); } }
     double val[2] = {0, 0};
+    CK(cudaSetDevice(s->device));
     CK(cudaEventRecord(s->ev[0], s->stream));
     forward(s, 1, theta);
+    CK(cudaSetDevice(s->device));
     CK(cudaEventRecord(s->ev[1], s->stream));
-    happly(s, 1, s->lay[1].ham, &s->lay[1].sham, s->lam.p, val);
+    happly(s, 1, own_views(s, 1), true);
+    CK(cudaSetDevice(s->device));
     CK(cudaEventRecord(s->ev[2], s->stream));
     reverse_sweep(s, 1);
+    reduce_mail(s, MQC_MAIL_GRAD + s->n_theta);
+    CK(cudaSetDevice(s->device));
     CK(cudaEventRecord(s->ev[3], s->stream));
+    CK(cudaMemcpyAsync(val, reduced_scalars(s), 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (grad && s->n_theta)
-        CK(cudaMemcpyAsync(grad, s->grad.p, sizeof(double) * s->n_theta, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+        CK(cudaMemcpyAsync(grad, reduced_grad(s), sizeof(double) * s->n_theta, cudaMemcpyDeviceToHost, s->stream));
+    sync_all(s);
     finish_timing(s, true);
     *energy = val[0];
 }
@@ -819,16 +1150,18 @@ int mqc_event_elapsed_ms(mqc_solver_t* s, double* ms) {
 }
 
 static void ensure_state(mqc_solver* s, const double* theta) {
-    if (theta) { forward(s, 0, theta); return; }
+    if (theta) { connect_group(s, false); forward(s, 0, theta); return; }
     if (s->state_layout >= 0) return;
     if ((int)s->theta_host.size() != s->n_theta || !s->have_ansatz) throw MqcError("no prepared state: pass theta");
     std::vector<double> th = s->theta_host;
+    connect_group(s, false);
     forward(s, 0, th.data());
 }
 
 int mqc_state(mqc_solver_t* s, const double* theta, double* re_im, int64_t n_amplitudes) {
     MQC_TRY
     require_gpu(s);
+    if (s->n_ranks > 1) throw MqcError("mqc_state needs an unsharded handle: read shards with mqc_shard_read");
     if (!re_im || (u64)n_amplitudes != s->dim) throw MqcError("state buffer must hold 2^N amplitudes");
     reset_counters(s);
     ensure_state(s, theta);
@@ -841,62 +1174,103 @@ int mqc_state(mqc_solver_t* s, const double* theta, double* re_im, int64_t n_amp
     MQC_CATCH
 }
 
-int mqc_expectation(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask, const uint64_t* zmask,
+int mqc_shard_read(mqc_solver_t* L, const double* theta, int32_t member, double* re_im, int64_t n_amplitudes,
+                   int32_t* phys_of_logical) {
+    MQC_TRY
+    require_gpu(L);
+    if (member < 0 || member >= (int)L->members.size()) throw MqcError("member out of range");
+    mqc_solver* s = L->members[member];
+    if (!re_im || (u64)n_amplitudes != s->dim) throw MqcError("shard buffer must hold 2^n_local amplitudes");
+    ensure_state(L, theta);
+    sync_all(L);
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemcpy(re_im, s->psi.p, sizeof(double2) * s->dim, cudaMemcpyDeviceToHost));
+    if (phys_of_logical) for (int l = 0; l < s->n; ++l) phys_of_logical[l] = s->lay[s->state_layout].phys[l];
+    CK(cudaSetDevice(L->device));
+    MQC_CATCH
+}
+
+int mqc_expectation(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask, const uint64_t* zmask,
                     const double* coeff_re, const double* coeff_im, double* value_re, double* value_im) {
     MQC_TRY
-    require_gpu(s);
+    require_gpu(L);
     if (n_terms < 0 || (n_terms && (!xmask || !zmask || !coeff_re)) || !value_re) throw MqcError("bad arguments");
-    ensure_state(s, nullptr);
-    const int w = s->state_layout;
+    ensure_state(L, nullptr);
+    const int w = L->state_layout;
     HamHost H;
     H.x.assign(xmask, xmask + n_terms);
     H.z.assign(zmask, zmask + n_terms);
     H.c.resize(n_terms);
     for (int64_t t = 0; t < n_terms; ++t) H.c[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
-    HamTables T;
-    SecHamTables ST;
-    const bool sec = s->conserving && s->use_sector;
-    if (sec) { build_sector_tables(s, s->lay[w], s->na, s->nb); build_sec_ham(s, H, s->lay[w].phys, ST); }
-    else build_ham_tables(s, H, s->lay[w].phys, T);
+    const bool sec = L->conserving && L->use_sector;
+    const size_t nm = L->members.size();
+    std::vector<HamTables> T(nm);
+    std::vector<SecHamTables> ST(nm);
+    std::vector<HamView> views;
+    for (size_t i = 0; i < nm; ++i) {
+        mqc_solver* s = L->members[i];
+        CK(cudaSetDevice(s->device));
+        if (sec) { build_sector_tables(s, s->lay[w], s->na, s->nb); build_sec_ham(s, H, s->lay[w].phys, ST[i]); }
+        else build_ham_tables(s, H, s->lay[w].phys, T[i]);
+        views.push_back(HamView{&T[i], sec ? &ST[i] : nullptr});
+    }
     double val[2] = {0, 0};
-    happly(s, w, T, sec ? &ST : nullptr, nullptr, val);
-    CK(cudaStreamSynchronize(s->stream));
+    happly(L, w, views, false);
+    reduce_mail(L, 4);
+    CK(cudaSetDevice(L->device));
+    CK(cudaMemcpyAsync(val, reduced_scalars(L), 2 * sizeof(double), cudaMemcpyDeviceToHost, L->stream));
+    sync_all(L);
     *value_re = val[0];
     if (value_im) *value_im = val[1];
     MQC_CATCH
 }
 
-int mqc_rdm12(mqc_solver_t* s, int32_t n_orb, int32_t n_alpha, int32_t n_beta, double* rdm1, double* rdm2) {
+// RDMs of this handle's ranks (every rank of the group when they share the process; this
+// rank's partial sums when each rank is its own process: the host adds them up)
+int mqc_rdm12(mqc_solver_t* L, int32_t n_orb, int32_t n_alpha, int32_t n_beta, double* rdm1, double* rdm2) {
     MQC_TRY
-    require_gpu(s);
+    require_gpu(L);
     if (!rdm1) throw MqcError("null rdm1");
-    if (2 * n_orb != s->n) throw MqcError("n_orb must be n_qubits / 2");
-    ensure_state(s, nullptr);
-    const int w = s->state_layout;
-    LayoutTables& L = s->lay[w];
-    build_sector_tables(s, L, n_alpha, n_beta);
-    MqcSectorDev S = sector_dev(L, true);
-    const u64 count = (u64)L.astr.n * (u64)L.bstr.n;
+    if (2 * n_orb != L->n) throw MqcError("n_orb must be n_qubits / 2");
+    ensure_state(L, nullptr);
+    sync_all(L);
+    const int w = L->state_layout;
     const size_t n2 = (size_t)n_orb * n_orb, n4 = n2 * n2;
     const int copies = 8;
-    MqcRdmDev R{n_orb, L.qbit.p, L.below.p, copies};
-    const size_t need = (size_t)copies * (rdm2 ? n4 : n2);
-    if (s->rdm_acc.n < need) s->rdm_acc.alloc(need);
-    CK(cudaMemsetAsync(s->rdm_acc.p, 0, sizeof(double) * (size_t)copies * n2, s->stream));
-    k_rdm1<<<(unsigned)((count + 127) / 128), 128, 0, s->stream>>>(s->psi.p, S, R, count, s->rdm_acc.p);
-    k_reduce_copies<<<(unsigned)((n2 + 255) / 256), 256, 0, s->stream>>>(s->rdm_acc.p, n2, copies);
-    CK(cudaMemcpyAsync(rdm1, s->rdm_acc.p, sizeof(double) * n2, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    if (rdm2) {
-        CK(cudaMemsetAsync(s->rdm_acc.p, 0, sizeof(double) * (size_t)copies * n4, s->stream));
-        const u64 work = count * (u64)(2 * n_orb);
-        k_rdm2<<<(unsigned)((work + 127) / 128), 128, 0, s->stream>>>(s->psi.p, S, R, count, s->rdm_acc.p);
-        k_reduce_copies<<<(unsigned)((n4 + 255) / 256), 256, 0, s->stream>>>(s->rdm_acc.p, n4, copies);
-        CK(cudaMemcpyAsync(rdm2, s->rdm_acc.p, sizeof(double) * n4, cudaMemcpyDeviceToHost, s->stream));
+    std::vector<double> acc1(n2, 0.0), acc2(rdm2 ? n4 : 0, 0.0), tmp(rdm2 ? n4 : n2);
+    for (mqc_solver* s : L->members) {
+        CK(cudaSetDevice(s->device));
+        LayoutTables& Lt = s->lay[w];
+        build_sector_tables(s, Lt, n_alpha, n_beta);
+        MqcSectorDev S = sector_dev(Lt, true);
+        const u64 count = (u64)Lt.astr.n * (u64)Lt.bstr.n;
+        const u64 d0 = count * s->rank / s->n_ranks, d1 = count * (s->rank + 1) / s->n_ranks;
+        MqcRdmDev R{n_orb, Lt.qbit.p, Lt.below.p, copies};
+        const size_t need = (size_t)copies * (rdm2 ? n4 : n2);
+        if (s->rdm_acc.n < need) s->rdm_acc.alloc(need);
+        const MqcPeers PR = peers_of(s);
+        CK(cudaMemsetAsync(s->rdm_acc.p, 0, sizeof(double) * (size_t)copies * n2, s->stream));
+        if (d1 > d0) k_rdm1<<<(unsigned)((d1 - d0 + 127) / 128), 128, 0, s->stream>>>(PR, S, R, d0, d1, s->rdm_acc.p);
+        k_reduce_copies<<<(unsigned)((n2 + 255) / 256), 256, 0, s->stream>>>(s->rdm_acc.p, n2, copies);
+        CK(cudaMemcpyAsync(tmp.data(), s->rdm_acc.p, sizeof(double) * n2, cudaMemcpyDeviceToHost, s->stream));
         CK(cudaStreamSynchronize(s->stream));
+        for (size_t i = 0; i < n2; ++i) acc1[i] += tmp[i];
+        if (rdm2) {
+            CK(cudaMemsetAsync(s->rdm_acc.p, 0, sizeof(double) * (size_t)copies * n4, s->stream));
+            const u64 work = (d1 - d0) * (u64)(2 * n_orb);
+            if (work) k_rdm2<<<(unsigned)((work + 127) / 128), 128, 0, s->stream>>>(PR, S, R, d0, d1, s->rdm_acc.p);
+            k_reduce_copies<<<(unsigned)((n4 + 255) / 256), 256, 0, s->stream>>>(s->rdm_acc.p, n4, copies);
+            CK(cudaMemcpyAsync(tmp.data(), s->rdm_acc.p, sizeof(double) * n4, cudaMemcpyDeviceToHost, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+            for (size_t i = 0; i < n4; ++i) acc2[i] += tmp[i];
+        }
+        // the sector tables of this layout may now be for a different (na, nb) than the ansatz's
+        if (s->conserving && s->use_sector && (n_alpha != s->na || n_beta != s->nb)) build_sector_tables(s, Lt, s->na, s->nb);
     }
-    // the sector tables of this layout may now be for a different (na, nb) than the ansatz's
-    if (s->conserving && s->use_sector && (n_alpha != s->na || n_beta != s->nb)) build_sector_tables(s, L, s->na, s->nb);
+    std::memcpy(rdm1, acc1.data(), sizeof(double) * n2);
+    if (rdm2) std::memcpy(rdm2, acc2.data(), sizeof(double) * n4);
+    group_sync(L);          // no rank re-prepares its shard while a peer still reads it
+    sync_all(L);
     MQC_CATCH
 }
 
@@ -908,7 +1282,7 @@ int mqc_last_timing(mqc_solver_t* s, double* ms4, int64_t* counters3) {
     MQC_CATCH
 }
 
-int mqc_schedule_info(mqc_solver_t* s, int32_t which, int32_t* n_passes, int32_t* tile_bits, int32_t* n_tile_factors) {
+int mqc_schedule_info(mqc_solver_t* s, int32_t which /*0 energy, 1 gradient*/, int32_t* n_passes, int32_t* tile_bits, int32_t* n_tile_factors) {
     MQC_TRY
     if (!s || which < 0 || which > 1 || !s->have_ansatz) throw MqcError("no schedule");
     if (n_passes) *n_passes = (int32_t)s->sched[which].passes.size();
@@ -930,6 +1304,20 @@ int mqc_schedule_pass(mqc_solver_t* s, int32_t which, int32_t pass, int32_t* fir
     if (pos16) for (int j = 0; j < 16; ++j) pos16[j] = j < P.k ? P.pos[j] : -1;
     if (perm16) for (int j = 0; j < 16; ++j) perm16[j] = j < P.k ? P.perm[j] : -1;
     if (has_perm) *has_perm = P.has_perm;
+    MQC_CATCH
+}
+
+int mqc_schedule_tile_map(mqc_solver_t* s, int32_t which, int32_t pass, int32_t rank, uint64_t* tau_hi,
+                          uint64_t* fixed_bits, uint64_t* n_tiles) {
+    MQC_TRY
+    if (!s || which < 0 || which > 1 || !s->have_ansatz) throw MqcError("no schedule");
+    const MqcSchedule& S = s->sched[which];
+    if (pass < 0 || pass >= (int)S.passes.size()) throw MqcError("pass out of range");
+    if (rank < 0 || rank >= s->n_ranks) throw MqcError("rank out of range");
+    const MqcTileMap M = mqc_tile_map(S.passes[pass], s->n, s->n_global, rank);
+    if (tau_hi) *tau_hi = M.tau_hi;
+    if (fixed_bits) *fixed_bits = M.fixed_bits;
+    if (n_tiles) *n_tiles = M.n_tiles;
     MQC_CATCH
 }
 

@@ -31,6 +31,25 @@ struct MqcHamDev {
     const double2* tc;         // [T] coefficient
 };
 
+// Shards of the state.  The top physical index bits select the rank; every
+// rank maps all peers' shards (same process: peer access; one process per GPU: CUDA IPC), so
+// a physical index resolves to (peer pointer, local offset) and a tile whose active bits
+// include rank bits is loaded from / stored to the peers' HBM directly over NVLink.
+#define MQC_MAX_RANKS 8
+struct MqcPeers {
+    double2* psi[MQC_MAX_RANKS];
+    double2* lam[MQC_MAX_RANKS];
+    int n_local;               // address bits inside one shard
+    u64 tau_hi;                // this rank's share of the pass's tiles (mqc_tile_map)
+    u64 fixed_bits;            // rank bits at inactive global positions
+};
+__device__ __forceinline__ double2* peer_psi(const MqcPeers& R, u64 g) {
+    return R.psi[g >> R.n_local] + (g & ((1ull << R.n_local) - 1ull));
+}
+__device__ __forceinline__ double2* peer_lam(const MqcPeers& R, u64 g) {
+    return R.lam[g >> R.n_local] + (g & ((1ull << R.n_local) - 1ull));
+}
+
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
     double2 r;
     asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
@@ -132,10 +151,9 @@ struct MqcSparse {
 
 template <bool ADJ>
 __global__ void __launch_bounds__(256)
-k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass P,
+k_tile_sparse(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass P,
               const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
-              double* __restrict__ grad, const int n_bits, const int reverse, const MqcSparse SP,
-              const u64 rank_bits) {
+              double* __restrict__ grad, const int reverse, const MqcSparse SP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = P.k;
     const uint32_t T = 1u << K;
@@ -171,10 +189,9 @@ k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPas
         if (tid == 0) scount[0] = 0;
     }
     __syncthreads();
-    // n_bits counts the LOCAL address bits; rank_bits are the shard's global bits (already
-    // shifted above them): they enter parities and electron counts, never addresses.
-    const u64 base = mqc_deposit_complement((u64)blockIdx.x, P.act_mask, n_bits);
-    const u64 sbase = base | rank_bits;
+    // tile counter -> inactive LOCAL bits; inactive rank bits are this rank's own
+    const u64 base = mqc_deposit_complement((u64)blockIdx.x | PR.tau_hi, P.act_mask, PR.n_local) | PR.fixed_bits;
+    const u64 sbase = base;
     uint32_t aloc = 0, bloc = 0;
     for (int j = 0; j < K; ++j) {
         aloc |= (uint32_t)((SP.amask >> spos[j]) & 1ull) << j;
@@ -239,8 +256,8 @@ k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPas
         uint32_t t = slist[e];
         if (other_layout_load) t = (uint32_t)(inv_lo[t & lo_mask] | inv_hi[t >> h0]);
         const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
-        cp_async16(sp + e, psi + g);
-        if (ADJ) cp_async16(sl + e, lam + g);
+        cp_async16(sp + e, peer_psi(PR, g));
+        if (ADJ) cp_async16(sl + e, peer_lam(PR, g));
     }
 
     // ---- factors, in chunks ---------------------------------------------------------
@@ -309,8 +326,8 @@ k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPas
             uint32_t t = slist[e];
             if (other_layout_load) t = (uint32_t)(inv_lo[t & lo_mask] | inv_hi[t >> h0]);
             const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
-            psi[g] = make_double2(0.0, 0.0);
-            if (ADJ) lam[g] = make_double2(0.0, 0.0);
+            *peer_psi(PR, g) = make_double2(0.0, 0.0);
+            if (ADJ) *peer_lam(PR, g) = make_double2(0.0, 0.0);
         }
         __syncthreads();
     }
@@ -318,8 +335,8 @@ k_tile_sparse(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPas
         uint32_t t = slist[e];
         if (other_layout_store) t = (uint32_t)(inv_lo[t & lo_mask] | inv_hi[t >> h0]);
         const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
-        psi[g] = sp[e];
-        if (ADJ) lam[g] = sl[e];
+        *peer_psi(PR, g) = sp[e];
+        if (ADJ) *peer_lam(PR, g) = sl[e];
     }
 }
 
@@ -347,9 +364,9 @@ static inline size_t mqc_sparse_smem_bytes(int K, int cap, bool adj) {
 
 template <bool ADJ>
 __global__ void __launch_bounds__(512)
-k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass P,
+k_tile_sweep(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass P,
              const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
-             double* __restrict__ grad, const int n_bits, const int reverse, const u64 rank_bits) {
+             double* __restrict__ grad, const int reverse) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = P.k;
     const uint32_t T = 1u << K;
@@ -392,7 +409,7 @@ k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass
         for (int j = 0; j < h1; ++j) { const u64 b = ((u64)t >> j) & 1ull; d |= b << spos[h0 + j]; pm |= (uint32_t)b << sperm[h0 + j]; }
         dep_hi[t] = d; prm_hi[t] = (uint16_t)pm;
     }
-    const u64 base = mqc_deposit_complement((u64)blockIdx.x, P.act_mask, n_bits);
+    const u64 base = mqc_deposit_complement((u64)blockIdx.x | PR.tau_hi, P.act_mask, PR.n_local) | PR.fixed_bits;
     __syncthreads();
 
     // ---- load (cp.async: whole tile in flight, no register staging) -------------------
@@ -402,8 +419,8 @@ k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass
         const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
         const uint32_t st = perm_load ? (uint32_t)(prm_lo[t & lo_mask] | prm_hi[t >> h0]) : t;
         const uint32_t sw = swz(st);
-        cp_async16(sp + sw, psi + g);
-        if (ADJ) cp_async16(sl + sw, lam + g);
+        cp_async16(sp + sw, peer_psi(PR, g));
+        if (ADJ) cp_async16(sl + sw, peer_lam(PR, g));
     }
 
     // ---- factors, in chunks ---------------------------------------------------------
@@ -426,7 +443,7 @@ k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass
             if (xl < T) val = swz(xl) | (((uint32_t)__popc(xl & fz) & 1u) << 15);
             if (e < 32) {                                       // v and the per-tile sign ride on table A
                 const uint32_t fv = Fp->v;
-                const uint32_t sg = ((uint32_t)__popc(fv & fz) + (uint32_t)__popcll((base | rank_bits) & Fp->z_out) + Fp->sign0) & 1u;
+                const uint32_t sg = ((uint32_t)__popc(fv & fz) + (uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
                 val ^= swz(fv) | (sg << 15);
             }
             slut[w] = (uint16_t)val;
@@ -500,8 +517,8 @@ k_tile_sweep(double2* __restrict__ psi, double2* __restrict__ lam, const MqcPass
         const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
         const uint32_t st = perm_store ? (uint32_t)(prm_lo[t & lo_mask] | prm_hi[t >> h0]) : t;
         const uint32_t sw = swz(st);
-        st_stream(psi + g, sp[sw]);
-        if (ADJ) st_stream(lam + g, sl[sw]);
+        st_stream(peer_psi(PR, g), sp[sw]);
+        if (ADJ) st_stream(peer_lam(PR, g), sl[sw]);
     }
 }
 
@@ -575,8 +592,8 @@ __global__ void k_adjoint_direct(double2* __restrict__ psi, double2* __restrict_
 // One thread per output amplitude y; with a sector, y runs over alpha-string x beta-string
 // and partners outside the sector are skipped (they hold exact zeros).
 __global__ void __launch_bounds__(256)
-k_happly(const double2* __restrict__ psi, double2* __restrict__ lam, const MqcHamDev H,
-         const MqcSectorDev S, const u64 count, double* __restrict__ e_out) {
+k_happly(const __grid_constant__ MqcPeers PR, double2* __restrict__ lam, const MqcHamDev H,
+         const MqcSectorDev S, const u64 count, const u64 y_rank_bits, double* __restrict__ e_out) {
     __shared__ double red[2][8];
     const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     double er = 0.0, ei = 0.0;
@@ -586,13 +603,13 @@ k_happly(const double2* __restrict__ psi, double2* __restrict__ lam, const MqcHa
             const u64 ia = tid / S.n_b, ib = tid - ia * S.n_b;
             y = S.astr[ia] | S.bstr[ib];
         } else {
-            y = tid;
+            y = tid | y_rank_bits;          // this rank's shard
         }
         double ar = 0.0, ai = 0.0;
         for (int g = 0; g < H.n_groups; ++g) {
             const u64 x = y ^ __ldg(H.gmask + g);
             if (S.enabled && (__popcll(x & S.amask) != S.na || __popcll(x & S.bmask) != S.nb)) continue;
-            const double2 p = psi[x];
+            const double2 p = *peer_psi(PR, x);
             if (p.x == 0.0 && p.y == 0.0) continue;
             const int t0 = __ldg(H.goff + g), t1 = __ldg(H.goff + g + 1);
             double cr = 0.0, ci = 0.0;
@@ -604,8 +621,8 @@ k_happly(const double2* __restrict__ psi, double2* __restrict__ lam, const MqcHa
             ar += cr * p.x - ci * p.y;
             ai += cr * p.y + ci * p.x;
         }
-        if (lam) lam[y] = make_double2(ar, ai);
-        const double2 py = psi[y];
+        if (lam) lam[y & ((1ull << PR.n_local) - 1ull)] = make_double2(ar, ai);
+        const double2 py = *peer_psi(PR, y);
         er = py.x * ar + py.y * ai;       // conj(psi[y]) * acc
         ei = py.x * ai - py.y * ar;
     }
@@ -656,22 +673,66 @@ struct MqcSecHamDev {
     unsigned n_a, n_b;
 };
 
-__global__ void k_sector_gather(const double2* __restrict__ psi, double2* __restrict__ C,
+// rows [ia0, ia1) of the sector matrix; the state is read through the peer table, so on a
+// sharded state every rank can assemble whatever rows it needs
+__global__ void k_sector_gather(const __grid_constant__ MqcPeers PR, double2* __restrict__ C,
                                 const u64* __restrict__ astr, const u64* __restrict__ bstr,
-                                const unsigned n_a, const unsigned n_b) {
+                                const unsigned ia0, const unsigned ia1, const unsigned n_b) {
     const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (u64)n_a * n_b) return;
-    const unsigned ia = (unsigned)(tid / n_b), ib = (unsigned)(tid - (u64)ia * n_b);
-    C[tid] = psi[astr[ia] | bstr[ib]];
+    if (tid >= (u64)(ia1 - ia0) * n_b) return;
+    const unsigned ia = ia0 + (unsigned)(tid / n_b), ib = (unsigned)(tid % n_b);
+    C[(u64)ia * n_b + ib] = *peer_psi(PR, astr[ia] | bstr[ib]);
 }
 
-__global__ void k_sector_scatter(double2* __restrict__ lam, const double2* __restrict__ L,
+__global__ void k_sector_scatter(const __grid_constant__ MqcPeers PR, const double2* __restrict__ L,
                                  const u64* __restrict__ astr, const u64* __restrict__ bstr,
-                                 const unsigned n_a, const unsigned n_b) {
+                                 const unsigned ia0, const unsigned ia1, const unsigned n_b) {
     const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (u64)n_a * n_b) return;
-    const unsigned ia = (unsigned)(tid / n_b), ib = (unsigned)(tid - (u64)ia * n_b);
-    lam[astr[ia] | bstr[ib]] = L[tid];
+    if (tid >= (u64)(ia1 - ia0) * n_b) return;
+    const unsigned ia = ia0 + (unsigned)(tid / n_b), ib = (unsigned)(tid % n_b);
+    *peer_lam(PR, astr[ia] | bstr[ib]) = L[(u64)ia * n_b + ib];
+}
+
+// ------------------------------------------------------------------------------------------
+// cross-rank plumbing of a sharded state (one process per GPU): barrier and sum over peers
+// ------------------------------------------------------------------------------------------
+struct MqcFlags {
+    unsigned long long* flags[MQC_MAX_RANKS];   // flags[r][q]: rank q's arrival counter as seen by rank r
+    int n_ranks, rank;
+};
+// All ranks launch this with the same epoch.  System-scope fence + release store publish
+// everything this GPU wrote (to its own and to peers' HBM) before the arrival flag; the
+// acquire spin returns once every peer has arrived.  Spins are bounded (~10 s) so that a dead
+// peer becomes an error flag, not a hung GPU.
+__global__ void k_rank_barrier(const __grid_constant__ MqcFlags F, const unsigned long long epoch,
+                               int* __restrict__ err) {
+    const int q = threadIdx.x;
+    if (q >= F.n_ranks) return;
+    __threadfence_system();
+    unsigned long long* dst = F.flags[q] + F.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+    const unsigned long long* src = F.flags[F.rank] + q;
+    const long long t0 = clock64();
+    unsigned long long seen = 0;
+    while (true) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+        if (seen >= epoch) break;
+        if (clock64() - t0 > 20000000000ll) { *err = 1; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+struct MqcSumPeers {
+    const double* src[MQC_MAX_RANKS];
+    int n_ranks;
+};
+__global__ void k_sum_peers(const __grid_constant__ MqcSumPeers S, double* __restrict__ out, const int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = 0.0;
+    for (int r = 0; r < S.n_ranks; ++r) v += S.src[r][i];
+    out[i] = v;
 }
 
 #define MQC_HS_R 4
@@ -683,9 +744,9 @@ __device__ __forceinline__ unsigned pext_small(unsigned x, unsigned m) {   // ga
 
 __global__ void __launch_bounds__(256)
 k_happly_sector(const double2* __restrict__ C, double2* __restrict__ L, const MqcSecHamDev H,
-                double* __restrict__ e_out) {
+                double* __restrict__ e_out, const unsigned ia0) {
     __shared__ double red[2][8];
-    const unsigned iap = blockIdx.x;
+    const unsigned iap = ia0 + blockIdx.x;
     const unsigned ap = H.aorb[iap];
     unsigned bp[MQC_HS_R];
     unsigned ibp[MQC_HS_R];
@@ -838,13 +899,13 @@ struct MqcRdmDev {
 };
 
 // rdm1[a/2][i/2] += sign * Re(conj(psi[D]) psi[D'])   with D' = a^+ i D   (rdm.py:131-138)
-__global__ void k_rdm1(const double2* __restrict__ psi, const MqcSectorDev S, const MqcRdmDev R,
-                       const u64 count, double* __restrict__ rdm1) {
-    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= count) return;
+__global__ void k_rdm1(const __grid_constant__ MqcPeers PR, const MqcSectorDev S, const MqcRdmDev R,
+                       const u64 det0, const u64 det1, double* __restrict__ rdm1) {
+    const u64 tid = det0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= det1) return;
     const u64 ia = tid / S.n_b, ib = tid - ia * S.n_b;
     const u64 y = S.astr[ia] | S.bstr[ib];
-    const double2 c0 = psi[y];
+    const double2 c0 = *peer_psi(PR, y);
     if (c0.x == 0.0 && c0.y == 0.0) return;
     const int n = R.n_orb, nq = 2 * n;
     double* out = rdm1 + (size_t)(blockIdx.x % R.n_copies) * n * n;
@@ -859,7 +920,7 @@ __global__ void k_rdm1(const double2* __restrict__ psi, const MqcSectorDev S, co
             if (y1 & ba) continue;
             if (a == i) continue;
             const u64 y2 = y1 | ba;
-            const double2 c1 = psi[y2];
+            const double2 c1 = *peer_psi(PR, y2);
             if (c1.x == 0.0 && c1.y == 0.0) continue;
             const int par = par_i + __popcll(y1 & R.below[a]);
             const double v = c0.x * c1.x + c0.y * c1.y;
@@ -870,18 +931,18 @@ __global__ void k_rdm1(const double2* __restrict__ psi, const MqcSectorDev S, co
 
 // dm2[p,q,r,s] = sum_{sigma,tau} <p_sigma^+ r_tau^+ s_tau q_sigma>   (pyscf order, what
 // make_rdm12 + reorder_rdm return, rdm.py:157-172).  One thread per (determinant, q_sigma).
-__global__ void k_rdm2(const double2* __restrict__ psi, const MqcSectorDev S, const MqcRdmDev R,
-                       const u64 count, double* __restrict__ rdm2) {
+__global__ void k_rdm2(const __grid_constant__ MqcPeers PR, const MqcSectorDev S, const MqcRdmDev R,
+                       const u64 det0, const u64 det1, double* __restrict__ rdm2) {
     const int n = R.n_orb, nq = 2 * n;
     const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u64 det = gid / nq;
-    const int Q = (int)(gid - det * nq);
-    if (det >= count) return;
+    const u64 det = det0 + gid / nq;
+    const int Q = (int)(gid % nq);
+    if (det >= det1) return;
     const u64 ia = det / S.n_b, ib = det - ia * S.n_b;
     const u64 y = S.astr[ia] | S.bstr[ib];
     const u64 bQ = R.qbit[Q];
     if (!(y & bQ)) return;
-    const double2 c0 = psi[y];
+    const double2 c0 = *peer_psi(PR, y);
     if (c0.x == 0.0 && c0.y == 0.0) return;
     const size_t n2 = (size_t)n * n, n4 = n2 * n2;
     double* out = rdm2 + (size_t)(blockIdx.x % R.n_copies) * n4;
@@ -901,7 +962,7 @@ __global__ void k_rdm2(const double2* __restrict__ psi, const MqcSectorDev S, co
                 const u64 bP = R.qbit[Pp];
                 if (y3 & bP) continue;
                 const u64 y4 = y3 | bP;
-                const double2 c1 = psi[y4];
+                const double2 c1 = *peer_psi(PR, y4);
                 if (c1.x == 0.0 && c1.y == 0.0) continue;
                 const int par = par_r + __popcll(y3 & R.below[Pp]);
                 const double v = c1.x * c0.x + c1.y * c0.y;       // Re(conj(psi[D']) psi[D])

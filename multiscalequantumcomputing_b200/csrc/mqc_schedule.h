@@ -9,6 +9,14 @@
 // stores ("re-layout") for free; the scheduler uses this to move the bits the NEXT pass
 // needs into the low positions, so consecutive passes only have to share L bits.
 //
+// Sharded state: the top n_global physical positions are the rank id; each
+// rank holds 2^(n_bits - n_global) amplitudes.  A global position may be ACTIVE like any
+// other: the tile then straddles the 2^ga ranks that differ in the active global bits, its
+// CTA reads and writes the peers' shards directly over NVLink, and the same free re-layout
+// moves the logical bit that sat in the rank id into local memory while a bit that is not
+// needed for the longest time takes its place (Belady's rule).  The global-qubit exchange is
+// therefore fused into a compute pass: no separate swap pass, no staging buffer.
+//
 // Factor order is preserved exactly (excitation factors do not commute in general).
 // Pure C++ (no CUDA): testable on a CPU-only box through mqc_schedule_* in the C ABI.
 #pragma once
@@ -19,18 +27,9 @@
 
 #include "mqc_common.h"
 
-// One step of a (possibly sharded) sweep: a tile pass on the local shard, or the exchange of
-// the amplitudes' global bit (physical position pg >= n_local) with local position pl between
-// rank pairs r <-> r ^ (1 << (pg - n_local)).
-struct MqcStep {
-    int type;      // 0 = tile pass, 1 = exchange
-    int a, b;      // pass index, 0   |   pg, pl
-};
-
 struct MqcSchedule {
     int n_bits = 0, k = 0, low = 0;
     int n_global = 0;              // top physical positions that live in the rank id
-    std::vector<MqcStep> steps;
     std::vector<MqcPass> passes;
     std::vector<MqcTileFactor> tf;
     std::vector<std::vector<int>> pass_phys_before, pass_phys_after;   // layout around each pass
@@ -45,6 +44,30 @@ static inline u64 mqc_map_mask(u64 mask, const std::vector<int>& phys) {
     return out;
 }
 
+// Which tiles of a pass a rank sweeps, and where they start.  The 2^ga ranks that differ
+// only in the pass's ACTIVE global bits share one set of 2^(n_local - K + ga) tiles; each
+// takes the 2^(n_local - K) of them whose top ga tile-counter bits equal its own bits at the
+// active global positions.  Inactive global bits of a tile are the rank's own.
+struct MqcTileMap {
+    u64 tau_hi;        // OR-ed into the tile counter (blockIdx) before it is deposited
+    u64 fixed_bits;    // rank bits at inactive global positions, in physical coordinates
+    u64 n_tiles;       // grid size
+};
+static inline MqcTileMap mqc_tile_map(const MqcPass& P, int n_bits, int n_global, int rank) {
+    const int N = n_bits - n_global;
+    const u64 gact = P.act_mask >> N;                    // active global positions (rank-bit coordinates)
+    int ga = 0;
+    u64 share = 0;
+    for (int b = 0; b < n_global; ++b)
+        if ((gact >> b) & 1ull) { share |= (u64)((rank >> b) & 1) << ga; ++ga; }
+    MqcTileMap M;
+    const int lg_tiles = N - P.k;                        // per rank, always
+    M.n_tiles = 1ull << lg_tiles;
+    M.tau_hi = share << lg_tiles;
+    M.fixed_bits = ((u64)rank << N) & ~P.act_mask;
+    return M;
+}
+
 // factors are given in LOGICAL bit coordinates
 static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
                                              const std::vector<MqcFactor>& fac, int cap = MQC_MAX_PASS_FACTORS,
@@ -57,28 +80,31 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
     const int K = std::min(k_req, N);
     const int L = std::min(low_req, K);
     if (K > 16) throw std::runtime_error("tile bits too large");
-    if (K < N && K < L + 4) throw std::runtime_error("tile bits must be >= low bits + 4");
+    if (K < NT && K < L + 4) throw std::runtime_error("tile bits must be >= low bits + 4");
     S.n_bits = NT; S.k = K; S.low = L;
     std::vector<int> phys(NT), inv(NT);
     for (int l = 0; l < NT; ++l) phys[l] = inv[l] = l;
     const size_t n = fac.size();
-    // next use of every logical bit after factor t (for the exchange victim choice)
+    // first factor at or after `from` that moves logical bit `bit` (n + 1: never again)
     auto next_use = [&](int bit, size_t from) -> size_t {
         for (size_t t = from; t < n; ++t) if ((fac[t].m >> bit) & 1ull) return t;
         return n + 1;
     };
+    auto swap_to = [&](int b, int target) {          // put logical bit b at physical position target
+        const int p_old = phys[b], other = inv[target];
+        phys[b] = target; inv[target] = b;
+        phys[other] = p_old; inv[p_old] = other;
+    };
     // The reference state is a single determinant, so the initial layout is free: put the
-    // bits the first factors move into the low physical positions.
-    if (K < N && L > 0) {
+    // bits the first factors move into the low physical positions ...
+    if (K < NT && L > 0) {
         int placed = 0;
         u64 seen = 0;
         for (size_t t = 0; t < n && placed < L; ++t) {
             u64 mm = fac[t].m & ~seen;
             while (mm && placed < L) {
                 const int b = __builtin_ctzll(mm); mm &= mm - 1; seen |= 1ull << b;
-                const int p_old = phys[b], other = inv[placed];
-                phys[b] = placed; inv[placed] = b;
-                phys[other] = p_old; inv[p_old] = other;
+                swap_to(b, placed);
                 ++placed;
             }
         }
@@ -86,63 +112,36 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
     // ... and the bits whose first use is farthest away into the global (rank) positions
     if (n_global > 0) {
         std::vector<int> cand;
-        for (int l = 0; l < NT; ++l) if (!(K < N && phys[l] < L)) cand.push_back(l);
+        for (int l = 0; l < NT; ++l) if (!(K < NT && phys[l] < L)) cand.push_back(l);
         std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return next_use(a, 0) > next_use(b, 0); });
-        for (int t = 0; t < n_global && t < (int)cand.size(); ++t) {
-            const int b = cand[t], target = N + t;
-            if (phys[b] == target) continue;
-            const int other = inv[target], p_old = phys[b];
-            phys[b] = target; inv[target] = b;
-            phys[other] = p_old; inv[p_old] = other;
-        }
+        for (int t = 0; t < n_global && t < (int)cand.size(); ++t) swap_to(cand[t], N + t);
     }
     S.phys_init = phys;
     size_t i = 0;
     while (i < n) {
-        // bring the bits the next factor moves into the local shard
-        {
-            u64 need = fac[i].m;
-            while (need) {
-                const int b = __builtin_ctzll(need); need &= need - 1;
-                if (phys[b] < N) continue;
-                // victim: local bit, not moved by this factor, whose next use is farthest away
-                int victim = -1; size_t far = 0;
-                for (int p = N - 1; p >= 0; --p) {
-                    const int lb = inv[p];
-                    if ((fac[i].m >> lb) & 1ull) continue;
-                    const size_t nu = next_use(lb, i);
-                    if (victim < 0 || nu > far) { victim = lb; far = nu; }
-                }
-                if (victim < 0) throw std::runtime_error("no local bit to exchange with");
-                const int pg = phys[b], pl = phys[victim];
-                S.steps.push_back(MqcStep{1, pg, pl});
-                phys[b] = pl; inv[pl] = b;
-                phys[victim] = pg; inv[pg] = victim;
-            }
-        }
         u64 A = 0;                                   // logical active set
         for (int p = 0; p < L; ++p) A |= 1ull << inv[p];
-        if (K == N) { A = 0; for (int p = 0; p < N; ++p) A |= 1ull << inv[p]; }
         size_t j = i;
         while (j < n && (int)(j - i) < cap) {
-            bool local = true;
-            { u64 mm = fac[j].m; while (mm) { const int b = __builtin_ctzll(mm); mm &= mm - 1; if (phys[b] >= N) local = false; } }
-            if (!local) break;
             const u64 U = A | fac[j].m;
             if (MQC_POPC64(U) > K) break;
             A = U; ++j;
         }
         if (j == i) throw std::runtime_error("factor does not fit a tile");
+        bool has_global = false;
+        for (int p = N; p < NT; ++p) if ((A >> inv[p]) & 1ull) has_global = true;
         // look-ahead: bits the following factors move, in order of first use
         std::vector<int> ahead;
         u64 seen = 0;
-        for (size_t t = j; t < n && (int)ahead.size() < N; ++t) {
+        for (size_t t = j; t < n && (int)ahead.size() < NT; ++t) {
             u64 mm = fac[t].m & ~seen;
             while (mm) { int b = __builtin_ctzll(mm); mm &= mm - 1; ahead.push_back(b); seen |= 1ull << b; }
             if ((int)ahead.size() >= 2 * K) break;
         }
-        // fill A up to K bits: first with bits needed soonest, then lowest physical positions
-        for (size_t t = 0; t < ahead.size() && MQC_POPC64(A) < K; ++t) if (phys[ahead[t]] < N) A |= 1ull << ahead[t];
+        // fill A up to K bits: first with bits needed soonest, then lowest physical positions.
+        // A bit that sits in the rank id is only prefetched when the tile straddles ranks anyway.
+        for (size_t t = 0; t < ahead.size() && MQC_POPC64(A) < K; ++t)
+            if (phys[ahead[t]] < N || has_global) A |= 1ull << ahead[t];
         for (int p = 0; p < N && MQC_POPC64(A) < K; ++p) A |= 1ull << inv[p];
 
         MqcPass P{};
@@ -150,7 +149,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
         P.f0 = (int)S.tf.size();
         S.pass_phys_before.push_back(phys);
         std::vector<int> pos;                       // physical positions of A, ascending
-        for (int p = 0; p < N; ++p) if ((A >> inv[p]) & 1ull) pos.push_back(p);
+        for (int p = 0; p < NT; ++p) if ((A >> inv[p]) & 1ull) pos.push_back(p);
         u64 act = 0;
         std::vector<int> local_of_phys(NT, -1);
         for (int jj = 0; jj < K; ++jj) { P.pos[jj] = pos[jj]; act |= 1ull << pos[jj]; local_of_phys[pos[jj]] = jj; }
@@ -176,31 +175,68 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
             S.tf.push_back(q);
         }
         P.f1 = (int)S.tf.size();
-        // choose the next low set among A: bits needed soonest first
+        // Re-layout among the active positions.  Active global positions receive the active
+        // bits whose next use is farthest away; the low positions the bits needed soonest;
+        // every other bit stays where it is whenever its position is still free.
         P.has_perm = 0;
         for (int jj = 0; jj < K; ++jj) P.perm[jj] = (uint8_t)jj;
-        if (j < n && K < N && L > 0) {
-            std::vector<int> newlow;
-            u64 chosen = 0;
-            for (size_t t = 0; t < ahead.size() && (int)newlow.size() < L; ++t)
-                if (((A >> ahead[t]) & 1ull) && !((chosen >> ahead[t]) & 1ull)) { newlow.push_back(ahead[t]); chosen |= 1ull << ahead[t]; }
-            // keep current low bits where possible (identity is cheapest), then anything in A
-            for (int p = 0; p < L && (int)newlow.size() < L; ++p)
-                if (!((chosen >> inv[p]) & 1ull)) { newlow.push_back(inv[p]); chosen |= 1ull << inv[p]; }
-            // new layout inside the active positions: members of newlow that already sit in
-            // a low position stay; the others swap with low-position bits that leave.
-            std::vector<int> newphys = phys;
-            std::vector<int> leaving;                // low positions whose bit is not in newlow
-            for (int p = 0; p < L; ++p) if (!((chosen >> inv[p]) & 1ull)) leaving.push_back(p);
-            size_t li = 0;
-            for (int b : newlow) {
-                if (phys[b] >= L) {
-                    const int plow = leaving[li++];
-                    const int other = inv[plow];
-                    newphys[b] = plow;
-                    newphys[other] = phys[b];
+        if (j < n && K < NT) {
+            std::vector<int> bitsA;                  // logical bits of A
+            for (int jj = 0; jj < K; ++jj) bitsA.push_back(inv[pos[jj]]);
+            std::vector<int> gpos;                   // active global positions
+            for (int jj = 0; jj < K; ++jj) if (pos[jj] >= N) gpos.push_back(pos[jj]);
+            u64 chosen_g = 0, chosen_low = 0;
+            std::vector<int> glist, lowlist;
+            if (!gpos.empty()) {
+                std::vector<int> order = bitsA;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                    const size_t ua = next_use(a, j), ub = next_use(b, j);
+                    if (ua != ub) return ua > ub;
+                    return (phys[a] >= N) > (phys[b] >= N);          // ties: stay in the rank id
+                });
+                for (size_t t = 0; t < gpos.size(); ++t) { glist.push_back(order[t]); chosen_g |= 1ull << order[t]; }
+            }
+            if (L > 0) {
+                for (size_t t = 0; t < ahead.size() && (int)lowlist.size() < L; ++t) {
+                    const int b = ahead[t];
+                    if (((A >> b) & 1ull) && !((chosen_g >> b) & 1ull) && !((chosen_low >> b) & 1ull)) {
+                        lowlist.push_back(b); chosen_low |= 1ull << b;
+                    }
+                }
+                // keep current low bits where possible (identity is cheapest), then anything in A
+                for (int p = 0; p < L && (int)lowlist.size() < L; ++p) {
+                    const int b = inv[p];
+                    if (!((chosen_g >> b) & 1ull) && !((chosen_low >> b) & 1ull)) { lowlist.push_back(b); chosen_low |= 1ull << b; }
+                }
+                for (int b : bitsA) {
+                    if ((int)lowlist.size() >= L) break;
+                    if (!((chosen_g >> b) & 1ull) && !((chosen_low >> b) & 1ull)) { lowlist.push_back(b); chosen_low |= 1ull << b; }
                 }
             }
+            std::vector<int> newphys = phys;
+            std::vector<char> taken(NT, 0);          // positions of pos[] already assigned
+            std::vector<char> done(NT, 0);           // logical bits already assigned
+            auto assign_class = [&](const std::vector<int>& bits, const std::vector<int>& places) {
+                // bits already sitting in one of `places` stay; the others take the free ones
+                std::vector<char> is_place(NT, 0);
+                for (int p : places) is_place[p] = 1;
+                for (int b : bits) if (is_place[phys[b]]) { newphys[b] = phys[b]; taken[phys[b]] = 1; done[b] = 1; }
+                size_t pi = 0;
+                for (int b : bits) {
+                    if (done[b]) continue;
+                    while (pi < places.size() && taken[places[pi]]) ++pi;
+                    newphys[b] = places[pi]; taken[places[pi]] = 1; done[b] = 1;
+                }
+            };
+            std::vector<int> lowpos;
+            for (int p = 0; p < L; ++p) lowpos.push_back(p);
+            assign_class(glist, gpos);
+            assign_class(lowlist, lowpos);
+            std::vector<int> rest_bits, rest_pos;
+            for (int b : bitsA) if (!done[b]) rest_bits.push_back(b);
+            for (int jj = 0; jj < K; ++jj) if (!taken[pos[jj]]) rest_pos.push_back(pos[jj]);
+            assign_class(rest_bits, rest_pos);
+
             bool changed = false;
             for (int l = 0; l < NT; ++l) if (newphys[l] != phys[l]) changed = true;
             if (changed) {
@@ -217,7 +253,6 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
                 for (int l = 0; l < NT; ++l) inv[phys[l]] = l;
             }
         }
-        S.steps.push_back(MqcStep{0, (int)S.passes.size(), 0});
         S.passes.push_back(P);
         S.pass_phys_after.push_back(phys);
         i = j;

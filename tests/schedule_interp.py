@@ -69,3 +69,55 @@ def to_logical(psi_phys, layout):
     i = np.arange(1 << n, dtype=np.uint64)
     p = _deposit(i, [int(v) for v in layout])
     return psi_phys[p.astype(np.int64)]
+
+
+def run_forward_sharded(sched, n_bits, n_ranks, ref_index, cos_sin):
+    """The same passes executed the way the ranks of a sharded state do (csrc `launch_tile` +
+    `peer_psi`): every rank sweeps the tiles of its tile map, an amplitude with physical index g
+    lives in shard g >> n_local at offset g & (2^n_local - 1).  Also checks that the ranks'
+    tiles partition the register in every pass.  Returns the list of shards."""
+    g_bits = n_ranks.bit_length() - 1
+    n_local = n_bits - g_bits
+    lmask = (1 << n_local) - 1
+    shards = [np.zeros(1 << n_local, dtype=np.complex128) for _ in range(n_ranks)]
+    ref_phys = 0
+    for l, p in enumerate(sched["initial_layout"]):
+        ref_phys |= ((ref_index >> l) & 1) << int(p)
+    shards[ref_phys >> n_local][ref_phys & lmask] = 1.0
+    K = sched["tile_bits"]
+    t = np.arange(1 << K, dtype=np.uint64)
+    flat = np.concatenate(shards)                               # index = physical index (rank bits on top)
+    for P in sched["passes"]:
+        pos = [int(p) for p in P["pos"]]
+        act = int(P["act_mask"])
+        inactive_local = [b for b in range(n_local) if not (act >> b) & 1]
+        touched = np.zeros(1 << n_bits, dtype=np.int32)
+        new = flat.copy()
+        for r in range(n_ranks):
+            tau_hi, fixed, ntiles = P["tile_map"][r]
+            assert ntiles == 1 << (n_local - K)
+            tau = np.arange(ntiles, dtype=np.uint64) | np.uint64(tau_hi)
+            base = _deposit(tau, inactive_local) | np.uint64(fixed)
+            g = (base[:, None] | _deposit(t, pos)[None, :]).astype(np.int64)
+            np.add.at(touched, g.ravel(), 1)
+            tile = flat[g]
+            for F in P["factors"]:
+                m, v, z = np.uint64(F["m"]), np.uint64(F["v"]), np.uint64(F["z"])
+                c, sn = cos_sin[F["slot"]]
+                x0 = t[(t & m) == v]
+                x1 = x0 ^ m
+                par_in = _parity(x0 & z)
+                par_tile = (_parity(base & np.uint64(F["z_out"])) + F["sign0"]) & 1
+                s = 1.0 - 2.0 * ((par_in[None, :] + par_tile[:, None]) & 1)
+                a = tile[:, x0.astype(np.int64)]
+                b = tile[:, x1.astype(np.int64)]
+                tile[:, x0.astype(np.int64)] = c * a - s * sn * b
+                tile[:, x1.astype(np.int64)] = c * b + s * sn * a
+            if P["has_perm"]:
+                src = _deposit(t, [int(p) for p in P["perm"]]).astype(np.int64)
+                new[g] = tile[:, src]
+            else:
+                new[g] = tile
+        assert (touched == 1).all(), "the ranks' tiles must partition the register"
+        flat = new
+    return [flat[r << n_local:(r + 1) << n_local] for r in range(n_ranks)]

@@ -1,0 +1,116 @@
+"""GPU parity of the SHARDED state path (BASELINE.json configs[4]) against
+the CPU oracle: rank bits are physical index bits, tile passes that contain one read and
+write the peers' shards directly, energy / gradient partial sums are reduced over peer
+memory.  `ShardGroup` with a repeated device puts several ranks on ONE GPU, so the whole
+protocol (tile maps, peer addressing, ordering between ranks, reductions) runs on the
+single-GPU test tier; the one-process-per-GPU transport (CUDA IPC + flag barrier) is
+exercised by `scripts/shard_ipc_check.py` under torchrun when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from multiscalequantumcomputing_b200 import _lib
+from multiscalequantumcomputing_b200.jw import fragment_term_table, s2_term_table
+from multiscalequantumcomputing_b200.synth.hydrogen import random_fragment_integrals
+from multiscalequantumcomputing_b200.uccsd import uccsd_factors
+from oracle import rdm as ordm
+from oracle.hamiltonian import apply_terms
+from oracle.statevector import UCCSDOracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+E_TOL, G_TOL, R_TOL, S_TOL = 1e-10, 1e-9, 1e-9, 1e-12
+
+
+def _devices(ranks):
+    n = _lib.device_count()
+    return [r % n for r in range(ranks)]
+
+
+def _setup(n, ne, ranks, order="blocked", opts=None, seed=1234):
+    h1, eri = random_fragment_integrals(n, seed)
+    tab = fragment_term_table(h1, eri, 0, 0.0, 0.25)
+    F = uccsd_factors(n, ne, order)
+    h = _lib.ShardGroup(2 * n, _devices(ranks))
+    for k, v in (opts or {}).items():
+        h.set_option(k, v)
+    h.set_hamiltonian(*tab)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    orc = UCCSDOracle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, tab)
+    th = np.random.default_rng(4321).normal(0, 0.05, F.n_theta)
+    return h, orc, F, tab, th
+
+
+CASES = [
+    (5, 4, 2, "lex", {"tile_bits": 6, "grad_tile_bits": 6, "low_bits": 2}),
+    (6, 6, 2, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "low_bits": 3}),
+    (6, 6, 4, "lex", {"tile_bits": 8, "grad_tile_bits": 8, "low_bits": 2}),
+    (6, 6, 4, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "sparse_tiles": 0}),     # dense tiles
+    (6, 6, 2, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "sector": 0}),           # dense H|psi>
+    (7, 6, 8, "blocked", {"tile_bits": 9, "grad_tile_bits": 8}),
+    (8, 8, 8, "blocked", {}),                                                           # 16 qubits, 13 local bits
+    (8, 8, 2, "blocked", {"sparse_tiles": 0}),
+]
+
+
+@pytest.mark.parametrize("n,ne,ranks,order,opts", CASES)
+def test_sharded_state_energy_gradient(n, ne, ranks, order, opts):
+    h, orc, F, tab, th = _setup(n, ne, ranks, order, opts)
+    ref = orc.state(th)
+    psi = h.gather_state(th)
+    assert abs(psi - ref).max() < S_TOL
+    e_ref, g_ref = orc.energy_grad(th)
+    assert abs(h.energy(th) - e_ref) < E_TOL
+    e, g = h.energy_grad(th)
+    assert abs(e - e_ref) < E_TOL
+    assert abs(g - g_ref).max() < G_TOL
+    e2, g2 = h.energy_grad(th)                       # repeatable (mail / flags re-used)
+    assert abs(e2 - e) < 1e-13 and abs(g - g2).max() < 1e-12
+    h.close()
+
+
+def test_sharded_rdm_and_expectation():
+    n, ne = 6, 6
+    h, orc, F, tab, th = _setup(n, ne, 4, "blocked", {"tile_bits": 8, "grad_tile_bits": 7})
+    h.prepare(th)
+    psi = orc.state(th)
+    r1, r2 = h.rdm12(n, ne // 2, ne // 2)
+    o1, o2 = ordm.get_rdm12(psi, ne, n)
+    assert abs(r1 - o1).max() < R_TOL and abs(r2 - o2).max() < R_TOL
+    s2 = s2_term_table(n)
+    assert abs(h.expectation(*s2) - np.vdot(psi, apply_terms(*s2, psi))) < 1e-10
+    h.close()
+
+
+def test_sharded_equals_unsharded_20_qubits():
+    """Above the oracle's comfortable size: 8 ranks vs the single-shard path, same inputs."""
+    n = 10
+    h1, eri = random_fragment_integrals(n, 7)
+    tab = fragment_term_table(h1, eri, 0, 0.0, 0.25)
+    F = uccsd_factors(n, n, "blocked")
+    th = np.random.default_rng(11).normal(0, 0.05, F.n_theta)
+    h0 = _lib.Handle(2 * n)
+    h0.set_hamiltonian(*tab)
+    h0.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    e0, g0 = h0.energy_grad(th)
+    h8 = _lib.ShardGroup(2 * n, _devices(8))
+    h8.set_hamiltonian(*tab)
+    h8.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    e8, g8 = h8.energy_grad(th)
+    assert abs(e8 - e0) < E_TOL and abs(g8 - g0).max() < G_TOL
+    S = h8.schedule(1)
+    assert any(p["act_mask"] >> 17 for p in S["passes"])
+    h0.close(); h8.close()
+
+
+@pytest.mark.skipif(_lib.device_count() < 2, reason="needs two GPUs (one process per GPU, CUDA IPC)")
+def test_ipc_ranks_under_torchrun():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29571",
+           os.path.join(ROOT, "scripts", "shard_ipc_check.py"), "--n-orb", "7"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "shard ipc ok" in res.stdout

@@ -56,3 +56,44 @@ def test_factor_counts():
     # n_theta = 2ov + 2C(o,2)C(v,2) + (ov)^2
     for n, cnt in ((4, 26), (8, 360)):
         assert len(uccsd_factors(n, n)) == cnt
+
+
+@pytest.mark.parametrize("n,ne,kb,lb,ranks,order", [
+    (5, 4, 6, 2, 2, "lex"),
+    (6, 6, 7, 3, 2, "blocked"),
+    (6, 6, 7, 2, 4, "lex"),
+    (6, 4, 8, 3, 4, "blocked"),
+    (7, 6, 8, 3, 8, "blocked"),
+    (7, 6, 9, 3, 8, "lex"),
+])
+def test_sharded_schedule_reproduces_oracle_state(n, ne, kb, lb, ranks, order):
+    """Rank bits are physical index bits like any other: a pass whose active set contains
+    one straddles the ranks and its re-layout swaps the global qubit into local memory."""
+    F = uccsd_factors(n, ne, order)
+    h = _lib.ShardGroup(2 * n, [0] * ranks)
+    h.set_option("tile_bits", kb)
+    h.set_option("low_bits", lb)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    S = h.schedule(0)
+    n_local = 2 * n - (ranks.bit_length() - 1)
+    assert h.shard_info() == dict(rank=0, n_ranks=ranks, n_local_bits=n_local, members=ranks)
+    th = np.random.default_rng(5).normal(0, 0.2, F.n_theta)
+    cs = [(np.cos(th[t]), np.sin(th[t])) for t in F.theta_index]
+    ref = UCCSDOracle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, EMPTY).state(th)
+    shards = SI.run_forward_sharded(S, 2 * n, ranks, F.ref_index, cs)
+    psi = _lib.assemble_state(shards, S["final_layout"])
+    assert abs(psi - ref).max() < 1e-14
+    slots = [f["slot"] for p in S["passes"] for f in p["factors"]]
+    assert slots == list(range(len(F)))
+    n_glob = sum(1 for p in S["passes"] if p["act_mask"] >> n_local)
+    assert 0 < n_glob < len(S["passes"])            # some passes straddle ranks, not all
+
+
+def test_sharded_schedule_global_pass_share():
+    """34 qubits on 8 GPUs (BASELINE.json configs[4] shape): how many passes touch NVLink."""
+    F = uccsd_factors(12, 12, "blocked")
+    h = _lib.ShardGroup(24, [0] * 8)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    S = h.schedule(0)
+    n_glob = sum(1 for p in S["passes"] if p["act_mask"] >> 21)
+    assert len(S["passes"]) <= 60 and n_glob <= len(S["passes"]) // 2
