@@ -77,7 +77,8 @@ int mqc_shard_read(mqc_solver_t* s, const double* theta, int32_t member, double*
  * "grad_tile_bits" (12), "mode" (1 = fused tile sweep, 0 = one factor per pass),
  * "sector" (1 = exploit particle-number/S_z conservation of the ansatz in H|psi>),
  * "sparse_tiles" (1 = compressed-sector tiles when the ansatz conserves N_alpha, N_beta),
- * "tile_threads" (256), "sparse_threads" (128). */
+ * "tile_threads" (256), "sparse_threads" (128), "sigma" (1 = link-table kernel for the sector
+ * form of H|psi>, 0 = first-generation X-group kernel). */
 int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value);
 
 /* Replaces: `mapping(fermi_ham,'JW',...)` + `get_sparse_operator(qubit_ham)`,
@@ -127,6 +128,17 @@ int mqc_expectation(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask, con
  * on the prepared state, restricted to the (n_alpha, n_beta) sector.  rdm2 may be NULL. */
 int mqc_rdm12(mqc_solver_t* s, int32_t n_orb, int32_t n_alpha, int32_t n_beta,
               double* rdm1, double* rdm2);
+
+/* Host-only check of the excitation link tables behind the sector form of H|psi>
+ * (csrc/mqc_sigma.h): builds them for the (n_alpha, n_beta) sector of an operator and applies
+ * them on one CPU thread to a sector matrix C[n_rows][n_cols] (complex128, alpha string major,
+ * strings in ascending integer order).  Terms the tables cannot express are counted in
+ * *n_fallback and left out.  Test infrastructure for the table construction; the CUDA kernel
+ * executes the same tables.  c_re_im / l_re_im may be NULL to query the sizes. */
+int mqc_sigma_host_apply(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int64_t n_terms,
+                         const uint64_t* xmask, const uint64_t* zmask, const double* coeff_re,
+                         const double* coeff_im, const double* c_re_im, double* l_re_im,
+                         int64_t* n_rows, int64_t* n_cols, int64_t* n_fallback);
 
 /* Device-side timing of the last energy / energy_grad call (CUDA events on the solver's
  * stream): ms[0] forward sweep, ms[1] H apply, ms[2] reverse sweep, ms[3] total;

@@ -46,6 +46,8 @@ SIGNATURES = {
     "mqc_expectation": [_H, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p],
     "mqc_rdm12": [_H, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p],
     "mqc_last_timing": [_H, _f64p, _i64p],
+    "mqc_sigma_host_apply": [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p,
+                             _i64p, _i64p, _i64p],
     "mqc_schedule_info": [_H, C.c_int32, _i32p, _i32p, _i32p],
     "mqc_schedule_pass": [_H, C.c_int32, C.c_int32, _i32p, _i32p, _u64p, _i32p, _i32p, _i32p],
     "mqc_schedule_factor": [_H, C.c_int32, C.c_int32, _u32p, _u32p, _u32p, _u64p, _i32p, _i32p],
@@ -98,6 +100,28 @@ def device_count() -> int:
     n = C.c_int32(0)
     check(load().mqc_device_count(C.byref(n)))
     return n.value
+
+
+def sigma_host_apply(n_qubits, n_alpha, n_beta, table, c_sector=None):
+    """Host-only evaluation of the link tables (see include/mqc_b200.h).  Returns
+    (L or None, (n_rows, n_cols), n_fallback_terms)."""
+    lib = load()
+    x = np.ascontiguousarray(table[0], dtype=np.uint64)
+    z = np.ascontiguousarray(table[1], dtype=np.uint64)
+    c = np.asarray(table[2], dtype=np.complex128)
+    cr, ci = np.ascontiguousarray(c.real), np.ascontiguousarray(c.imag)
+    nr, nc, nf = C.c_int64(), C.c_int64(), C.c_int64()
+    check(lib.mqc_sigma_host_apply(n_qubits, n_alpha, n_beta, len(x), ptr(x, _u64p), ptr(z, _u64p), ptr(cr, _f64p),
+                                   ptr(ci, _f64p), None, None, C.byref(nr), C.byref(nc), C.byref(nf)))
+    out = None
+    if c_sector is not None:
+        cs = np.ascontiguousarray(c_sector, dtype=np.complex128)
+        assert cs.shape == (nr.value, nc.value)
+        out = np.zeros_like(cs)
+        check(lib.mqc_sigma_host_apply(n_qubits, n_alpha, n_beta, len(x), ptr(x, _u64p), ptr(z, _u64p), ptr(cr, _f64p),
+                                       ptr(ci, _f64p), C.cast(cs.ctypes.data, _f64p), C.cast(out.ctypes.data, _f64p),
+                                       C.byref(nr), C.byref(nc), C.byref(nf)))
+    return out, (nr.value, nc.value), nf.value
 
 
 class Handle:

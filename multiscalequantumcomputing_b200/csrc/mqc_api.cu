@@ -15,6 +15,7 @@
 #include "mqc_common.h"
 #include "mqc_kernels.cuh"
 #include "mqc_schedule.h"
+#include "mqc_sigma.h"
 
 static thread_local std::string g_err;
 
@@ -81,6 +82,17 @@ struct SecHamTables {               // Hamiltonian in sector form for one layout
     }
 };
 
+struct SigmaTables {                // link-table form of a sector Hamiltonian (mqc_sigma.h), layout independent
+    DevBuf<unsigned> lnk_a1, lnk_a2, ell_b1, ell_b2, m2_mask, sa_b2, sb_a2, sa_b4, sb_a4, aorb, borb;
+    DevBuf<int> cls_off, cls_of_m2;
+    DevBuf<double> w22, w4a, w4b, ta1, tb1, tab, tbb, hdiag, diag_c;
+    DevBuf<u64> aq, bq, diag_z;
+    MqcSigmaDev dev{};
+    bool ready = false;
+    unsigned row0 = 0, row1 = 0;
+    size_t n_fallback = 0, n_fast = 0;
+};
+
 struct LayoutTables {
     std::vector<int> phys;          // logical bit -> physical position
     HamTables ham;
@@ -138,7 +150,9 @@ struct mqc_solver {
     double* grad_p() const { return mail.p + MQC_MAIL_GRAD; }
     unsigned long long* flags_p() const { return reinterpret_cast<unsigned long long*>(mail.p + MQC_MAIL_FLAGS); }
 
-    HamHost ham;
+    HamHost ham, ham_fb;            // all terms / the terms the link-table kernel leaves to k_happly_sector
+    SigmaTables sig;
+    int use_sigma = 1;
     bool have_ham = false, have_ansatz = false;
 
     std::vector<MqcFactor> fac;     // logical coordinates
@@ -237,6 +251,8 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_tile_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_tile_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_sigma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000));
+    CK(cudaFuncSetAttribute(k_sigma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000));
     s->gpu_ready = true;
 }
 
@@ -425,6 +441,54 @@ static MqcSectorDev sector_dev(const LayoutTables& L, bool enabled) {
     return S;
 }
 
+static u64 logical_to_qubit(u64 m, int n) {
+    u64 out = 0;
+    for (int q = 0; q < n; ++q) if ((m >> (n - 1 - q)) & 1ull) out |= 1ull << q;
+    return out;
+}
+
+static void row_slice(const mqc_solver* s, unsigned n_rows, unsigned& r0, unsigned& r1) {
+    r0 = (unsigned)(((u64)n_rows * s->rank) / s->n_ranks);
+    r1 = (unsigned)(((u64)n_rows * (s->rank + 1)) / s->n_ranks);
+}
+
+// link tables of operator H for the (na, nb) sector; the terms they do not cover go to `fb`
+static void build_sigma(mqc_solver* s, const HamHost& H, int na, int nb, SigmaTables& T, HamHost& fb) {
+    const int n = s->n, n_orb = n / 2;
+    std::vector<u64> xq(H.x.size()), zq(H.x.size());
+    for (size_t t = 0; t < H.x.size(); ++t) { xq[t] = logical_to_qubit(H.x[t], n); zq[t] = logical_to_qubit(H.z[t], n); }
+    MqcSigmaHost S = mqc_sigma_build(n_orb, na, nb, xq, zq, H.c);
+    fb.x.clear(); fb.z.clear(); fb.c.clear();
+    for (size_t t : S.fallback_terms) { fb.x.push_back(H.x[t]); fb.z.push_back(H.z[t]); fb.c.push_back(H.c[t]); }
+    T.n_fallback = S.fallback_terms.size(); T.n_fast = S.n_fast_terms;
+    cudaStream_t st = s->stream;
+    T.lnk_a1.upload(S.lnk_a1, st); T.lnk_a2.upload(S.lnk_a2, st); T.ell_b1.upload(S.ell_b1, st); T.ell_b2.upload(S.ell_b2, st);
+    T.m2_mask.upload(S.m2_mask.empty() ? std::vector<unsigned>(1, 0) : S.m2_mask, st);
+    T.sa_b2.upload(S.sa_b2, st); T.sb_a2.upload(S.sb_a2, st); T.sa_b4.upload(S.sa_b4, st); T.sb_a4.upload(S.sb_a4, st);
+    T.aorb.upload(S.aorb, st); T.borb.upload(S.borb, st);
+    T.cls_off.upload(S.cls_off, st); T.cls_of_m2.upload(S.cls_of_m2, st);
+    T.w22.upload(S.w22, st); T.w4a.upload(S.w4a, st); T.w4b.upload(S.w4b, st);
+    T.ta1.upload(S.ta1, st); T.tb1.upload(S.tb1, st); T.tab.upload(S.tab, st); T.tbb.upload(S.tbb, st);
+    T.aq.upload(S.aq, st); T.bq.upload(S.bq, st);
+    if (S.diag_z.empty()) { S.diag_z.push_back(0); S.diag_c.push_back(0.0); }
+    T.diag_z.upload(S.diag_z, st); T.diag_c.upload(S.diag_c, st);
+    row_slice(s, S.n_a, T.row0, T.row1);
+    const u64 cnt = (u64)(T.row1 - T.row0) * S.n_b;
+    T.hdiag.alloc(std::max<u64>(1, cnt));
+    if (cnt) k_sigma_hdiag<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(T.aq.p, T.bq.p, T.diag_z.p, T.diag_c.p, (int)S.diag_z.size(),
+                                                                          T.row0, T.row1, S.n_b, T.hdiag.p);
+    MqcSigmaDev D{};
+    D.n_a = S.n_a; D.n_b = S.n_b; D.n_m2 = S.n_m2; D.n_m4 = S.n_m4;
+    D.lnk_a1 = T.lnk_a1.p; D.e1a = S.e1a; D.lnk_a2 = T.lnk_a2.p; D.e2a = S.e2a;
+    D.ell_b1 = T.ell_b1.p; D.cls_off = T.cls_off.p; D.cls_of_m2 = T.cls_of_m2.p; D.ell_b2 = T.ell_b2.p; D.e2b = S.e2b;
+    D.w22 = T.w22.p; D.w4a = T.w4a.p; D.w4b = T.w4b.p; D.ta1 = T.ta1.p; D.tb1 = T.tb1.p; D.tab = T.tab.p; D.tbb = T.tbb.p;
+    D.m2_mask = T.m2_mask.p; D.sa_b2 = T.sa_b2.p; D.sb_a2 = T.sb_a2.p; D.sa_b4 = T.sa_b4.p; D.sb_a4 = T.sb_a4.p;
+    D.aorb = T.aorb.p; D.borb = T.borb.p; D.hdiag = T.hdiag.p; D.row0 = T.row0;
+    T.dev = D;
+    CK(cudaStreamSynchronize(st));
+    T.ready = true;
+}
+
 static void ensure_layout_ready(mqc_solver* s, int which) {
     LayoutTables& L = s->lay[which];
     if (!s->have_ham) throw MqcError("mqc_set_hamiltonian has not been called");
@@ -434,7 +498,9 @@ static void ensure_layout_ready(mqc_solver* s, int which) {
     }
     if (s->conserving && s->use_sector) {
         build_sector_tables(s, L, s->na, s->nb);
-        if (!L.sham_ready) { build_sec_ham(s, s->ham, L.phys, L.sham); L.sham_ready = true; }
+        const bool sigma = s->use_sigma && s->n / 2 <= 18;
+        if (sigma && !s->sig.ready) build_sigma(s, s->ham, s->na, s->nb, s->sig, s->ham_fb);
+        if (!L.sham_ready) { build_sec_ham(s, sigma ? s->ham_fb : s->ham, L.phys, L.sham); L.sham_ready = true; }
     }
 }
 
@@ -581,13 +647,8 @@ static void forward(mqc_solver* L, int which, const double* theta) {
     for (mqc_solver* s : L->members) s->state_layout = which;
 }
 
-static void row_slice(const mqc_solver* s, unsigned n_rows, unsigned& r0, unsigned& r1) {
-    r0 = (unsigned)(((u64)n_rows * s->rank) / s->n_ranks);
-    r1 = (unsigned)(((u64)n_rows * (s->rank + 1)) / s->n_ranks);
-}
-
 // lambda = H psi (optional) and this group's energy partials in every member's scalars
-struct HamView { const HamTables* T; const SecHamTables* ST; };
+struct HamView { const HamTables* T; const SecHamTables* ST; const SigmaTables* SG; };
 static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, bool want_lam) {
     const bool sec = L->conserving && L->use_sector && views[0].ST;
     for (size_t i = 0; i < L->members.size(); ++i) {
@@ -605,13 +666,28 @@ static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, 
             unsigned r0, r1;
             row_slice(s, nA, r0, r1);
             if (r1 > r0) {
-                unsigned bd = 256;
-                while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
-                dim3 grid(r1 - r0, (nB + bd * MQC_HS_R - 1) / (bd * MQC_HS_R));
-                k_happly_sector<<<grid, bd, 0, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr,
-                                                            sec_ham_dev(Lt, *views[i].ST), s->scalars_p(), r0);
+                const SigmaTables* SG = views[i].SG;
+                bool have = false;
+                if (SG && SG->ready) {
+                    MqcSigmaDev D = SG->dev;
+                    const bool stage = (size_t)nB * sizeof(double2) <= 65536;
+                    const size_t smem = mqc_sigma_smem_bytes(D, stage);
+                    dim3 grid(r1 - r0, (nB + MQC_SG_THREADS * MQC_SG_R - 1) / (MQC_SG_THREADS * MQC_SG_R));
+                    if (stage) k_sigma<true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
+                    else k_sigma<false><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
+                    s->counters[0]++;
+                    have = true;
+                }
+                if (!have || SG->n_fallback) {
+                    unsigned bd = 256;
+                    while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
+                    dim3 grid(r1 - r0, (nB + bd * MQC_HS_R - 1) / (bd * MQC_HS_R));
+                    k_happly_sector<<<grid, bd, 0, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr,
+                                                                sec_ham_dev(Lt, *views[i].ST), s->scalars_p(), r0, have ? 1 : 0);
+                    s->counters[0]++;
+                }
             }
-            s->counters[0] += 2;
+            s->counters[0] += 1;
             if (want_lam) CK(cudaMemsetAsync(s->lam.p, 0, sizeof(double2) * s->dim, s->stream));
         } else {
             MqcSectorDev S = sector_dev(Lt, false);
@@ -713,7 +789,8 @@ static void finish_timing(mqc_solver* s, bool with_reverse) {
 
 static std::vector<HamView> own_views(mqc_solver* L, int which) {
     std::vector<HamView> v;
-    for (mqc_solver* s : L->members) v.push_back(HamView{&s->lay[which].ham, &s->lay[which].sham});
+    for (mqc_solver* s : L->members)
+        v.push_back(HamView{&s->lay[which].ham, &s->lay[which].sham, (s->use_sigma && s->sig.ready) ? &s->sig : nullptr});
     return v;
 }
 
@@ -849,6 +926,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "tile_threads") s->tile_threads = (int)value;
     else if (k == "sparse_tiles") s->sparse_tiles = (int)value;
     else if (k == "sparse_threads") s->sparse_threads = (int)value;
+    else if (k == "sigma") s->use_sigma = (int)value;
     else throw MqcError("unknown option: " + k);
     if (s->tile_bits < 5 || s->tile_bits > MQC_MAX_TILE_BITS || s->grad_tile_bits < 5 || s->grad_tile_bits > MQC_MAX_TILE_BITS - 1)
         throw MqcError("tile_bits must be in [5,13], grad_tile_bits in [5,12]");
@@ -881,6 +959,7 @@ int mqc_set_hamiltonian(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask,
         s->have_ham = true;
         s->lay[0].ham_ready = s->lay[1].ham_ready = false;
         s->lay[0].sham_ready = s->lay[1].sham_ready = false;
+        s->sig.ready = false;
     }
     MQC_CATCH
 }
@@ -932,6 +1011,7 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
     }
     s->have_ansatz = true;
     s->state_layout = -1;
+    s->sig.ready = false;
     s->connected = (s->n_ranks == 1);
     // device side is set up lazily so that schedules can be inspected without a GPU
     int cnt = 0;
@@ -1206,13 +1286,19 @@ int mqc_expectation(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask, con
     const size_t nm = L->members.size();
     std::vector<HamTables> T(nm);
     std::vector<SecHamTables> ST(nm);
+    std::vector<SigmaTables> SG(nm);
     std::vector<HamView> views;
     for (size_t i = 0; i < nm; ++i) {
         mqc_solver* s = L->members[i];
         CK(cudaSetDevice(s->device));
-        if (sec) { build_sector_tables(s, s->lay[w], s->na, s->nb); build_sec_ham(s, H, s->lay[w].phys, ST[i]); }
-        else build_ham_tables(s, H, s->lay[w].phys, T[i]);
-        views.push_back(HamView{&T[i], sec ? &ST[i] : nullptr});
+        const bool sigma = sec && s->use_sigma && s->n / 2 <= 18;
+        if (sec) {
+            build_sector_tables(s, s->lay[w], s->na, s->nb);
+            HamHost fb;
+            if (sigma) build_sigma(s, H, s->na, s->nb, SG[i], fb);
+            build_sec_ham(s, sigma ? fb : H, s->lay[w].phys, ST[i]);
+        } else build_ham_tables(s, H, s->lay[w].phys, T[i]);
+        views.push_back(HamView{&T[i], sec ? &ST[i] : nullptr, sigma ? &SG[i] : nullptr});
     }
     double val[2] = {0, 0};
     happly(L, w, views, false);
@@ -1334,6 +1420,31 @@ int mqc_schedule_factor(mqc_solver_t* s, int32_t which, int32_t tile_factor, uin
     if (z_out) *z_out = F.z_out;
     if (sign0) *sign0 = F.sign0;
     if (slot) *slot = F.slot;
+    MQC_CATCH
+}
+
+// Host-only: build the link tables of an operator for the (n_alpha, n_beta) sector and apply
+// them to a sector matrix C[n_a][n_b] on ONE CPU thread (tests of the table construction; the
+// kernels k_sigma<> execute exactly these tables).  Terms the tables do not cover are counted
+// in *n_fallback and left out of L.
+int mqc_sigma_host_apply(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int64_t n_terms, const uint64_t* xmask,
+                         const uint64_t* zmask, const double* coeff_re, const double* coeff_im, const double* c_re_im,
+                         double* l_re_im, int64_t* n_rows, int64_t* n_cols, int64_t* n_fallback) {
+    MQC_TRY
+    if (n_qubits < 2 || n_qubits > 36 || (n_qubits & 1)) throw MqcError("n_qubits must be even, <= 36");
+    if (n_terms < 0 || (n_terms && (!xmask || !zmask || !coeff_re))) throw MqcError("bad arguments");
+    std::vector<u64> xq(n_terms), zq(n_terms);
+    std::vector<double2> cf(n_terms);
+    for (int64_t t = 0; t < n_terms; ++t) {
+        xq[t] = logical_to_qubit(xmask[t], n_qubits); zq[t] = logical_to_qubit(zmask[t], n_qubits);
+        cf[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
+    }
+    MqcSigmaHost S = mqc_sigma_build(n_qubits / 2, n_alpha, n_beta, xq, zq, cf);
+    if (n_rows) *n_rows = S.n_a;
+    if (n_cols) *n_cols = S.n_b;
+    if (n_fallback) *n_fallback = (int64_t)S.fallback_terms.size();
+    if (c_re_im && l_re_im)
+        mqc_sigma_apply_host(S, reinterpret_cast<const double2*>(c_re_im), reinterpret_cast<double2*>(l_re_im));
     MQC_CATCH
 }
 

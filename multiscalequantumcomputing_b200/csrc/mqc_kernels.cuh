@@ -744,7 +744,7 @@ __device__ __forceinline__ unsigned pext_small(unsigned x, unsigned m) {   // ga
 
 __global__ void __launch_bounds__(256)
 k_happly_sector(const double2* __restrict__ C, double2* __restrict__ L, const MqcSecHamDev H,
-                double* __restrict__ e_out, const unsigned ia0) {
+                double* __restrict__ e_out, const unsigned ia0, const int accumulate) {
     __shared__ double red[2][8];
     const unsigned iap = ia0 + blockIdx.x;
     const unsigned ap = H.aorb[iap];
@@ -865,7 +865,10 @@ k_happly_sector(const double2* __restrict__ C, double2* __restrict__ L, const Mq
     for (int r = 0; r < MQC_HS_R; ++r) {
         if (ibp[r] < H.n_b) {
             const size_t o = (size_t)iap * H.n_b + ibp[r];
-            if (L) L[o] = make_double2(ar[r], ai[r]);
+            if (L) {
+                if (accumulate) { const double2 o0 = L[o]; L[o] = make_double2(o0.x + ar[r], o0.y + ai[r]); }
+                else L[o] = make_double2(ar[r], ai[r]);
+            }
             const double2 py = C[o];
             er += py.x * ar[r] + py.y * ai[r];
             ei += py.x * ai[r] - py.y * ar[r];
