@@ -140,6 +140,12 @@ int mqc_sigma_host_apply(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int6
                          const double* coeff_im, const double* c_re_im, double* l_re_im,
                          int64_t* n_rows, int64_t* n_cols, int64_t* n_fallback);
 
+/* Host-only check of the compressed-sector tile plan (pattern tables and per-factor pair lists
+ * that k_tile_sp2 walks): executes schedule `which` on one CPU thread and returns the state in
+ * OpenFermion order.  Unsharded handles up to 22 qubits. */
+int mqc_sparse_plan_host_state(mqc_solver_t* s, int32_t which, const double* theta, double* re_im,
+                               int64_t n_amplitudes);
+
 /* Device-side timing of the last energy / energy_grad call (CUDA events on the solver's
  * stream): ms[0] forward sweep, ms[1] H apply, ms[2] reverse sweep, ms[3] total;
  * counters[0] kernel launches, counters[1] forward passes, counters[2] reverse passes. */

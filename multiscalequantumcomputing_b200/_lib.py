@@ -46,6 +46,7 @@ SIGNATURES = {
     "mqc_expectation": [_H, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p],
     "mqc_rdm12": [_H, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p],
     "mqc_last_timing": [_H, _f64p, _i64p],
+    "mqc_sparse_plan_host_state": [_H, C.c_int32, _f64p, _f64p, C.c_int64],
     "mqc_sigma_host_apply": [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p,
                              _i64p, _i64p, _i64p],
     "mqc_schedule_info": [_H, C.c_int32, _i32p, _i32p, _i32p],
@@ -211,6 +212,13 @@ class Handle:
         out = np.empty(1 << self.n_qubits, dtype=np.complex128)
         tp = ptr(self._theta(theta), _f64p) if theta is not None else None
         check(self.lib.mqc_state(self.h, tp, C.cast(out.ctypes.data, _f64p), out.shape[0]))
+        return out
+
+    def sparse_plan_host_state(self, theta, which=0) -> np.ndarray:
+        """CPU execution of the compressed-sector tile plan (test of the plan tables)."""
+        out = np.empty(1 << self.n_qubits, dtype=np.complex128)
+        t = self._theta(theta)
+        check(self.lib.mqc_sparse_plan_host_state(self.h, which, ptr(t, _f64p), C.cast(out.ctypes.data, _f64p), out.shape[0]))
         return out
 
     def expectation(self, xmask, zmask, coeff) -> complex:

@@ -138,6 +138,7 @@ struct mqc_solver {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t user_ev[2] = {nullptr, nullptr};
     bool gpu_ready = false;
+    int n_sm = 148;
 
     // options
     int tile_bits = 12, low_bits = 3, grad_tile_bits = 12, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
@@ -146,6 +147,11 @@ struct mqc_solver {
     DevBuf<double> theta, mail, red, rdm_acc;
     DevBuf<int> theta_index, err;
     DevBuf<MqcTileFactor> tf[2];
+    MqcSparsePlan plan[2];          // compressed-sector tile plan per schedule (host copy of the pass records)
+    DevBuf<u64> pl_dep[2], pl_depp[2];
+    DevBuf<uint32_t> pl_lists[2];
+    DevBuf<uint2> pl_hdr[2];
+    int sp2 = 1, sp2_warps = 4;
     double* scalars_p() const { return mail.p; }
     double* grad_p() const { return mail.p + MQC_MAIL_GRAD; }
     unsigned long long* flags_p() const { return reinterpret_cast<unsigned long long*>(mail.p + MQC_MAIL_FLAGS); }
@@ -245,12 +251,15 @@ static void require_gpu(mqc_solver* s) {
     if (s->device >= cnt) throw MqcError("device index out of range");
     CK(cudaSetDevice(s->device));
     CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CK(cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, s->device));
     for (auto& e2 : s->ev) CK(cudaEventCreate(&e2));
     CK(cudaEventCreateWithFlags(&s->sync_ev, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(k_tile_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_tile_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_tile_sp2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_tile_sp2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_sigma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000));
     CK(cudaFuncSetAttribute(k_sigma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000));
     s->gpu_ready = true;
@@ -565,6 +574,23 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
     PR.tau_hi = TM.tau_hi; PR.fixed_bits = TM.fixed_bits;
     CK(cudaSetDevice(s->device));
     const bool sparse = s->conserving && s->use_sector && s->sparse_tiles;
+    if (sparse && s->sp2 && s->plan[which].ok) {
+        const MqcSpPass& SPP = s->plan[which].pass[pass];
+        int warps = s->sp2_warps;
+        size_t smem = mqc_sp2_smem_bytes(SPP.cap, nf, adj, warps);
+        while (warps > 1 && smem > 200000) { warps >>= 1; smem = mqc_sp2_smem_bytes(SPP.cap, nf, adj, warps); }
+        if (smem <= 200000) {
+            int per_sm = (int)std::min<size_t>(16, (220 * 1024) / (smem + 1024));
+            per_sm = std::max(1, std::min(per_sm, 64 / warps));
+            const u64 want = (TM.n_tiles + warps - 1) / warps;
+            const unsigned g2 = (unsigned)std::min<u64>(want, (u64)s->n_sm * per_sm);
+            MqcSpTables TB{s->pl_dep[which].p, s->pl_depp[which].p, s->pl_lists[which].p, s->pl_hdr[which].p};
+            if (adj) k_tile_sp2<true><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, s->grad_p(), reverse, TM.n_tiles);
+            else k_tile_sp2<false><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, nullptr, reverse, TM.n_tiles);
+            s->counters[0]++;
+            return;
+        }
+    }
     if (sparse) {
         // alpha = even qubits, beta = odd qubits.  Tile-local coordinates are those of the
         // forward pass's LOAD layout in both directions (the reverse pass un-permutes while
@@ -927,6 +953,8 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sparse_tiles") s->sparse_tiles = (int)value;
     else if (k == "sparse_threads") s->sparse_threads = (int)value;
     else if (k == "sigma") s->use_sigma = (int)value;
+    else if (k == "sp2") s->sp2 = (int)value;
+    else if (k == "sp2_warps") { if (value < 1 || value > 8) throw MqcError("sp2_warps must be in [1,8]"); s->sp2_warps = (int)value; }
     else throw MqcError("unknown option: " + k);
     if (s->tile_bits < 5 || s->tile_bits > MQC_MAX_TILE_BITS || s->grad_tile_bits < 5 || s->grad_tile_bits > MQC_MAX_TILE_BITS - 1)
         throw MqcError("tile_bits must be in [5,13], grad_tile_bits in [5,12]");
@@ -1006,6 +1034,11 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
     for (int q = 0; q < n; ++q)
         if ((ref_index >> (n - 1 - q)) & 1ull) { if (q & 1) s->nb++; else s->na++; }
     for (int w = 0; w < 2; ++w) {
+        if (copy_from) s->plan[w] = copy_from->plan[w];
+        else if (s->conserving && s->mode == 1) s->plan[w] = mqc_build_sparse_plan(s->sched[w], s->na, s->nb);
+        else s->plan[w] = MqcSparsePlan();
+    }
+    for (int w = 0; w < 2; ++w) {
         s->lay[w].reset();
         s->lay[w].phys = s->sched[w].phys_final;
     }
@@ -1028,6 +1061,14 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         s->epoch = 0;
         s->cs.alloc(std::max(1, n_factors));
         for (int w = 0; w < 2; ++w) {
+            if (s->plan[w].ok) {
+                s->pl_dep[w].upload(s->plan[w].dep, s->stream);
+                s->pl_depp[w].upload(s->plan[w].depp, s->stream);
+                s->pl_lists[w].upload(s->plan[w].lists, s->stream);
+                std::vector<uint2> hd(s->plan[w].hdr.size() / 2);
+                for (size_t i = 0; i < hd.size(); ++i) hd[i] = make_uint2(s->plan[w].hdr[2 * i], s->plan[w].hdr[2 * i + 1]);
+                s->pl_hdr[w].upload(hd, s->stream);
+            }
             s->tf[w].upload(s->sched[w].tf, s->stream);
             std::vector<int> ph = s->lay[w].phys;
             s->lay[w].phys_dev.upload(ph, s->stream);
@@ -1420,6 +1461,29 @@ int mqc_schedule_factor(mqc_solver_t* s, int32_t which, int32_t tile_factor, uin
     if (z_out) *z_out = F.z_out;
     if (sign0) *sign0 = F.sign0;
     if (slot) *slot = F.slot;
+    MQC_CATCH
+}
+
+// Host-only: run the compressed-sector tile plan of schedule `which` on the CPU (one thread)
+// and return the state in OpenFermion order.  Tests of the plan tables; small registers only.
+int mqc_sparse_plan_host_state(mqc_solver_t* s, int32_t which, const double* theta, double* re_im, int64_t n_amplitudes) {
+    MQC_TRY
+    if (!s || which < 0 || which > 1 || !s->have_ansatz || !theta || !re_im) throw MqcError("bad arguments");
+    if (s->n > 22 || s->n_ranks > 1 || s->mode != 1) throw MqcError("host plan execution: unsharded tile schedules up to 22 qubits");
+    if (!s->conserving) throw MqcError("the ansatz does not conserve (N_alpha, N_beta)");
+    if ((u64)n_amplitudes != (1ull << s->n)) throw MqcError("state buffer must hold 2^N amplitudes");
+    const MqcSchedule& S = s->sched[which];
+    MqcSparsePlan PL = mqc_build_sparse_plan(S, s->na, s->nb);
+    if (!PL.ok) throw MqcError("no sparse plan for this schedule");
+    const size_t dim = (size_t)1 << s->n;
+    std::vector<double> re(dim, 0.0), im(dim, 0.0), cv(s->fac.size()), sv(s->fac.size());
+    for (size_t k = 0; k < s->fac.size(); ++k) { cv[k] = std::cos(theta[s->fac[k].theta]); sv[k] = std::sin(theta[s->fac[k].theta]); }
+    re[mqc_map_mask(s->ref_index, S.phys_init)] = 1.0;
+    mqc_sparse_plan_forward_host(S, PL, re, im, cv, sv);
+    for (size_t i = 0; i < dim; ++i) {
+        const u64 p = mqc_map_mask((u64)i, S.phys_final);
+        re_im[2 * i] = re[p]; re_im[2 * i + 1] = im[p];
+    }
     MQC_CATCH
 }
 

@@ -58,6 +58,23 @@ struct MqcPass {
     uint8_t perm[16];       // forward store: new local bit j' <- old local bit perm[j']
 };
 
+// Compressed-sector tile plan (second generation).  With a_act alpha and b_act beta active
+// bits, the non-zero amplitudes of a tile are the product set  {alpha-local patterns with ka
+// bits} x {beta-local patterns with kb bits}; slot = ja * cntB[kb] + jb with ja / jb the ranks
+// of the patterns (ascending local-mask value).  Per pass and per (factor, ka) [resp. kb] the
+// host tabulates the pattern pairs the factor couples on that spin species, so the kernel
+// enumerates exactly the coupled slot pairs (pair list A x pair list B) instead of scanning.
+#define MQC_SP_KMAX 17
+struct MqcSpPass {
+    uint32_t patoffA[MQC_SP_KMAX], patoffB[MQC_SP_KMAX];   // first pattern of class ka / kb in dep[] / depp[]
+    uint16_t cntA[MQC_SP_KMAX], cntB[MQC_SP_KMAX];         // C(a_act, ka), C(b_act, kb)
+    uint32_t hdrA_off, hdrB_off;                           // header (factor, k) -> {list offset, count}
+    int32_t a_act, b_act;
+    u64 amask, bmask;                                      // physical masks of alpha / beta qubits (load layout)
+    int32_t na, nb, cap;                                   // sector, max slots of any tile of this pass
+};
+// pair list entry: lo pattern rank (12) | hi pattern rank << 12 | in-tile parity << 24
+
 // insert zero bits at the (ascending) positions pos[0..npos)
 MQC_HD u64 mqc_insert_zeros(u64 u, const int32_t* pos, int npos) {
     for (int i = 0; i < npos; ++i) {

@@ -340,6 +340,156 @@ k_tile_sparse(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPa
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 / K3, sector form, second generation: one WARP per compressed tile, pair lists
+// ------------------------------------------------------------------------------------------
+// The non-zero amplitudes of a tile are the product set {alpha-local patterns with ka bits} x
+// {beta-local patterns with kb bits} (MqcSpPass): slot = ja * nBl + jb.  The host tabulates,
+// per (factor, ka) and (factor, kb), the pattern pairs the factor couples on each spin species
+// (identity pairs where it does not act), so the lanes of a warp enumerate exactly the coupled
+// slot pairs  listA x listB  - no scan over the tile, no index->slot map, no block barrier: a
+// warp owns its tile and factors are separated by __syncwarp().  Warps are persistent (grid =
+// resident warps, tiles strided), which also lets a CTA sum its gradient partials in shared
+// memory and issue one global atomic per (CTA, factor) instead of one per (tile, factor).
+struct MqcSpTables {
+    const u64* dep;            // pattern -> physical offset, load layout
+    const u64* depp;           // pattern -> physical offset, other layout of a re-layout pass
+    const uint32_t* lists;     // pair lists
+    const uint2* hdr;          // (factor, k) -> {first entry, count}
+};
+#define MQC_SP2_HDR_BYTES (32 * (16 + 8 + 8 + 4 + 4))
+
+template <bool ADJ>
+__global__ void __launch_bounds__(256)
+k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass P, const __grid_constant__ MqcSpPass SP,
+           const MqcSpTables TB, const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
+           double* __restrict__ grad, const int reverse, const u64 n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nf = P.f1 - P.f0;
+    const int cap = SP.cap;
+    const size_t per_warp = (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2) + MQC_SP2_HDR_BYTES;
+    unsigned char* wb = smem_raw + (size_t)warp * per_warp;
+    double2* sp = reinterpret_cast<double2*>(wb);
+    double2* sl = sp + (ADJ ? cap : 0);
+    unsigned char* q = wb + (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2);
+    double2* hcs = reinterpret_cast<double2*>(q);   q += 32 * sizeof(double2);
+    uint2* hA = reinterpret_cast<uint2*>(q);        q += 32 * sizeof(uint2);
+    uint2* hB = reinterpret_cast<uint2*>(q);        q += 32 * sizeof(uint2);
+    uint32_t* hsg = reinterpret_cast<uint32_t*>(q); q += 32 * sizeof(uint32_t);
+    int* hfi = reinterpret_cast<int*>(q);
+    double* gblk = reinterpret_cast<double*>(smem_raw + (size_t)W * per_warp);
+    if (ADJ) {
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) gblk[i] = 0.0;
+        __syncthreads();
+    }
+    const bool alt_load = reverse && P.has_perm, alt_store = (!reverse) && P.has_perm;
+    const u64* __restrict__ dl = alt_load ? TB.depp : TB.dep;
+    const u64* __restrict__ ds = alt_store ? TB.depp : TB.dep;
+
+    for (u64 tile = (u64)blockIdx.x * W + warp; tile < n_tiles; tile += (u64)gridDim.x * W) {
+        const u64 base = mqc_deposit_complement(tile | PR.tau_hi, P.act_mask, PR.n_local) | PR.fixed_bits;
+        const int ka = SP.na - __popcll(base & SP.amask);
+        const int kb = SP.nb - __popcll(base & SP.bmask);
+        if (ka < 0 || kb < 0 || ka > SP.a_act || kb > SP.b_act) continue;       // tile holds only zeros
+        const int nAl = SP.cntA[ka], nBl = SP.cntB[kb];
+        const int cnt = nAl * nBl;
+        const uint32_t offA = SP.patoffA[ka], offB = SP.patoffB[kb];
+        const float rcpB = __frcp_rn((float)nBl);
+        __syncwarp();                                             // previous tile's stores have read sp / sl
+        // ---- load ---------------------------------------------------------------------------
+        for (int e = lane; e < cnt; e += 32) {
+            const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
+            const u64 g = base | __ldg(dl + offA + ja) | __ldg(dl + offB + jb);
+            cp_async16(sp + e, peer_psi(PR, g));
+            if (ADJ) cp_async16(sl + e, peer_lam(PR, g));
+        }
+        // ---- factors ------------------------------------------------------------------------
+        for (int c0 = 0; c0 < nf; c0 += 32) {
+            const int nc = min(32, nf - c0);
+            __syncwarp();                                         // previous chunk's headers are consumed
+            if (lane < nc) {
+                const int f = reverse ? (nf - 1 - (c0 + lane)) : (c0 + lane);
+                const MqcTileFactor* Fp = tf + P.f0 + f;
+                const double2 v = cs[Fp->slot];
+                hcs[lane] = make_double2(v.x, reverse ? -v.y : v.y);
+                hA[lane] = __ldg(TB.hdr + SP.hdrA_off + (size_t)f * MQC_SP_KMAX + ka);
+                hB[lane] = __ldg(TB.hdr + SP.hdrB_off + (size_t)f * MQC_SP_KMAX + kb);
+                hsg[lane] = ((uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
+                hfi[lane] = f;
+            }
+            if (c0 == 0) cp_async_wait_all();
+            __syncwarp();
+            for (int fc = 0; fc < nc; ++fc) {
+                const uint2 A = hA[fc], B = hB[fc];
+                const int nLB = (int)B.y;
+                const int npairs = (int)A.y * nLB;
+                if (npairs == 0) continue;                        // uniform over the warp
+                const double2 csv = hcs[fc];
+                const double c = csv.x, sn = csv.y;
+                const uint32_t sg = hsg[fc];
+                const float rcp = __frcp_rn((float)nLB);
+                double gacc = 0.0;
+                for (int u = lane; u < npairs; u += 32) {
+                    const int ua = (int)(((float)u + 0.5f) * rcp), ub = u - ua * nLB;
+                    const uint32_t la = __ldg(TB.lists + A.x + ua), lb = __ldg(TB.lists + B.x + ub);
+                    const int e0 = (int)(la & 0xfffu) * nBl + (int)(lb & 0xfffu);
+                    const int e1 = (int)((la >> 12) & 0xfffu) * nBl + (int)((lb >> 12) & 0xfffu);
+                    const bool neg = ((((la ^ lb) >> 24) ^ sg) & 1u) != 0u;
+                    const double ssn = neg ? -sn : sn;
+                    const double2 a = sp[e0], b = sp[e1];
+                    if (ADJ) {
+                        const double2 xa = sl[e0], xb = sl[e1];
+                        const double gv = xb.x * a.x + xb.y * a.y - xa.x * b.x - xa.y * b.y;
+                        gacc += neg ? -gv : gv;
+                        sl[e0] = make_double2(c * xa.x - ssn * xb.x, c * xa.y - ssn * xb.y);
+                        sl[e1] = make_double2(c * xb.x + ssn * xa.x, c * xb.y + ssn * xa.y);
+                    }
+                    sp[e0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
+                    sp[e1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
+                }
+                if (ADJ) {
+                    gacc = warp_sum(gacc);
+                    if (lane == 0 && gacc != 0.0) atomicAdd(gblk + hfi[fc], gacc);
+                }
+                __syncwarp();
+            }
+        }
+        if (nf == 0) { cp_async_wait_all(); __syncwarp(); }
+        // ---- store --------------------------------------------------------------------------
+        // a re-layout pass moves the elements to other addresses of the same tile: clear the
+        // addresses they came from first (everything outside the sector stays exactly zero)
+        if (P.has_perm) {
+            for (int e = lane; e < cnt; e += 32) {
+                const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
+                const u64 g = base | __ldg(dl + offA + ja) | __ldg(dl + offB + jb);
+                *peer_psi(PR, g) = make_double2(0.0, 0.0);
+                if (ADJ) *peer_lam(PR, g) = make_double2(0.0, 0.0);
+            }
+            __syncwarp();
+        }
+        for (int e = lane; e < cnt; e += 32) {
+            const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
+            const u64 g = base | __ldg(ds + offA + ja) | __ldg(ds + offB + jb);
+            *peer_psi(PR, g) = sp[e];
+            if (ADJ) *peer_lam(PR, g) = sl[e];
+        }
+    }
+    if (ADJ) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+            const double g = gblk[i];
+            if (g != 0.0) atomicAdd(grad + tf[P.f0 + i].theta, 2.0 * g);
+        }
+    }
+}
+
+static inline size_t mqc_sp2_smem_bytes(int cap, int nf, bool adj, int warps) {
+    size_t b = (size_t)warps * ((size_t)(adj ? 2 : 1) * cap * sizeof(double2) + MQC_SP2_HDR_BYTES);
+    if (adj) b += (size_t)nf * sizeof(double);
+    return b;
+}
+
 static inline size_t mqc_sparse_smem_bytes(int K, int cap, bool adj) {
     size_t b = (size_t)(adj ? 2 : 1) * cap * sizeof(double2);
     b += 2 * 128 * sizeof(u64);

@@ -260,3 +260,153 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
     S.phys_final = phys;
     return S;
 }
+
+// ---------------------------------------------------------------------------------------------
+// compressed-sector tile plan (see MqcSpPass in mqc_common.h); needs every factor to conserve
+// (N_alpha, N_beta).  Qubit q (alpha: even, beta: odd) <-> logical bit n_bits - 1 - q.
+// ---------------------------------------------------------------------------------------------
+struct MqcSparsePlan {
+    std::vector<MqcSpPass> pass;
+    std::vector<u64> dep, depp;          // physical offset of a pattern in the load / the other layout
+    std::vector<uint32_t> lists;
+    std::vector<uint32_t> hdr;           // pairs {offset, count}
+    bool ok = false;
+};
+
+static inline MqcSparsePlan mqc_build_sparse_plan(const MqcSchedule& S, int na, int nb) {
+    MqcSparsePlan PL;
+    const int n = S.n_bits, K = S.k;
+    const int n_orb_a = (n + 1) / 2, n_orb_b = n / 2;
+    for (size_t p = 0; p < S.passes.size(); ++p) {
+        const MqcPass& P = S.passes[p];
+        const std::vector<int>& ph = S.pass_phys_before[p];
+        MqcSpPass SP{};
+        for (int q = 0; q < n; ++q) {
+            const u64 bit = 1ull << ph[n - 1 - q];
+            if (q & 1) SP.bmask |= bit; else SP.amask |= bit;
+        }
+        uint32_t loc[2] = {0, 0};                       // local masks of alpha / beta active bits
+        for (int j = 0; j < K; ++j) {
+            if ((SP.amask >> P.pos[j]) & 1ull) loc[0] |= 1u << j;
+            if ((SP.bmask >> P.pos[j]) & 1ull) loc[1] |= 1u << j;
+        }
+        SP.a_act = __builtin_popcount(loc[0]); SP.b_act = __builtin_popcount(loc[1]);
+        SP.na = na; SP.nb = nb;
+        if (SP.a_act >= MQC_SP_KMAX || SP.b_act >= MQC_SP_KMAX) return PL;
+        // other-layout position of local bit j: new local bit j' takes old local bit perm[j']
+        int newpos[16];
+        for (int j = 0; j < K; ++j) newpos[j] = P.pos[j];
+        if (P.has_perm) for (int jp = 0; jp < K; ++jp) newpos[P.perm[jp]] = P.pos[jp];
+        std::vector<uint32_t> pats[2][MQC_SP_KMAX];     // [spin][k] -> local masks, ascending
+        std::vector<int> rank_of[2];
+        for (int sp = 0; sp < 2; ++sp) {
+            const int act = sp ? SP.b_act : SP.a_act;
+            rank_of[sp].assign((size_t)1 << K, -1);
+            // enumerate subsets of loc[sp] in ascending order of the mask value
+            uint32_t sub = 0;
+            while (true) {
+                const int k = __builtin_popcount(sub);
+                rank_of[sp][sub] = (int)pats[sp][k].size();
+                pats[sp][k].push_back(sub);
+                if (sub == loc[sp]) break;
+                sub = (sub - loc[sp]) & loc[sp];
+            }
+            for (int k = 0; k <= act; ++k) {
+                if (pats[sp][k].size() >= 4096) return PL;
+                (sp ? SP.patoffB : SP.patoffA)[k] = (uint32_t)PL.dep.size();
+                (sp ? SP.cntB : SP.cntA)[k] = (uint16_t)pats[sp][k].size();
+                for (uint32_t t : pats[sp][k]) {
+                    u64 d = 0, dp = 0;
+                    for (int j = 0; j < K; ++j) if ((t >> j) & 1u) { d |= 1ull << P.pos[j]; dp |= 1ull << newpos[j]; }
+                    PL.dep.push_back(d); PL.depp.push_back(dp);
+                }
+            }
+        }
+        // feasible classes and the slot capacity
+        double best = 1;
+        {
+            int ca = 0, cb = 0;
+            for (int k = 0; k <= SP.a_act; ++k) if (k <= na && na - k <= n_orb_a - SP.a_act) ca = std::max(ca, (int)SP.cntA[k]);
+            for (int k = 0; k <= SP.b_act; ++k) if (k <= nb && nb - k <= n_orb_b - SP.b_act) cb = std::max(cb, (int)SP.cntB[k]);
+            best = (double)std::max(1, ca) * std::max(1, cb);
+        }
+        SP.cap = (int)best;
+        const int nf = P.f1 - P.f0;
+        for (int sp = 0; sp < 2; ++sp) {
+            (sp ? SP.hdrB_off : SP.hdrA_off) = (uint32_t)(PL.hdr.size() / 2);
+            const int act = sp ? SP.b_act : SP.a_act;
+            for (int f = 0; f < nf; ++f) {
+                const MqcTileFactor& F = S.tf[P.f0 + f];
+                const uint32_t fm = F.m & loc[sp], fv = F.v & loc[sp], fz = F.z & loc[sp];
+                for (int k = 0; k < MQC_SP_KMAX; ++k) {
+                    const uint32_t off = (uint32_t)PL.lists.size();
+                    uint32_t cnt = 0;
+                    if (k <= act) for (uint32_t t : pats[sp][k]) {
+                        if ((t & fm) != fv) continue;
+                        const uint32_t lo = (uint32_t)rank_of[sp][t], hi = (uint32_t)rank_of[sp][t ^ fm];
+                        const uint32_t par = (uint32_t)__builtin_popcount(t & fz) & 1u;
+                        PL.lists.push_back(lo | (hi << 12) | (par << 24));
+                        ++cnt;
+                    }
+                    PL.hdr.push_back(off); PL.hdr.push_back(cnt);
+                }
+            }
+        }
+        PL.pass.push_back(SP);
+    }
+    if (PL.lists.empty()) PL.lists.push_back(0);
+    if (PL.hdr.empty()) { PL.hdr.push_back(0); PL.hdr.push_back(0); }
+    if (PL.dep.empty()) { PL.dep.push_back(0); PL.depp.push_back(0); }
+    PL.ok = true;
+    return PL;
+}
+
+// Host execution of the plan on a dense 2^n_bits vector in physical order (tests: the kernel
+// k_tile_sp2 walks exactly these tables).  cs[slot] = (cos, sin).
+static inline void mqc_sparse_plan_forward_host(const MqcSchedule& S, const MqcSparsePlan& PL, std::vector<double>& re,
+                                                std::vector<double>& im, const std::vector<double>& cosv,
+                                                const std::vector<double>& sinv) {
+    const int n = S.n_bits, K = S.k;
+    for (size_t p = 0; p < S.passes.size(); ++p) {
+        const MqcPass& P = S.passes[p];
+        const MqcSpPass& SP = PL.pass[p];
+        const int nf = P.f1 - P.f0;
+        const u64 n_tiles = 1ull << (n - K);
+        std::vector<double> tr, ti;
+        for (u64 tile = 0; tile < n_tiles; ++tile) {
+            const u64 base = mqc_deposit_complement(tile, P.act_mask, n);
+            const int ka = SP.na - __builtin_popcountll(base & SP.amask), kb = SP.nb - __builtin_popcountll(base & SP.bmask);
+            if (ka < 0 || kb < 0 || ka > SP.a_act || kb > SP.b_act) continue;
+            const int nAl = SP.cntA[ka], nBl = SP.cntB[kb], cnt = nAl * nBl;
+            tr.assign(cnt, 0.0); ti.assign(cnt, 0.0);
+            for (int e = 0; e < cnt; ++e) {
+                const u64 g = base | PL.dep[SP.patoffA[ka] + e / nBl] | PL.dep[SP.patoffB[kb] + e % nBl];
+                tr[e] = re[g]; ti[e] = im[g];
+            }
+            for (int f = 0; f < nf; ++f) {
+                const MqcTileFactor& F = S.tf[P.f0 + f];
+                const uint32_t* hA = &PL.hdr[2 * (SP.hdrA_off + (size_t)f * MQC_SP_KMAX + ka)];
+                const uint32_t* hB = &PL.hdr[2 * (SP.hdrB_off + (size_t)f * MQC_SP_KMAX + kb)];
+                const unsigned sg = ((unsigned)__builtin_popcountll(base & F.z_out) + F.sign0) & 1u;
+                const double c = cosv[F.slot], sn = sinv[F.slot];
+                for (uint32_t ua = 0; ua < hA[1]; ++ua) for (uint32_t ub = 0; ub < hB[1]; ++ub) {
+                    const uint32_t la = PL.lists[hA[0] + ua], lb = PL.lists[hB[0] + ub];
+                    const int e0 = (int)(la & 0xfffu) * nBl + (int)(lb & 0xfffu), e1 = (int)((la >> 12) & 0xfffu) * nBl + (int)((lb >> 12) & 0xfffu);
+                    const double ssn = ((((la ^ lb) >> 24) ^ sg) & 1u) ? -sn : sn;
+                    const double ax = tr[e0], ay = ti[e0], bx = tr[e1], by = ti[e1];
+                    tr[e0] = c * ax - ssn * bx; ti[e0] = c * ay - ssn * by;
+                    tr[e1] = c * bx + ssn * ax; ti[e1] = c * by + ssn * ay;
+                }
+            }
+            if (P.has_perm) for (int e = 0; e < cnt; ++e) {
+                const u64 g = base | PL.dep[SP.patoffA[ka] + e / nBl] | PL.dep[SP.patoffB[kb] + e % nBl];
+                re[g] = 0.0; im[g] = 0.0;
+            }
+            const std::vector<u64>& ds = P.has_perm ? PL.depp : PL.dep;
+            for (int e = 0; e < cnt; ++e) {
+                const u64 g = base | ds[SP.patoffA[ka] + e / nBl] | ds[SP.patoffB[kb] + e % nBl];
+                re[g] = tr[e]; im[g] = ti[e];
+            }
+        }
+    }
+}

@@ -47,6 +47,10 @@ CASES = [
     (7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 9}),
     (8, 8, "blocked", {}),                                       # 16 qubits, default 12/11-bit tiles
     (8, 8, "blocked", {"grad_tile_bits": 12, "tile_threads": 512}),
+    (6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "sp2": 0}),           # first-generation sector tiles
+    (8, 8, "blocked", {"sp2": 0, "sigma": 0}),                                     # ... and X-group H kernel
+    (7, 6, "lex", {"tile_bits": 10, "grad_tile_bits": 9, "sp2_warps": 2}),
+    (6, 2, "blocked", {"tile_bits": 8, "grad_tile_bits": 8}),                     # dilute sector
 ]
 
 

@@ -53,6 +53,7 @@ CASES = [
     (7, 6, 8, "blocked", {"tile_bits": 9, "grad_tile_bits": 8}),
     (8, 8, 8, "blocked", {}),                                                           # 16 qubits, 13 local bits
     (8, 8, 2, "blocked", {"sparse_tiles": 0}),
+    (7, 6, 4, "blocked", {"tile_bits": 9, "grad_tile_bits": 8, "sp2": 0, "sigma": 0}),  # first-generation kernels
 ]
 
 

@@ -97,3 +97,28 @@ def test_sharded_schedule_global_pass_share():
     S = h.schedule(0)
     n_glob = sum(1 for p in S["passes"] if p["act_mask"] >> 21)
     assert len(S["passes"]) <= 60 and n_glob <= len(S["passes"]) // 2
+
+
+@pytest.mark.parametrize("n,ne,kb,lb,order", [
+    (4, 4, 12, 3, "blocked"),
+    (4, 2, 6, 2, "lex"),
+    (5, 4, 7, 3, "lex"),
+    (6, 6, 8, 2, "blocked"),
+    (6, 4, 9, 4, "blocked"),
+    (7, 6, 10, 3, "blocked"),
+    (8, 8, 12, 3, "blocked"),
+])
+def test_sparse_plan_reproduces_oracle_state(n, ne, kb, lb, order):
+    """Compressed-sector tile plan (product-set slots, per-factor pair lists, re-layout offsets)
+    executed on the host by the library = oracle state."""
+    F = uccsd_factors(n, ne, order)
+    h = _lib.Handle(2 * n)
+    h.set_option("tile_bits", kb)
+    h.set_option("grad_tile_bits", min(kb, 12))
+    h.set_option("low_bits", lb)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    th = np.random.default_rng(5).normal(0, 0.2, F.n_theta)
+    ref = UCCSDOracle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, EMPTY).state(th)
+    for which in (0, 1):
+        psi = h.sparse_plan_host_state(th, which)
+        assert abs(psi - ref).max() < 1e-13
