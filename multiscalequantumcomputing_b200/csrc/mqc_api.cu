@@ -138,7 +138,7 @@ struct mqc_solver {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t user_ev[2] = {nullptr, nullptr};
     bool gpu_ready = false;
-    int n_sm = 148;
+    int n_sm = 148, sp2_carveout_set = -1;
 
     // options
     int tile_bits = 12, low_bits = 3, grad_tile_bits = 12, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
@@ -150,8 +150,11 @@ struct mqc_solver {
     MqcSparsePlan plan[2];          // compressed-sector tile plan per schedule (host copy of the pass records)
     DevBuf<u64> pl_dep[2], pl_depp[2];
     DevBuf<uint32_t> pl_lists[2];
-    DevBuf<uint2> pl_hdr[2];
-    int sp2 = 1, sp2_warps = 4;
+    DevBuf<uint16_t> pl_pat[2];
+    DevBuf<uint4> pl_hdr[2];
+    MqcTileLists tlist[2];          // host copy of the offsets; tiles live in pl_tiles
+    DevBuf<u64> pl_tiles[2];
+    int sp2 = 1, sp2_warps = 4, sp2_list = 1, sp2_smem_kb = 220;
     double* scalars_p() const { return mail.p; }
     double* grad_p() const { return mail.p + MQC_MAIL_GRAD; }
     unsigned long long* flags_p() const { return reinterpret_cast<unsigned long long*>(mail.p + MQC_MAIL_FLAGS); }
@@ -258,8 +261,10 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_tile_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_tile_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_tile_sp2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_tile_sp2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_tile_sp2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_tile_sp2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_tile_sp2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_tile_sp2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_sigma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000));
     CK(cudaFuncSetAttribute(k_sigma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000));
     s->gpu_ready = true;
@@ -577,16 +582,37 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
     if (sparse && s->sp2 && s->plan[which].ok) {
         const MqcSpPass& SPP = s->plan[which].pass[pass];
         int warps = s->sp2_warps;
-        size_t smem = mqc_sp2_smem_bytes(SPP.cap, nf, adj, warps);
-        while (warps > 1 && smem > 200000) { warps >>= 1; smem = mqc_sp2_smem_bytes(SPP.cap, nf, adj, warps); }
+        size_t smem = mqc_sp2_smem_bytes(SPP, nf, adj, warps);
+        while (warps > 1 && smem > 200000) { warps >>= 1; smem = mqc_sp2_smem_bytes(SPP, nf, adj, warps); }
         if (smem <= 200000) {
-            int per_sm = (int)std::min<size_t>(16, (220 * 1024) / (smem + 1024));
+            int per_sm = (int)std::min<size_t>(16, ((size_t)s->sp2_smem_kb * 1024) / (smem + 1024));
             per_sm = std::max(1, std::min(per_sm, 64 / warps));
-            const u64 want = (TM.n_tiles + warps - 1) / warps;
+            const bool list = s->tlist[which].ok && s->sp2_list;
+            MqcSpTables TB{s->pl_dep[which].p, s->pl_depp[which].p, s->pl_lists[which].p, s->pl_pat[which].p, s->pl_hdr[which].p, nullptr, 0};
+            u64 n_work = TM.n_tiles;
+            if (list) {
+                TB.tiles = s->pl_tiles[which].p + s->tlist[which].off[pass];
+                TB.n_list = s->tlist[which].off[pass + 1] - s->tlist[which].off[pass];
+                n_work = TB.n_list;
+            }
+            if (n_work == 0) return;
+            if (s->sp2_carveout_set != s->sp2_smem_kb) {           // leave the rest of the 256 KB to L1 (tables, lists, headers)
+                const int pct = std::min(100, (s->sp2_smem_kb + 8) * 100 / 228);
+                CK(cudaFuncSetAttribute(k_tile_sp2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                CK(cudaFuncSetAttribute(k_tile_sp2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                CK(cudaFuncSetAttribute(k_tile_sp2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                CK(cudaFuncSetAttribute(k_tile_sp2<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                s->sp2_carveout_set = s->sp2_smem_kb;
+            }
+            const u64 want = (n_work + warps - 1) / warps;
             const unsigned g2 = (unsigned)std::min<u64>(want, (u64)s->n_sm * per_sm);
-            MqcSpTables TB{s->pl_dep[which].p, s->pl_depp[which].p, s->pl_lists[which].p, s->pl_hdr[which].p};
-            if (adj) k_tile_sp2<true><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, s->grad_p(), reverse, TM.n_tiles);
-            else k_tile_sp2<false><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, nullptr, reverse, TM.n_tiles);
+            if (list) {
+                if (adj) k_tile_sp2<true, true><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, s->grad_p(), reverse, TM.n_tiles);
+                else k_tile_sp2<false, true><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, nullptr, reverse, TM.n_tiles);
+            } else {
+                if (adj) k_tile_sp2<true, false><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, s->grad_p(), reverse, TM.n_tiles);
+                else k_tile_sp2<false, false><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, nullptr, reverse, TM.n_tiles);
+            }
             s->counters[0]++;
             return;
         }
@@ -954,10 +980,12 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sparse_threads") s->sparse_threads = (int)value;
     else if (k == "sigma") s->use_sigma = (int)value;
     else if (k == "sp2") s->sp2 = (int)value;
+    else if (k == "sp2_list") s->sp2_list = (int)value;
+    else if (k == "sp2_smem_kb") { if (value < 16 || value > 220) throw MqcError("sp2_smem_kb must be in [16,220]"); s->sp2_smem_kb = (int)value; }
     else if (k == "sp2_warps") { if (value < 1 || value > 8) throw MqcError("sp2_warps must be in [1,8]"); s->sp2_warps = (int)value; }
     else throw MqcError("unknown option: " + k);
-    if (s->tile_bits < 5 || s->tile_bits > MQC_MAX_TILE_BITS || s->grad_tile_bits < 5 || s->grad_tile_bits > MQC_MAX_TILE_BITS - 1)
-        throw MqcError("tile_bits must be in [5,13], grad_tile_bits in [5,12]");
+    if (s->tile_bits < 5 || s->tile_bits > 14 || s->grad_tile_bits < 5 || s->grad_tile_bits > 14)
+        throw MqcError("tile_bits and grad_tile_bits must be in [5,14] (dense tiles: <= 13 / 12)");
     if (s->low_bits < 0 || s->low_bits > 6) throw MqcError("low_bits must be in [0,6]");
     if (s->tile_threads < 32 || s->tile_threads > 512 || (s->tile_threads & (s->tile_threads - 1)))
         throw MqcError("tile_threads must be a power of two in [32,512]");
@@ -1065,9 +1093,17 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
                 s->pl_dep[w].upload(s->plan[w].dep, s->stream);
                 s->pl_depp[w].upload(s->plan[w].depp, s->stream);
                 s->pl_lists[w].upload(s->plan[w].lists, s->stream);
-                std::vector<uint2> hd(s->plan[w].hdr.size() / 2);
-                for (size_t i = 0; i < hd.size(); ++i) hd[i] = make_uint2(s->plan[w].hdr[2 * i], s->plan[w].hdr[2 * i + 1]);
+                s->pl_pat[w].upload(s->plan[w].pat, s->stream);
+                std::vector<uint4> hd(s->plan[w].hdr.size() / 4);
+                for (size_t i = 0; i < hd.size(); ++i)
+                    hd[i] = make_uint4(s->plan[w].hdr[4 * i], s->plan[w].hdr[4 * i + 1], s->plan[w].hdr[4 * i + 2], s->plan[w].hdr[4 * i + 3]);
                 s->pl_hdr[w].upload(hd, s->stream);
+                s->tlist[w] = mqc_build_tile_lists(s->sched[w], s->plan[w], s->rank);
+                if (s->tlist[w].ok) {
+                    s->pl_tiles[w].upload(s->tlist[w].tiles, s->stream);
+                    CK(cudaStreamSynchronize(s->stream));
+                    s->tlist[w].tiles.clear(); s->tlist[w].tiles.shrink_to_fit();
+                }
             }
             s->tf[w].upload(s->sched[w].tf, s->stream);
             std::vector<int> ph = s->lay[w].phys;

@@ -72,6 +72,7 @@ struct MqcSpPass {
     int32_t a_act, b_act;
     u64 amask, bmask;                                      // physical masks of alpha / beta qubits (load layout)
     int32_t na, nb, cap;                                   // sector, max slots of any tile of this pass
+    int32_t lcap;                                          // pair-list entries a 32-factor chunk can need
 };
 // pair list entry: lo pattern rank (12) | hi pattern rank << 12 | in-tile parity << 24
 

@@ -355,11 +355,30 @@ struct MqcSpTables {
     const u64* dep;            // pattern -> physical offset, load layout
     const u64* depp;           // pattern -> physical offset, other layout of a re-layout pass
     const uint32_t* lists;     // pair lists
-    const uint2* hdr;          // (factor, k) -> {first entry, count}
+    const uint16_t* pat;       // pattern -> tile-local mask
+    const uint4* hdr;          // (factor, k) -> {first entry, count, float bits of 1 / count, parity mask | identity << 16}
+    const u64* tiles;          // optional: non-empty tiles of this rank, heaviest first:
+    u64 n_list;                //   base (48 bits) | ka << 48 | kb << 56
 };
-#define MQC_SP2_HDR_BYTES (32 * (16 + 8 + 8 + 4 + 4))
+#define MQC_SP2_HDR_BYTES (32 * (16 + 16 + 16 + 4 + 4))
+static inline __host__ __device__ size_t mqc_sp2_dep_bytes(const MqcSpPass& SP) {     // [2 layouts][maxA + maxB] offsets per warp
+    int ma = 1, mb = 1;
+    for (int k = 0; k <= SP.a_act; ++k) ma = SP.cntA[k] > ma ? SP.cntA[k] : ma;
+    for (int k = 0; k <= SP.b_act; ++k) mb = SP.cntB[k] > mb ? SP.cntB[k] : mb;
+    return (size_t)2 * (ma + mb) * sizeof(u64) + (((size_t)(ma + mb) * sizeof(uint16_t) + 15) & ~(size_t)15)
+           + (((size_t)SP.lcap * sizeof(uint16_t) + 15) & ~(size_t)15);
+}
+static inline __host__ __device__ int mqc_sp2_max_patterns(const MqcSpPass& SP) {
+    int ma = 1, mb = 1;
+    for (int k = 0; k <= SP.a_act; ++k) ma = SP.cntA[k] > ma ? SP.cntA[k] : ma;
+    for (int k = 0; k <= SP.b_act; ++k) mb = SP.cntB[k] > mb ? SP.cntB[k] : mb;
+    return ma + mb;
+}
 
-template <bool ADJ>
+// LIST: tiles come from a host-built list (only the non-empty ones, sorted by size and dealt
+// round-robin over the CTAs so that every SM gets the same mix of large and small tiles);
+// otherwise every tile counter is decoded and tested on the fly (huge sharded registers).
+template <bool ADJ, bool LIST>
 __global__ void __launch_bounds__(256)
 k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass P, const __grid_constant__ MqcSpPass SP,
            const MqcSpTables TB, const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
@@ -368,39 +387,62 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nf = P.f1 - P.f0;
     const int cap = SP.cap;
-    const size_t per_warp = (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2) + MQC_SP2_HDR_BYTES;
+    const size_t gw_bytes = ADJ ? (((size_t)nf * sizeof(double) + 15) & ~(size_t)15) : 0;
+    const size_t dep_bytes = mqc_sp2_dep_bytes(SP);
+    const size_t per_warp = (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2) + MQC_SP2_HDR_BYTES + dep_bytes + gw_bytes;
     unsigned char* wb = smem_raw + (size_t)warp * per_warp;
     double2* sp = reinterpret_cast<double2*>(wb);
     double2* sl = sp + (ADJ ? cap : 0);
     unsigned char* q = wb + (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2);
+    const int maxpat = mqc_sp2_max_patterns(SP);
+    u64* sdl = reinterpret_cast<u64*>(q);                                 // offsets of this tile's patterns: load layout,
+    u64* sds = sdl + maxpat;                                              // store layout  ([alpha patterns][beta patterns])
+    uint16_t* spat = reinterpret_cast<uint16_t*>(sds + maxpat);           // the patterns themselves
+    uint16_t* slist = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(spat) + (((size_t)maxpat * sizeof(uint16_t) + 15) & ~(size_t)15));
+    q += dep_bytes;
     double2* hcs = reinterpret_cast<double2*>(q);   q += 32 * sizeof(double2);
-    uint2* hA = reinterpret_cast<uint2*>(q);        q += 32 * sizeof(uint2);
-    uint2* hB = reinterpret_cast<uint2*>(q);        q += 32 * sizeof(uint2);
+    uint4* hA = reinterpret_cast<uint4*>(q);        q += 32 * sizeof(uint4);
+    uint4* hB = reinterpret_cast<uint4*>(q);        q += 32 * sizeof(uint4);
     uint32_t* hsg = reinterpret_cast<uint32_t*>(q); q += 32 * sizeof(uint32_t);
-    int* hfi = reinterpret_cast<int*>(q);
-    double* gblk = reinterpret_cast<double*>(smem_raw + (size_t)W * per_warp);
+    int* hfi = reinterpret_cast<int*>(q);           q += 32 * sizeof(int);
+    double* gw = reinterpret_cast<double*>(q);      // [nf] gradient partials of this warp (ADJ)
     if (ADJ) {
-        for (int i = threadIdx.x; i < nf; i += blockDim.x) gblk[i] = 0.0;
-        __syncthreads();
+        for (int i = lane; i < nf; i += 32) gw[i] = 0.0;
+        __syncwarp();
     }
     const bool alt_load = reverse && P.has_perm, alt_store = (!reverse) && P.has_perm;
     const u64* __restrict__ dl = alt_load ? TB.depp : TB.dep;
     const u64* __restrict__ ds = alt_store ? TB.depp : TB.dep;
+    const u64 n_work = LIST ? TB.n_list : n_tiles;
 
-    for (u64 tile = (u64)blockIdx.x * W + warp; tile < n_tiles; tile += (u64)gridDim.x * W) {
-        const u64 base = mqc_deposit_complement(tile | PR.tau_hi, P.act_mask, PR.n_local) | PR.fixed_bits;
-        const int ka = SP.na - __popcll(base & SP.amask);
-        const int kb = SP.nb - __popcll(base & SP.bmask);
-        if (ka < 0 || kb < 0 || ka > SP.a_act || kb > SP.b_act) continue;       // tile holds only zeros
+    for (u64 it = (u64)blockIdx.x + (u64)gridDim.x * warp; it < n_work; it += (u64)gridDim.x * W) {
+        u64 base;
+        int ka, kb;
+        if (LIST) {
+            const u64 pk = __ldg(TB.tiles + it);
+            base = pk & 0xffffffffffffull; ka = (int)((pk >> 48) & 0xffu); kb = (int)(pk >> 56);
+        } else {
+            base = mqc_deposit_complement(it | PR.tau_hi, P.act_mask, PR.n_local) | PR.fixed_bits;
+            ka = SP.na - __popcll(base & SP.amask);
+            kb = SP.nb - __popcll(base & SP.bmask);
+            if (ka < 0 || kb < 0 || ka > SP.a_act || kb > SP.b_act) continue;   // tile holds only zeros
+        }
         const int nAl = SP.cntA[ka], nBl = SP.cntB[kb];
         const int cnt = nAl * nBl;
         const uint32_t offA = SP.patoffA[ka], offB = SP.patoffB[kb];
         const float rcpB = __frcp_rn((float)nBl);
-        __syncwarp();                                             // previous tile's stores have read sp / sl
+        __syncwarp();                                             // previous tile's stores have read sp / sl / sd*
+        for (int i = lane; i < nAl + nBl; i += 32) {
+            const uint32_t src = i < nAl ? offA + i : offB + (i - nAl);
+            sdl[i] = base | __ldg(dl + src);
+            sds[i] = base | __ldg(ds + src);
+            spat[i] = __ldg(TB.pat + src);
+        }
+        __syncwarp();
         // ---- load ---------------------------------------------------------------------------
         for (int e = lane; e < cnt; e += 32) {
             const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
-            const u64 g = base | __ldg(dl + offA + ja) | __ldg(dl + offB + jb);
+            const u64 g = sdl[ja] | sdl[nAl + jb];
             cp_async16(sp + e, peer_psi(PR, g));
             if (ADJ) cp_async16(sl + e, peer_lam(PR, g));
         }
@@ -408,34 +450,63 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
         for (int c0 = 0; c0 < nf; c0 += 32) {
             const int nc = min(32, nf - c0);
             __syncwarp();                                         // previous chunk's headers are consumed
+            bool live = false;
+            uint4 a4 = make_uint4(0, 0, 0, 0), b4 = make_uint4(0, 0, 0, 0);
+            int nstage = 0;
             if (lane < nc) {
                 const int f = reverse ? (nf - 1 - (c0 + lane)) : (c0 + lane);
-                const MqcTileFactor* Fp = tf + P.f0 + f;
-                const double2 v = cs[Fp->slot];
-                hcs[lane] = make_double2(v.x, reverse ? -v.y : v.y);
-                hA[lane] = __ldg(TB.hdr + SP.hdrA_off + (size_t)f * MQC_SP_KMAX + ka);
-                hB[lane] = __ldg(TB.hdr + SP.hdrB_off + (size_t)f * MQC_SP_KMAX + kb);
-                hsg[lane] = ((uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
-                hfi[lane] = f;
+                a4 = __ldg(TB.hdr + SP.hdrA_off + (size_t)f * MQC_SP_KMAX + ka);
+                b4 = __ldg(TB.hdr + SP.hdrB_off + (size_t)f * MQC_SP_KMAX + kb);
+                live = (a4.y != 0u) && (b4.y != 0u);
+                if (live) {
+                    const MqcTileFactor* Fp = tf + P.f0 + f;
+                    const double2 v = cs[Fp->slot];
+                    hcs[lane] = make_double2(v.x, reverse ? -v.y : v.y);
+                    hsg[lane] = ((uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
+                    hfi[lane] = f;
+                    nstage = (int)(((a4.w >> 16) & 1u) ? 0u : a4.y) + (int)(((b4.w >> 16) & 1u) ? 0u : b4.y);
+                }
             }
+            // the short pair lists of the acting sides go to shared memory (one batch of loads per
+            // chunk instead of dependent global loads inside the pair loop)
+            int soff = nstage;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, soff, o); if (lane >= o) soff += t; }
+            soff -= nstage;
+            if (live) {
+                int w = soff;
+                if (!((a4.w >> 16) & 1u)) {
+                    for (uint32_t j = 0; j < a4.y; ++j) { const uint32_t en = __ldg(TB.lists + a4.x + j); slist[w + j] = (uint16_t)((en & 0x7fu) | (((en >> 12) & 0x7fu) << 7) | (((en >> 24) & 1u) << 14)); }
+                    a4.x = (uint32_t)w; w += (int)a4.y;
+                }
+                if (!((b4.w >> 16) & 1u)) {
+                    for (uint32_t j = 0; j < b4.y; ++j) { const uint32_t en = __ldg(TB.lists + b4.x + j); slist[w + j] = (uint16_t)((en & 0x7fu) | (((en >> 12) & 0x7fu) << 7) | (((en >> 24) & 1u) << 14)); }
+                    b4.x = (uint32_t)w;
+                }
+                hA[lane] = a4; hB[lane] = b4;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, live);     // factors that couple anything in this tile
             if (c0 == 0) cp_async_wait_all();
             __syncwarp();
-            for (int fc = 0; fc < nc; ++fc) {
-                const uint2 A = hA[fc], B = hB[fc];
+            while (todo) {
+                const int fc = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint4 A = hA[fc], B = hB[fc];
                 const int nLB = (int)B.y;
                 const int npairs = (int)A.y * nLB;
-                if (npairs == 0) continue;                        // uniform over the warp
                 const double2 csv = hcs[fc];
                 const double c = csv.x, sn = csv.y;
                 const uint32_t sg = hsg[fc];
-                const float rcp = __frcp_rn((float)nLB);
+                const float rcp = __uint_as_float(B.z);
+                const bool idA = (A.w >> 16) & 1u, idB = (B.w >> 16) & 1u;
                 double gacc = 0.0;
                 for (int u = lane; u < npairs; u += 32) {
                     const int ua = (int)(((float)u + 0.5f) * rcp), ub = u - ua * nLB;
-                    const uint32_t la = __ldg(TB.lists + A.x + ua), lb = __ldg(TB.lists + B.x + ub);
-                    const int e0 = (int)(la & 0xfffu) * nBl + (int)(lb & 0xfffu);
-                    const int e1 = (int)((la >> 12) & 0xfffu) * nBl + (int)((lb >> 12) & 0xfffu);
-                    const bool neg = ((((la ^ lb) >> 24) ^ sg) & 1u) != 0u;
+                    const uint32_t la = idA ? ((uint32_t)ua * 129u | (((uint32_t)__popc(spat[ua] & A.w) & 1u) << 14)) : (uint32_t)slist[A.x + ua];
+                    const uint32_t lb = idB ? ((uint32_t)ub * 129u | (((uint32_t)__popc(spat[nAl + ub] & B.w) & 1u) << 14)) : (uint32_t)slist[B.x + ub];
+                    const int e0 = (int)(la & 0x7fu) * nBl + (int)(lb & 0x7fu);
+                    const int e1 = (int)((la >> 7) & 0x7fu) * nBl + (int)((lb >> 7) & 0x7fu);
+                    const bool neg = ((((la ^ lb) >> 14) ^ sg) & 1u) != 0u;
                     const double ssn = neg ? -sn : sn;
                     const double2 a = sp[e0], b = sp[e1];
                     if (ADJ) {
@@ -449,8 +520,10 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
                     sp[e1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
                 }
                 if (ADJ) {
-                    gacc = warp_sum(gacc);
-                    if (lane == 0 && gacc != 0.0) atomicAdd(gblk + hfi[fc], gacc);
+                    // lanes >= npairs hold zero: only the butterfly stages below npairs matter
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) if (npairs > o) gacc += __shfl_xor_sync(0xffffffffu, gacc, o);
+                    if (lane == 0) gw[hfi[fc]] += gacc;
                 }
                 __syncwarp();
             }
@@ -462,7 +535,7 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
         if (P.has_perm) {
             for (int e = lane; e < cnt; e += 32) {
                 const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
-                const u64 g = base | __ldg(dl + offA + ja) | __ldg(dl + offB + jb);
+                const u64 g = sdl[ja] | sdl[nAl + jb];
                 *peer_psi(PR, g) = make_double2(0.0, 0.0);
                 if (ADJ) *peer_lam(PR, g) = make_double2(0.0, 0.0);
             }
@@ -470,24 +543,25 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
         }
         for (int e = lane; e < cnt; e += 32) {
             const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
-            const u64 g = base | __ldg(ds + offA + ja) | __ldg(ds + offB + jb);
+            const u64 g = sds[ja] | sds[nAl + jb];
             *peer_psi(PR, g) = sp[e];
             if (ADJ) *peer_lam(PR, g) = sl[e];
         }
     }
     if (ADJ) {
+        // CTA-level sum of the warps' partials, then one global atomic per (CTA, factor)
         __syncthreads();
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
-            const double g = gblk[i];
+            double g = 0.0;
+            for (int w = 0; w < W; ++w) g += *reinterpret_cast<double*>(smem_raw + (size_t)w * per_warp + (per_warp - gw_bytes) + (size_t)i * sizeof(double));
             if (g != 0.0) atomicAdd(grad + tf[P.f0 + i].theta, 2.0 * g);
         }
     }
 }
 
-static inline size_t mqc_sp2_smem_bytes(int cap, int nf, bool adj, int warps) {
-    size_t b = (size_t)warps * ((size_t)(adj ? 2 : 1) * cap * sizeof(double2) + MQC_SP2_HDR_BYTES);
-    if (adj) b += (size_t)nf * sizeof(double);
-    return b;
+static inline size_t mqc_sp2_smem_bytes(const MqcSpPass& SP, int nf, bool adj, int warps) {
+    const size_t gw_bytes = adj ? (((size_t)nf * sizeof(double) + 15) & ~(size_t)15) : 0;
+    return (size_t)warps * ((size_t)(adj ? 2 : 1) * SP.cap * sizeof(double2) + MQC_SP2_HDR_BYTES + mqc_sp2_dep_bytes(SP) + gw_bytes);
 }
 
 static inline size_t mqc_sparse_smem_bytes(int K, int cap, bool adj) {

@@ -21,6 +21,7 @@
 // Pure C++ (no CUDA): testable on a CPU-only box through mqc_schedule_* in the C ABI.
 #pragma once
 #include <algorithm>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -268,8 +269,9 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
 struct MqcSparsePlan {
     std::vector<MqcSpPass> pass;
     std::vector<u64> dep, depp;          // physical offset of a pattern in the load / the other layout
+    std::vector<uint16_t> pat;           // the pattern itself (tile-local mask), same indexing
     std::vector<uint32_t> lists;
-    std::vector<uint32_t> hdr;           // pairs {offset, count}
+    std::vector<uint32_t> hdr;           // quadruples {offset, count, float bits of 1 / count, 0}
     bool ok = false;
 };
 
@@ -312,13 +314,13 @@ static inline MqcSparsePlan mqc_build_sparse_plan(const MqcSchedule& S, int na, 
                 sub = (sub - loc[sp]) & loc[sp];
             }
             for (int k = 0; k <= act; ++k) {
-                if (pats[sp][k].size() >= 4096) return PL;
+                if (pats[sp][k].size() > 127) return PL;         // pair-list entries hold 7-bit pattern ranks
                 (sp ? SP.patoffB : SP.patoffA)[k] = (uint32_t)PL.dep.size();
                 (sp ? SP.cntB : SP.cntA)[k] = (uint16_t)pats[sp][k].size();
                 for (uint32_t t : pats[sp][k]) {
                     u64 d = 0, dp = 0;
                     for (int j = 0; j < K; ++j) if ((t >> j) & 1u) { d |= 1ull << P.pos[j]; dp |= 1ull << newpos[j]; }
-                    PL.dep.push_back(d); PL.depp.push_back(dp);
+                    PL.dep.push_back(d); PL.depp.push_back(dp); PL.pat.push_back((uint16_t)t);
                 }
             }
         }
@@ -332,8 +334,9 @@ static inline MqcSparsePlan mqc_build_sparse_plan(const MqcSchedule& S, int na, 
         }
         SP.cap = (int)best;
         const int nf = P.f1 - P.f0;
+        int max_act_list[2] = {0, 0};
         for (int sp = 0; sp < 2; ++sp) {
-            (sp ? SP.hdrB_off : SP.hdrA_off) = (uint32_t)(PL.hdr.size() / 2);
+            (sp ? SP.hdrB_off : SP.hdrA_off) = (uint32_t)(PL.hdr.size() / 4);
             const int act = sp ? SP.b_act : SP.a_act;
             for (int f = 0; f < nf; ++f) {
                 const MqcTileFactor& F = S.tf[P.f0 + f];
@@ -348,14 +351,23 @@ static inline MqcSparsePlan mqc_build_sparse_plan(const MqcSchedule& S, int na, 
                         PL.lists.push_back(lo | (hi << 12) | (par << 24));
                         ++cnt;
                     }
-                    PL.hdr.push_back(off); PL.hdr.push_back(cnt);
+                    const float rcp = cnt ? 1.0f / (float)cnt : 0.0f;
+                    uint32_t rb;
+                    std::memcpy(&rb, &rcp, sizeof(rb));
+                    // a factor that does not act on this spin couples every pattern with itself: the
+                    // kernel then needs no list, only the parity mask
+                    const uint32_t ident = (fm == 0) ? 1u : 0u;
+                    if (!ident) max_act_list[sp] = std::max(max_act_list[sp], (int)cnt);
+                    PL.hdr.push_back(off); PL.hdr.push_back(cnt); PL.hdr.push_back(rb); PL.hdr.push_back(fz | (ident << 16));
                 }
             }
         }
+        SP.lcap = 32 * (max_act_list[0] + max_act_list[1]) + 32;
         PL.pass.push_back(SP);
     }
+    if (PL.pat.empty()) PL.pat.push_back(0);
     if (PL.lists.empty()) PL.lists.push_back(0);
-    if (PL.hdr.empty()) { PL.hdr.push_back(0); PL.hdr.push_back(0); }
+    if (PL.hdr.empty()) PL.hdr.assign(4, 0);
     if (PL.dep.empty()) { PL.dep.push_back(0); PL.depp.push_back(0); }
     PL.ok = true;
     return PL;
@@ -385,14 +397,19 @@ static inline void mqc_sparse_plan_forward_host(const MqcSchedule& S, const MqcS
             }
             for (int f = 0; f < nf; ++f) {
                 const MqcTileFactor& F = S.tf[P.f0 + f];
-                const uint32_t* hA = &PL.hdr[2 * (SP.hdrA_off + (size_t)f * MQC_SP_KMAX + ka)];
-                const uint32_t* hB = &PL.hdr[2 * (SP.hdrB_off + (size_t)f * MQC_SP_KMAX + kb)];
+                const uint32_t* hA = &PL.hdr[4 * (SP.hdrA_off + (size_t)f * MQC_SP_KMAX + ka)];
+                const uint32_t* hB = &PL.hdr[4 * (SP.hdrB_off + (size_t)f * MQC_SP_KMAX + kb)];
                 const unsigned sg = ((unsigned)__builtin_popcountll(base & F.z_out) + F.sign0) & 1u;
                 const double c = cosv[F.slot], sn = sinv[F.slot];
+                // mirrors k_tile_sp2: identity sides come from the pattern masks, acting sides from
+                // the 7-bit packed pair lists
+                const bool idA = (hA[3] >> 16) & 1u, idB = (hB[3] >> 16) & 1u;
                 for (uint32_t ua = 0; ua < hA[1]; ++ua) for (uint32_t ub = 0; ub < hB[1]; ++ub) {
-                    const uint32_t la = PL.lists[hA[0] + ua], lb = PL.lists[hB[0] + ub];
-                    const int e0 = (int)(la & 0xfffu) * nBl + (int)(lb & 0xfffu), e1 = (int)((la >> 12) & 0xfffu) * nBl + (int)((lb >> 12) & 0xfffu);
-                    const double ssn = ((((la ^ lb) >> 24) ^ sg) & 1u) ? -sn : sn;
+                    auto pack = [](uint32_t en) { return (en & 0x7fu) | (((en >> 12) & 0x7fu) << 7) | (((en >> 24) & 1u) << 14); };
+                    const uint32_t la = idA ? (ua * 129u | (((uint32_t)__builtin_popcount(PL.pat[SP.patoffA[ka] + ua] & hA[3] & 0xffffu) & 1u) << 14)) : pack(PL.lists[hA[0] + ua]);
+                    const uint32_t lb = idB ? (ub * 129u | (((uint32_t)__builtin_popcount(PL.pat[SP.patoffB[kb] + ub] & hB[3] & 0xffffu) & 1u) << 14)) : pack(PL.lists[hB[0] + ub]);
+                    const int e0 = (int)(la & 0x7fu) * nBl + (int)(lb & 0x7fu), e1 = (int)((la >> 7) & 0x7fu) * nBl + (int)((lb >> 7) & 0x7fu);
+                    const double ssn = ((((la ^ lb) >> 14) ^ sg) & 1u) ? -sn : sn;
                     const double ax = tr[e0], ay = ti[e0], bx = tr[e1], by = ti[e1];
                     tr[e0] = c * ax - ssn * bx; ti[e0] = c * ay - ssn * by;
                     tr[e1] = c * bx + ssn * ax; ti[e1] = c * by + ssn * ay;
@@ -409,4 +426,41 @@ static inline void mqc_sparse_plan_forward_host(const MqcSchedule& S, const MqcS
             }
         }
     }
+}
+
+// Non-empty tiles of every pass for one rank, heaviest first, packed base | ka << 48 | kb << 56.
+// off[p] .. off[p + 1] delimit pass p.  Empty result (ok = false) when the lists would be too
+// large to be worth it: the kernel then decodes and tests every tile counter itself.
+struct MqcTileLists {
+    std::vector<u64> tiles;
+    std::vector<u64> off;
+    bool ok = false;
+};
+static inline MqcTileLists mqc_build_tile_lists(const MqcSchedule& S, const MqcSparsePlan& PL, int rank, u64 max_entries = (8ull << 20)) {
+    MqcTileLists TL;
+    if (!PL.ok) return TL;
+    const int n_local = S.n_bits - S.n_global;
+    u64 total = 0;
+    for (const MqcPass& P : S.passes) total += 1ull << (n_local - P.k);
+    if (total > max_entries || S.n_bits > 47) return TL;
+    TL.off.push_back(0);
+    std::vector<std::pair<int, u64>> tmp;
+    for (size_t p = 0; p < S.passes.size(); ++p) {
+        const MqcPass& P = S.passes[p];
+        const MqcSpPass& SP = PL.pass[p];
+        const MqcTileMap TM = mqc_tile_map(P, S.n_bits, S.n_global, rank);
+        tmp.clear();
+        for (u64 t = 0; t < TM.n_tiles; ++t) {
+            const u64 base = mqc_deposit_complement(t | TM.tau_hi, P.act_mask, n_local) | TM.fixed_bits;
+            const int ka = SP.na - __builtin_popcountll(base & SP.amask), kb = SP.nb - __builtin_popcountll(base & SP.bmask);
+            if (ka < 0 || kb < 0 || ka > SP.a_act || kb > SP.b_act) continue;
+            tmp.emplace_back((int)SP.cntA[ka] * (int)SP.cntB[kb], base | ((u64)ka << 48) | ((u64)kb << 56));
+        }
+        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, u64>& a, const std::pair<int, u64>& b) { return a.first > b.first; });
+        for (auto& kv : tmp) TL.tiles.push_back(kv.second);
+        TL.off.push_back((u64)TL.tiles.size());
+    }
+    if (TL.tiles.empty()) TL.tiles.push_back(0);
+    TL.ok = true;
+    return TL;
 }
