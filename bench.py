@@ -36,6 +36,7 @@ N_ELEC = 12
 BOND = 1.0
 THETA_SEED = 4321
 THETA_SIGMA = 0.05
+BLOCK_ORBS = int(os.environ.get("MQC_BLOCK_ORBS", "6"))
 
 
 def workload():
@@ -44,7 +45,7 @@ def workload():
     from multiscalequantumcomputing_b200.uccsd import uccsd_factors
     h_mo, eri_mo, e_nuc, e_rhf = mo_integrals(hydrogen_chain(N_ORB, BOND), N_ELEC)
     table = fragment_term_table(h_mo, eri_mo, 0, 0.0, 0.25)
-    factors = uccsd_factors(N_ORB, N_ELEC, "blocked")
+    factors = uccsd_factors(N_ORB, N_ELEC, "blocked", block_orbs=BLOCK_ORBS)
     theta = np.random.default_rng(THETA_SEED).normal(0.0, THETA_SIGMA, factors.n_theta)
     return table, factors, theta, number_of_x_groups(table[0])
 

@@ -141,7 +141,7 @@ struct mqc_solver {
     int n_sm = 148, sp2_carveout_set = -1;
 
     // options
-    int tile_bits = 12, low_bits = 3, grad_tile_bits = 12, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
+    int tile_bits = 14, low_bits = 3, grad_tile_bits = 14, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
 
     DevBuf<double2> psi, lam, cs, scratch_state, csec, lsec;
     DevBuf<double> theta, mail, red, rdm_acc;
@@ -1043,8 +1043,12 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         s->fac = fac;
         s->conserving = conserving;
         // schedules: 0 = energy-only, 1 = energy + gradient
+        // compressed-sector tiles keep only the sector in shared memory and take 14-bit tiles;
+        // dense tiles hold 2^K amplitudes (x2 with the adjoint): 13 / 12 bits at most
+        const bool sector_tiles = s->conserving && s->use_sector && s->sparse_tiles && s->sp2;
         for (int w = 0; w < 2; ++w) {
-            const int kb = (w == 0) ? s->tile_bits : s->grad_tile_bits;
+            int kb = (w == 0) ? s->tile_bits : s->grad_tile_bits;
+            if (!sector_tiles) kb = std::min(kb, w == 0 ? MQC_MAX_TILE_BITS : MQC_MAX_TILE_BITS - 1);
             if (s->mode == 1) {
                 s->sched[w] = mqc_build_schedule(n, kb, s->low_bits, s->fac, MQC_MAX_PASS_FACTORS, s->n_global);
             } else {
