@@ -73,8 +73,11 @@ int mqc_shard_info(mqc_solver_t* s, int32_t* rank, int32_t* n_ranks, int32_t* n_
 int mqc_shard_read(mqc_solver_t* s, const double* theta, int32_t member, double* re_im,
                    int64_t n_amplitudes, int32_t* phys_of_logical);
 
-/* Options (before mqc_set_ansatz): "tile_bits" (default 12), "low_bits" (3),
- * "grad_tile_bits" (12), "mode" (1 = fused tile sweep, 0 = one factor per pass),
+/* Options (before mqc_set_ansatz): "tile_bits" (default 14; dense tiles are clamped to 13),
+ * "low_bits" (3), "grad_tile_bits" (14; dense: 12), "mode" (1 = fused tile sweep, 0 = one
+ * factor per pass), "sp2" (1 = warp-per-tile compressed-sector sweep k_tile_sp2, 0 = first
+ * generation), "sp2_warps" (4), "sp2_list" (1 = host-built lists of the non-empty tiles),
+ * "sp2_smem_kb" (220), "sigma_stage" (1 = stage source rows of H|psi> in shared memory),
  * "sector" (1 = exploit particle-number/S_z conservation of the ansatz in H|psi>),
  * "sparse_tiles" (1 = compressed-sector tiles when the ansatz conserves N_alpha, N_beta),
  * "tile_threads" (256), "sparse_threads" (128), "sigma" (1 = link-table kernel for the sector

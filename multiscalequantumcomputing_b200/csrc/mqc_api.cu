@@ -161,7 +161,7 @@ struct mqc_solver {
 
     HamHost ham, ham_fb;            // all terms / the terms the link-table kernel leaves to k_happly_sector
     SigmaTables sig;
-    int use_sigma = 1;
+    int use_sigma = 1, sigma_stage = 1;
     bool have_ham = false, have_ansatz = false;
 
     std::vector<MqcFactor> fac;     // logical coordinates
@@ -455,6 +455,13 @@ static MqcSectorDev sector_dev(const LayoutTables& L, bool enabled) {
     return S;
 }
 
+static double binom_d(int n, int k) {
+    if (k < 0 || k > n) return 0.0;
+    double r = 1.0;
+    for (int i = 1; i <= k; ++i) r = r * (n - k + i) / i;
+    return r;
+}
+
 static u64 logical_to_qubit(u64 m, int n) {
     u64 out = 0;
     for (int q = 0; q < n; ++q) if ((m >> (n - 1 - q)) & 1ull) out |= 1ull << q;
@@ -722,7 +729,7 @@ static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, 
                 bool have = false;
                 if (SG && SG->ready) {
                     MqcSigmaDev D = SG->dev;
-                    const bool stage = (size_t)nB * sizeof(double2) <= 65536;
+                    const bool stage = s->sigma_stage && (size_t)nB * sizeof(double2) <= 65536;
                     const size_t smem = mqc_sigma_smem_bytes(D, stage);
                     dim3 grid(r1 - r0, (nB + MQC_SG_THREADS * MQC_SG_R - 1) / (MQC_SG_THREADS * MQC_SG_R));
                     if (stage) k_sigma<true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
@@ -979,6 +986,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sparse_tiles") s->sparse_tiles = (int)value;
     else if (k == "sparse_threads") s->sparse_threads = (int)value;
     else if (k == "sigma") s->use_sigma = (int)value;
+    else if (k == "sigma_stage") s->sigma_stage = (int)value;
     else if (k == "sp2") s->sp2 = (int)value;
     else if (k == "sp2_list") s->sp2_list = (int)value;
     else if (k == "sp2_smem_kb") { if (value < 16 || value > 220) throw MqcError("sp2_smem_kb must be in [16,220]"); s->sp2_smem_kb = (int)value; }
@@ -1048,7 +1056,7 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         const bool sector_tiles = s->conserving && s->use_sector && s->sparse_tiles && s->sp2;
         for (int w = 0; w < 2; ++w) {
             int kb = (w == 0) ? s->tile_bits : s->grad_tile_bits;
-            if (!sector_tiles) kb = std::min(kb, w == 0 ? MQC_MAX_TILE_BITS : MQC_MAX_TILE_BITS - 1);
+            if (!sector_tiles) kb = std::min(kb, 12);
             if (s->mode == 1) {
                 s->sched[w] = mqc_build_schedule(n, kb, s->low_bits, s->fac, MQC_MAX_PASS_FACTORS, s->n_global);
             } else {
@@ -1102,7 +1110,10 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
                 for (size_t i = 0; i < hd.size(); ++i)
                     hd[i] = make_uint4(s->plan[w].hdr[4 * i], s->plan[w].hdr[4 * i + 1], s->plan[w].hdr[4 * i + 2], s->plan[w].hdr[4 * i + 3]);
                 s->pl_hdr[w].upload(hd, s->stream);
-                s->tlist[w] = mqc_build_tile_lists(s->sched[w], s->plan[w], s->rank);
+                // size-sorted tile lists balance the SMs while the sector is cache resident; once it
+                // lives in HBM the natural tile order has the better DRAM locality (measured at 30 qubits)
+                const double sector_bytes = 16.0 * binom_d((s->n + 1) / 2, s->na) * binom_d(s->n / 2, s->nb);
+                s->tlist[w] = sector_bytes <= 64e6 ? mqc_build_tile_lists(s->sched[w], s->plan[w], s->rank) : MqcTileLists();
                 if (s->tlist[w].ok) {
                     s->pl_tiles[w].upload(s->tlist[w].tiles, s->stream);
                     CK(cudaStreamSynchronize(s->stream));

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--max-factors", type=int, default=0, help="truncate the ansatz (0 = full UCCSD)")
     ap.add_argument("--check-norm", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value")
     args = ap.parse_args()
 
     import torch
@@ -91,6 +92,9 @@ def main():
         h = _lib.ShardRank(nq, local, rank, world) if world > 1 else _lib.Handle(nq, local)
     if args.dense:
         h.set_option("sparse_tiles", 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        h.set_option(k, int(v))
     if tab is not None:
         h.set_hamiltonian(*tab)
     h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
@@ -166,7 +170,7 @@ def main():
         "forward_aggregate_GBps": hbm_fwd / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None,
         "aggregate_hbm_peak_GBps": peak * world,
         "forward_frac_of_aggregate_hbm_peak": hbm_fwd / (fwd_ms * 1e-3) / 1e9 / (peak * world) if fwd_ms > 0 else None,
-        "value": val, "norm": norm, "setup_s": setup_s,
+        "value": val, "norm": norm, "setup_s": setup_s, "options": args.opt,
     }
     if rank == 0:
         print(json.dumps(out))

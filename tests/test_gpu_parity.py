@@ -51,6 +51,7 @@ CASES = [
     (8, 8, "blocked", {"sp2": 0, "sigma": 0}),                                     # ... and X-group H kernel
     (7, 6, "lex", {"tile_bits": 10, "grad_tile_bits": 9, "sp2_warps": 2}),
     (6, 2, "blocked", {"tile_bits": 8, "grad_tile_bits": 8}),                     # dilute sector
+    (7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 10, "sp2_list": 0, "sigma_stage": 0}),   # large-register paths
 ]
 
 
