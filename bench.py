@@ -247,7 +247,7 @@ def run_ours(args):
         n_det = comb(N_ORB, N_ELEC // 2) ** 2
         sector_bytes = 16.0 * n_det
         phase /= args.steps
-        names = ("k_tile_sparse<false> (forward sweep)", "k_happly_sector (H|psi>)", "k_tile_sparse<true> (adjoint reverse sweep)")
+        names = ("k_tile_sp2<false> (forward sweep)", "k_sigma (H|psi>)", "k_tile_sp2<true> (adjoint reverse sweep)")
         sparse = tim["forward_passes"] > 0 and "sparse_tiles=0" not in args.opt and "sector=0" not in args.opt
         if not sparse:
             names = ("k_tile_sweep<false> (forward sweep)", "k_happly (H|psi>)", "k_tile_sweep<true> (adjoint reverse sweep)")
@@ -268,6 +268,45 @@ def run_ours(args):
                 "unfused_equivalent": {
                     "B_alg_bytes": S * (6 * len(factors) + 2), "note": "SURVEY.md §8d: one HBM pass per factor",
                     "effective_GBps": S * (6 * len(factors) + 2) / (ms_step * 1e-3) / 1e9}}
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            tr = json.load(open(traffic_file))
+            key = names[dom].split(" ")[0]
+            if key in tr:
+                roof["traffic"] = tr[key]["dram_bytes_per_launch"]
+                roof["traffic_source"] = tr[key]["source"]
+        # The HBM-streaming form of the sweep (dense 2^K tiles, k_tile_sweep: what an ansatz that
+        # does not conserve particle number runs, and the kernel of the sharded 33-36 qubit
+        # sweeps) measured live on the same workload: 2 S bytes per launch.
+        streaming = None
+        try:
+            hd = _lib.Handle(factors.n_qubits, local)
+            hd.set_option("sparse_tiles", 0)
+            hd.set_hamiltonian(*table)
+            hd.set_ansatz(factors.kind, factors.idx, factors.theta_index, factors.n_theta, factors.ref_index)
+            ed = hd.energy_grad_into(th_np, g_np)
+            ph = np.zeros(3)
+            nst = max(2, min(args.steps, 5))
+            for _ in range(nst):
+                ed = hd.energy_grad_resident()
+                td = hd.last_timing()
+                ph += (td["forward_ms"], td["hamiltonian_ms"], td["reverse_ms"])
+            ph /= nst
+            assert abs(ed - e_ref) < 1e-9
+            fwd_ms = ph[0] / td["forward_passes"]
+            rev_ms = ph[2] / td["reverse_passes"]
+            streaming = {"kernel": "k_tile_sweep<false> (dense-tile forward sweep)", "bound": "hbm",
+                         "achieved": 2 * S / (fwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": 2 * S / (fwd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": 2 * S,
+                         "avg_launch_ms": fwd_ms, "launches_per_step": td["forward_passes"],
+                         "adjoint": {"kernel": "k_tile_sweep<true>", "achieved": 4 * S / (rev_ms * 1e-3) / 1e9,
+                                     "frac": 4 * S / (rev_ms * 1e-3) / 1e9 / peak, "avg_launch_ms": rev_ms,
+                                     "algorithmic_bytes_per_launch": 4 * S},
+                         "evals_per_s": 1e3 / float(ph.sum()),
+                         "phase_ms": {"forward": ph[0], "hamiltonian": ph[1], "reverse": ph[2]}}
+            hd.close()
+        except Exception as exc:
+            streaming = {"unavailable": str(exc)}
         cpu = None
         try:
             v, cores, sample = cpu_sample(table, factors, theta)
@@ -283,7 +322,7 @@ def run_ours(args):
                "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(theta_pin.numel() * 8),
                        "d2h_bytes_per_step": int(grad_pin.numel() * 8 + 16), "ms_per_step": e2e_ms / args.steps},
                "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
-               "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "clocks": clocks, "roofline": roof, "roofline_streaming": streaming, "cpu_baseline": cpu,
                "energy": e_ref, "setup_s": setup_s}
         print(json.dumps(out))
     h.close()

@@ -265,8 +265,8 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_tile_sp2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_tile_sp2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_tile_sp2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_sigma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000));
-    CK(cudaFuncSetAttribute(k_sigma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000));
+    CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     s->gpu_ready = true;
 }
 
@@ -729,11 +729,11 @@ static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, 
                 bool have = false;
                 if (SG && SG->ready) {
                     MqcSigmaDev D = SG->dev;
-                    const bool stage = s->sigma_stage && (size_t)nB * sizeof(double2) <= 65536;
-                    const size_t smem = mqc_sigma_smem_bytes(D, stage);
+                    const bool stage = s->sigma_stage && (size_t)MQC_SG_LB * nB * sizeof(double2) <= 98304;
+                    const size_t smem = mqc_sigma_smem_bytes(D, stage, MQC_SG_LB);
                     dim3 grid(r1 - r0, (nB + MQC_SG_THREADS * MQC_SG_R - 1) / (MQC_SG_THREADS * MQC_SG_R));
-                    if (stage) k_sigma<true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
-                    else k_sigma<false><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
+                    if (stage) k_sigma<true, MQC_SG_LB><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
+                    else k_sigma<false, MQC_SG_LB><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
                     s->counters[0]++;
                     have = true;
                 }

@@ -41,6 +41,7 @@
 
 #define MQC_SG_INVALID 0xffffffffu
 #define MQC_SG_THREADS 256
+#define MQC_SG_LB 4            // alpha links per batch (rows staged together, one pass over the ELL table)
 
 struct MqcSigmaDev {
     unsigned n_a, n_b;             // strings
@@ -366,6 +367,20 @@ static inline MqcSigmaHost mqc_sigma_build(int n_orb, int na, int nb, const std:
                 r2[i].push_back((unsigned)rank_a[a] | ((unsigned)i4 << 16) | ((unsigned)p6 << 28) | (sgn << 31));
             }
         }
+        // links of one output row are processed MQC_SG_LB at a time against ONE beta ELL table:
+        // order them by class and pad so that no batch mixes classes
+        for (auto& r : r1) {
+            std::stable_sort(r.begin(), r.end(), [&](unsigned x, unsigned y) {
+                return S.cls_of_m2[(x >> 16) & 0xffu] < S.cls_of_m2[(y >> 16) & 0xffu]; });
+            std::vector<unsigned> padded;
+            for (size_t k = 0; k < r.size(); ++k) {
+                if (k && S.cls_of_m2[(r[k] >> 16) & 0xffu] != S.cls_of_m2[(r[k - 1] >> 16) & 0xffu])
+                    while (padded.size() % MQC_SG_LB) padded.push_back(MQC_SG_INVALID);
+                padded.push_back(r[k]);
+            }
+            while (padded.size() % MQC_SG_LB) padded.push_back(MQC_SG_INVALID);
+            r.swap(padded);
+        }
         size_t e1 = 0, e2 = 0;
         for (auto& r : r1) e1 = std::max(e1, r.size());
         for (auto& r : r2) e2 = std::max(e2, r.size());
@@ -489,7 +504,7 @@ __device__ __forceinline__ double mqc_sg_flip(double w, unsigned s) {      // s 
 // One CTA per (output alpha string, block of MQC_SG_THREADS * MQC_SG_R output beta strings).
 // STAGE: the source row of C is copied to shared memory per link (rows up to 64 KB); otherwise
 // the gathers go to L1/L2 directly.
-template <bool STAGE>
+template <bool STAGE, int LB>
 __global__ void __launch_bounds__(MQC_SG_THREADS)
 k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_constant__ MqcSigmaDev S,
         double* __restrict__ e_out) {
@@ -497,8 +512,8 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
     const unsigned nA = S.n_a, nB = S.n_b;
     const int M2 = S.n_m2 > 0 ? S.n_m2 : 1;
     double2* srow = reinterpret_cast<double2*>(sg_smem);
-    double* wl = reinterpret_cast<double*>(sg_smem + (STAGE ? (size_t)nB * sizeof(double2) : 0));
-    double* sxd = wl + 2 * M2;
+    double* wl = reinterpret_cast<double*>(sg_smem + (STAGE ? (size_t)LB * nB * sizeof(double2) : 0));
+    double* sxd = wl + (size_t)LB * 2 * M2;
     unsigned char* sg4 = reinterpret_cast<unsigned char*>(sxd + M2);
     __shared__ double red[2][MQC_SG_THREADS / 32];
 
@@ -567,36 +582,61 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
     }
 
     // ---- phase 1: alpha single links (alpha-beta doubles + the alpha single groups) ----------
-    for (int l = 0; l < S.e1a; ++l) {
-        const unsigned ln = __ldg(S.lnk_a1 + (size_t)l * nA + i);
-        if (ln == MQC_SG_INVALID) continue;                       // uniform over the CTA
-        const unsigned src = ln & 0xffffu, ia = (ln >> 16) & 0xffu, pav = (ln >> 24) & 1u, sga = (ln >> 25) & 1u;
-        const unsigned a = __ldg(S.aorb + src), ma = __ldg(S.m2_mask + ia), zb = __ldg(S.sb_a2 + ia);
-        const int c = __ldg(S.cls_of_m2 + ia);
-        const double2* __restrict__ Crow = C + (size_t)src * nB;
-        __syncthreads();                                          // previous consumers of srow / wl are done
-        for (int k = tid; k < 2 * S.n_m2; k += MQC_SG_THREADS) {
-            const int ib = k >> 1, pbv = k & 1;
-            const unsigned mb = __ldg(S.m2_mask + ib);
-            const unsigned dest = pbv ? (mb & (0u - mb)) : (mb & (mb - 1u));   // output string's bit on mb
-            const unsigned sx = (__popc(a & __ldg(S.sa_b2 + ib) & ~ma) + __popc(dest & zb)) & 1u;
-            wl[k] = mqc_sg_flip(__ldg(S.w22 + ((size_t)ia * M2 + ib) * 4 + pav * 2 + pbv), sx);
-        }
-        if (STAGE) for (unsigned j = tid; j < nB; j += MQC_SG_THREADS) srow[j] = Crow[j];
-        __syncthreads();
-        const double2* __restrict__ row = STAGE ? srow : Crow;
-        const int e0 = __ldg(S.cls_off + c), e1 = __ldg(S.cls_off + c + 1);
-        const double al = __ldg(S.ta1 + (size_t)ia * nA + src);
-        double lr[MQC_SG_R], li[MQC_SG_R];
+    // LB links per batch: their source rows are staged together and every ELL entry (column,
+    // weight index, sign) is loaded and decoded once for all of them.
+    for (int l0 = 0; l0 < S.e1a; l0 += LB) {
+        unsigned src[LB], ia[LB], pav[LB], sga[LB], zb[LB];
+        bool ok[LB];
+        bool any = false;
+        int c = -1;
 #pragma unroll
-        for (int r = 0; r < MQC_SG_R; ++r) {
-            lr[r] = 0.0; li[r] = 0.0;
-            if (jb[r] < nB) {
-                const double w = al + __ldg(S.tb1 + ((size_t)ia * 2 + pav) * nB + jb[r]);
-                const double2 v = row[jb[r]];
-                lr[r] = w * v.x; li[r] = w * v.y;
+        for (int l = 0; l < LB; ++l) {
+            const unsigned ln = __ldg(S.lnk_a1 + (size_t)(l0 + l) * nA + i);
+            ok[l] = ln != MQC_SG_INVALID;
+            src[l] = ok[l] ? (ln & 0xffffu) : i;
+            ia[l] = ok[l] ? ((ln >> 16) & 0xffu) : 0u;
+            pav[l] = (ln >> 24) & 1u; sga[l] = (ln >> 25) & 1u;
+            zb[l] = __ldg(S.sb_a2 + ia[l]);
+            if (ok[l]) { any = true; c = __ldg(S.cls_of_m2 + ia[l]); }
+        }
+        if (!any) continue;                                       // uniform over the CTA
+        __syncthreads();                                          // previous consumers of srow / wl are done
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            const unsigned a = __ldg(S.aorb + src[l]), ma = __ldg(S.m2_mask + ia[l]);
+            for (int k = tid; k < 2 * S.n_m2; k += MQC_SG_THREADS) {
+                const int ib = k >> 1, pbv = k & 1;
+                const unsigned mb = __ldg(S.m2_mask + ib);
+                const unsigned dest = pbv ? (mb & (0u - mb)) : (mb & (mb - 1u));   // output string's bit on mb
+                const unsigned sx = (__popc(a & __ldg(S.sa_b2 + ib) & ~ma) + __popc(dest & zb[l])) & 1u;
+                wl[l * 2 * M2 + k] = ok[l] ? mqc_sg_flip(__ldg(S.w22 + ((size_t)ia[l] * M2 + ib) * 4 + pav[l] * 2 + pbv), sx) : 0.0;
+            }
+            if (STAGE) {
+                const double2* __restrict__ Crow = C + (size_t)src[l] * nB;
+                for (unsigned j = tid; j < nB; j += MQC_SG_THREADS) srow[(size_t)l * nB + j] = Crow[j];
             }
         }
+        __syncthreads();
+        const double2* row[LB];
+        unsigned sl[MQC_SG_R];                                    // bit l: sign of link l for output r
+#pragma unroll
+        for (int r = 0; r < MQC_SG_R; ++r) sl[r] = 0u;
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            row[l] = STAGE ? (srow + (size_t)l * nB) : (C + (size_t)src[l] * nB);
+            const double al = ok[l] ? __ldg(S.ta1 + (size_t)ia[l] * nA + src[l]) : 0.0;
+#pragma unroll
+            for (int r = 0; r < MQC_SG_R; ++r) {
+                const unsigned sg = (__popc(bp[r] & zb[l]) + sga[l]) & 1u;
+                sl[r] |= sg << l;
+                if (ok[l] && jb[r] < nB) {
+                    const double w = mqc_sg_flip(al + __ldg(S.tb1 + ((size_t)ia[l] * 2 + pav[l]) * nB + jb[r]), sg);
+                    const double2 v = row[l][jb[r]];
+                    ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
+                }
+            }
+        }
+        const int e0 = __ldg(S.cls_off + c), e1 = __ldg(S.cls_off + c + 1);
         for (int e = e0; e < e1; ++e) {
 #pragma unroll
             for (int r = 0; r < MQC_SG_R; ++r) {
@@ -604,15 +644,15 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
                 const unsigned en = __ldg(S.ell_b1 + (size_t)e * nB + jb[r]);
                 if (en == MQC_SG_INVALID) continue;
                 const unsigned col = en & 0xffffu;
-                const double w = mqc_sg_flip(wl[((en >> 16) & 0xffu) * 2u + ((en >> 24) & 1u)], (en >> 25) & 1u);
-                const double2 v = row[col];
-                lr[r] = fma(w, v.x, lr[r]); li[r] = fma(w, v.y, li[r]);
-            }
-        }
+                const unsigned widx = ((en >> 16) & 0xffu) * 2u + ((en >> 24) & 1u);
+                const unsigned sg = (en >> 25) & 1u;
 #pragma unroll
-        for (int r = 0; r < MQC_SG_R; ++r) {
-            const unsigned s = (__popc(bp[r] & zb) + sga) & 1u;
-            ar[r] += mqc_sg_flip(lr[r], s); ai[r] += mqc_sg_flip(li[r], s);
+                for (int l = 0; l < LB; ++l) {
+                    const double w = mqc_sg_flip(wl[l * 2 * M2 + widx], sg ^ (sl[r] >> l));
+                    const double2 v = row[l][col];
+                    ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
+                }
+            }
         }
     }
 
@@ -662,10 +702,10 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
     }
 }
 
-static inline size_t mqc_sigma_smem_bytes(const MqcSigmaDev& S, bool stage) {
+static inline size_t mqc_sigma_smem_bytes(const MqcSigmaDev& S, bool stage, int lb) {
     const int M2 = S.n_m2 > 0 ? S.n_m2 : 1;
-    size_t b = stage ? (size_t)S.n_b * sizeof(double2) : 0;
-    b += (size_t)3 * M2 * sizeof(double);
+    size_t b = stage ? (size_t)lb * S.n_b * sizeof(double2) : 0;
+    b += (size_t)(2 * lb + 1) * M2 * sizeof(double);
     b += (size_t)(S.n_m4 > 0 ? S.n_m4 : 1);
     return (b + 15) & ~(size_t)15;
 }
