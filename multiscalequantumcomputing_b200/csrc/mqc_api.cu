@@ -154,7 +154,7 @@ struct mqc_solver {
     DevBuf<uint4> pl_hdr[2];
     MqcTileLists tlist[2];          // host copy of the offsets; tiles live in pl_tiles
     DevBuf<u64> pl_tiles[2];
-    int sp2 = 1, sp2_warps = 4, sp2_list = 1, sp2_smem_kb = 220;
+    int sp2 = 1, sp2_warps = 4, sp2_list = 1, sp2_smem_kb = 220, sp2_team = 0;
     double* scalars_p() const { return mail.p; }
     double* grad_p() const { return mail.p + MQC_MAIL_GRAD; }
     unsigned long long* flags_p() const { return reinterpret_cast<unsigned long long*>(mail.p + MQC_MAIL_FLAGS); }
@@ -261,10 +261,12 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_tile_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_tile_sparse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_tile_sparse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_tile_sp2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_tile_sp2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_tile_sp2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_tile_sp2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+#define MQC_SP2_ATTR(TW_) \
+    CK(cudaFuncSetAttribute(k_tile_sp2<false, false, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000)); \
+    CK(cudaFuncSetAttribute(k_tile_sp2<true, false, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000)); \
+    CK(cudaFuncSetAttribute(k_tile_sp2<false, true, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000)); \
+    CK(cudaFuncSetAttribute(k_tile_sp2<true, true, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    MQC_SP2_ATTR(1) MQC_SP2_ATTR(2) MQC_SP2_ATTR(4)
     CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     s->gpu_ready = true;
@@ -588,9 +590,13 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
     const bool sparse = s->conserving && s->use_sector && s->sparse_tiles;
     if (sparse && s->sp2 && s->plan[which].ok) {
         const MqcSpPass& SPP = s->plan[which].pass[pass];
-        int warps = s->sp2_warps;
-        size_t smem = mqc_sp2_smem_bytes(SPP, nf, adj, warps);
-        while (warps > 1 && smem > 200000) { warps >>= 1; smem = mqc_sp2_smem_bytes(SPP, nf, adj, warps); }
+        // warps per tile: large tiles are shared by a team of warps
+        int tw = s->sp2_team;
+        if (tw <= 0) tw = SPP.cap >= 300 ? 2 : 1;
+        int warps = std::max(s->sp2_warps, tw);
+        warps -= warps % tw;
+        size_t smem = mqc_sp2_smem_bytes(SPP, nf, adj, warps, tw);
+        while (warps > tw && smem > 200000) { warps -= tw; smem = mqc_sp2_smem_bytes(SPP, nf, adj, warps, tw); }
         if (smem <= 200000) {
             int per_sm = (int)std::min<size_t>(16, ((size_t)s->sp2_smem_kb * 1024) / (smem + 1024));
             per_sm = std::max(1, std::min(per_sm, 64 / warps));
@@ -603,23 +609,14 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
                 n_work = TB.n_list;
             }
             if (n_work == 0) return;
-            if (s->sp2_carveout_set != s->sp2_smem_kb) {           // leave the rest of the 256 KB to L1 (tables, lists, headers)
-                const int pct = std::min(100, (s->sp2_smem_kb + 8) * 100 / 228);
-                CK(cudaFuncSetAttribute(k_tile_sp2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                CK(cudaFuncSetAttribute(k_tile_sp2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                CK(cudaFuncSetAttribute(k_tile_sp2<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                CK(cudaFuncSetAttribute(k_tile_sp2<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-                s->sp2_carveout_set = s->sp2_smem_kb;
-            }
-            const u64 want = (n_work + warps - 1) / warps;
+            const int teams = warps / tw;
+            const u64 want = (n_work + teams - 1) / teams;
             const unsigned g2 = (unsigned)std::min<u64>(want, (u64)s->n_sm * per_sm);
-            if (list) {
-                if (adj) k_tile_sp2<true, true><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, s->grad_p(), reverse, TM.n_tiles);
-                else k_tile_sp2<false, true><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, nullptr, reverse, TM.n_tiles);
-            } else {
-                if (adj) k_tile_sp2<true, false><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, s->grad_p(), reverse, TM.n_tiles);
-                else k_tile_sp2<false, false><<<g2, warps * 32, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, nullptr, reverse, TM.n_tiles);
-            }
+            const unsigned nt = warps * 32;
+#define MQC_SP2_LAUNCH(ADJ_, LIST_, TW_) k_tile_sp2<ADJ_, LIST_, TW_><<<g2, nt, smem, s->stream>>>(PR, P, SPP, TB, s->tf[which].p, s->cs.p, adj ? s->grad_p() : nullptr, reverse, TM.n_tiles)
+#define MQC_SP2_PICK(TW_) do { if (adj) { if (list) MQC_SP2_LAUNCH(true, true, TW_); else MQC_SP2_LAUNCH(true, false, TW_); } \
+                               else { if (list) MQC_SP2_LAUNCH(false, true, TW_); else MQC_SP2_LAUNCH(false, false, TW_); } } while (0)
+            if (tw == 4) MQC_SP2_PICK(4); else if (tw == 2) MQC_SP2_PICK(2); else MQC_SP2_PICK(1);
             s->counters[0]++;
             return;
         }
@@ -989,6 +986,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sigma_stage") s->sigma_stage = (int)value;
     else if (k == "sp2") s->sp2 = (int)value;
     else if (k == "sp2_list") s->sp2_list = (int)value;
+    else if (k == "sp2_team") { if (value != 0 && value != 1 && value != 2 && value != 4) throw MqcError("sp2_team must be 0 (auto), 1, 2 or 4"); s->sp2_team = (int)value; }
     else if (k == "sp2_smem_kb") { if (value < 16 || value > 220) throw MqcError("sp2_smem_kb must be in [16,220]"); s->sp2_smem_kb = (int)value; }
     else if (k == "sp2_warps") { if (value < 1 || value > 8) throw MqcError("sp2_warps must be in [1,8]"); s->sp2_warps = (int)value; }
     else throw MqcError("unknown option: " + k);

@@ -378,19 +378,32 @@ static inline __host__ __device__ int mqc_sp2_max_patterns(const MqcSpPass& SP) 
 // LIST: tiles come from a host-built list (only the non-empty ones, sorted by size and dealt
 // round-robin over the CTAs so that every SM gets the same mix of large and small tiles);
 // otherwise every tile counter is decoded and tested on the fly (huge sharded registers).
-template <bool ADJ, bool LIST>
+// TW: warps per TEAM.  A team owns a tile; with TW == 1 factors are separated by __syncwarp(),
+// with TW > 1 by a named barrier over the team's TW * 32 threads (14-bit tiles hold up to 1225
+// amplitudes and 100-350 pairs per factor: enough work for several warps, and four times
+// as many warps in flight as tiles).
+template <int TW>
+__device__ __forceinline__ void team_sync(const int team) {
+    if (TW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(TW * 32) : "memory");
+}
+
+template <bool ADJ, bool LIST, int TW>
 __global__ void __launch_bounds__(256)
 k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass P, const __grid_constant__ MqcSpPass SP,
            const MqcSpTables TB, const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
            double* __restrict__ grad, const int reverse, const u64 n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_teams = W / TW, team = warp / TW, wt = warp - team * TW;      // warp within its team
+    const int tl = wt * 32 + lane;                                            // thread within its team
+    constexpr int TT = TW * 32;
     const int nf = P.f1 - P.f0;
     const int cap = SP.cap;
     const size_t gw_bytes = ADJ ? (((size_t)nf * sizeof(double) + 15) & ~(size_t)15) : 0;
     const size_t dep_bytes = mqc_sp2_dep_bytes(SP);
-    const size_t per_warp = (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2) + MQC_SP2_HDR_BYTES + dep_bytes + gw_bytes;
-    unsigned char* wb = smem_raw + (size_t)warp * per_warp;
+    const size_t per_team = (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2) + MQC_SP2_HDR_BYTES + dep_bytes;
+    unsigned char* wb = smem_raw + (size_t)team * per_team;
     double2* sp = reinterpret_cast<double2*>(wb);
     double2* sl = sp + (ADJ ? cap : 0);
     unsigned char* q = wb + (size_t)(ADJ ? 2 : 1) * cap * sizeof(double2);
@@ -405,7 +418,10 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
     uint4* hB = reinterpret_cast<uint4*>(q);        q += 32 * sizeof(uint4);
     uint32_t* hsg = reinterpret_cast<uint32_t*>(q); q += 32 * sizeof(uint32_t);
     int* hfi = reinterpret_cast<int*>(q);           q += 32 * sizeof(int);
-    double* gw = reinterpret_cast<double*>(q);      // [nf] gradient partials of this warp (ADJ)
+    // [warp][nf] gradient partials (ADJ), after all team regions; the last word of the team's
+    // header block carries the chunk's live-factor mask from warp 0 to the other warps
+    double* gw = reinterpret_cast<double*>(smem_raw + (size_t)n_teams * per_team + (size_t)warp * gw_bytes);
+    __shared__ unsigned s_todo[8];
     if (ADJ) {
         for (int i = lane; i < nf; i += 32) gw[i] = 0.0;
         __syncwarp();
@@ -415,7 +431,7 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
     const u64* __restrict__ ds = alt_store ? TB.depp : TB.dep;
     const u64 n_work = LIST ? TB.n_list : n_tiles;
 
-    for (u64 it = (u64)blockIdx.x + (u64)gridDim.x * warp; it < n_work; it += (u64)gridDim.x * W) {
+    for (u64 it = (u64)blockIdx.x + (u64)gridDim.x * team; it < n_work; it += (u64)gridDim.x * n_teams) {
         u64 base;
         int ka, kb;
         if (LIST) {
@@ -425,22 +441,22 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
             base = mqc_deposit_complement(it | PR.tau_hi, P.act_mask, PR.n_local) | PR.fixed_bits;
             ka = SP.na - __popcll(base & SP.amask);
             kb = SP.nb - __popcll(base & SP.bmask);
-            if (ka < 0 || kb < 0 || ka > SP.a_act || kb > SP.b_act) continue;   // tile holds only zeros
+            if (ka < 0 || kb < 0 || ka > SP.a_act || kb > SP.b_act) continue;   // tile holds only zeros (uniform over the team)
         }
         const int nAl = SP.cntA[ka], nBl = SP.cntB[kb];
         const int cnt = nAl * nBl;
         const uint32_t offA = SP.patoffA[ka], offB = SP.patoffB[kb];
         const float rcpB = __frcp_rn((float)nBl);
-        __syncwarp();                                             // previous tile's stores have read sp / sl / sd*
-        for (int i = lane; i < nAl + nBl; i += 32) {
+        team_sync<TW>(team);                                      // previous tile's stores have read sp / sl / sd*
+        for (int i = tl; i < nAl + nBl; i += TT) {
             const uint32_t src = i < nAl ? offA + i : offB + (i - nAl);
             sdl[i] = base | __ldg(dl + src);
             sds[i] = base | __ldg(ds + src);
             spat[i] = __ldg(TB.pat + src);
         }
-        __syncwarp();
+        team_sync<TW>(team);
         // ---- load ---------------------------------------------------------------------------
-        for (int e = lane; e < cnt; e += 32) {
+        for (int e = tl; e < cnt; e += TT) {
             const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
             const u64 g = sdl[ja] | sdl[nAl + jb];
             cp_async16(sp + e, peer_psi(PR, g));
@@ -449,45 +465,49 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
         // ---- factors ------------------------------------------------------------------------
         for (int c0 = 0; c0 < nf; c0 += 32) {
             const int nc = min(32, nf - c0);
-            __syncwarp();                                         // previous chunk's headers are consumed
-            bool live = false;
-            uint4 a4 = make_uint4(0, 0, 0, 0), b4 = make_uint4(0, 0, 0, 0);
-            int nstage = 0;
-            if (lane < nc) {
-                const int f = reverse ? (nf - 1 - (c0 + lane)) : (c0 + lane);
-                a4 = __ldg(TB.hdr + SP.hdrA_off + (size_t)f * MQC_SP_KMAX + ka);
-                b4 = __ldg(TB.hdr + SP.hdrB_off + (size_t)f * MQC_SP_KMAX + kb);
-                live = (a4.y != 0u) && (b4.y != 0u);
-                if (live) {
-                    const MqcTileFactor* Fp = tf + P.f0 + f;
-                    const double2 v = cs[Fp->slot];
-                    hcs[lane] = make_double2(v.x, reverse ? -v.y : v.y);
-                    hsg[lane] = ((uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
-                    hfi[lane] = f;
-                    nstage = (int)(((a4.w >> 16) & 1u) ? 0u : a4.y) + (int)(((b4.w >> 16) & 1u) ? 0u : b4.y);
+            team_sync<TW>(team);                                  // previous chunk's headers are consumed
+            if (wt == 0) {
+                bool live = false;
+                uint4 a4 = make_uint4(0, 0, 0, 0), b4 = make_uint4(0, 0, 0, 0);
+                int nstage = 0;
+                if (lane < nc) {
+                    const int f = reverse ? (nf - 1 - (c0 + lane)) : (c0 + lane);
+                    a4 = __ldg(TB.hdr + SP.hdrA_off + (size_t)f * MQC_SP_KMAX + ka);
+                    b4 = __ldg(TB.hdr + SP.hdrB_off + (size_t)f * MQC_SP_KMAX + kb);
+                    live = (a4.y != 0u) && (b4.y != 0u);
+                    if (live) {
+                        const MqcTileFactor* Fp = tf + P.f0 + f;
+                        const double2 v = cs[Fp->slot];
+                        hcs[lane] = make_double2(v.x, reverse ? -v.y : v.y);
+                        hsg[lane] = ((uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
+                        hfi[lane] = f;
+                        nstage = (int)(((a4.w >> 16) & 1u) ? 0u : a4.y) + (int)(((b4.w >> 16) & 1u) ? 0u : b4.y);
+                    }
                 }
-            }
-            // the short pair lists of the acting sides go to shared memory (one batch of loads per
-            // chunk instead of dependent global loads inside the pair loop)
-            int soff = nstage;
+                // the short pair lists of the acting sides go to shared memory (one batch of loads
+                // per chunk instead of dependent global loads inside the pair loop)
+                int soff = nstage;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, soff, o); if (lane >= o) soff += t; }
-            soff -= nstage;
-            if (live) {
-                int w = soff;
-                if (!((a4.w >> 16) & 1u)) {
-                    for (uint32_t j = 0; j < a4.y; ++j) { const uint32_t en = __ldg(TB.lists + a4.x + j); slist[w + j] = (uint16_t)((en & 0x7fu) | (((en >> 12) & 0x7fu) << 7) | (((en >> 24) & 1u) << 14)); }
-                    a4.x = (uint32_t)w; w += (int)a4.y;
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, soff, o); if (lane >= o) soff += t; }
+                soff -= nstage;
+                if (live) {
+                    int w = soff;
+                    if (!((a4.w >> 16) & 1u)) {
+                        for (uint32_t j = 0; j < a4.y; ++j) { const uint32_t en = __ldg(TB.lists + a4.x + j); slist[w + j] = (uint16_t)((en & 0x7fu) | (((en >> 12) & 0x7fu) << 7) | (((en >> 24) & 1u) << 14)); }
+                        a4.x = (uint32_t)w; w += (int)a4.y;
+                    }
+                    if (!((b4.w >> 16) & 1u)) {
+                        for (uint32_t j = 0; j < b4.y; ++j) { const uint32_t en = __ldg(TB.lists + b4.x + j); slist[w + j] = (uint16_t)((en & 0x7fu) | (((en >> 12) & 0x7fu) << 7) | (((en >> 24) & 1u) << 14)); }
+                        b4.x = (uint32_t)w;
+                    }
+                    hA[lane] = a4; hB[lane] = b4;
                 }
-                if (!((b4.w >> 16) & 1u)) {
-                    for (uint32_t j = 0; j < b4.y; ++j) { const uint32_t en = __ldg(TB.lists + b4.x + j); slist[w + j] = (uint16_t)((en & 0x7fu) | (((en >> 12) & 0x7fu) << 7) | (((en >> 24) & 1u) << 14)); }
-                    b4.x = (uint32_t)w;
-                }
-                hA[lane] = a4; hB[lane] = b4;
+                const unsigned m = __ballot_sync(0xffffffffu, live);   // factors that couple anything in this tile
+                if (lane == 0) s_todo[team] = m;
             }
-            unsigned todo = __ballot_sync(0xffffffffu, live);     // factors that couple anything in this tile
             if (c0 == 0) cp_async_wait_all();
-            __syncwarp();
+            team_sync<TW>(team);
+            unsigned todo = s_todo[team];
             while (todo) {
                 const int fc = __ffs(todo) - 1;
                 todo &= todo - 1;
@@ -500,7 +520,7 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
                 const float rcp = __uint_as_float(B.z);
                 const bool idA = (A.w >> 16) & 1u, idB = (B.w >> 16) & 1u;
                 double gacc = 0.0;
-                for (int u = lane; u < npairs; u += 32) {
+                for (int u = tl; u < npairs; u += TT) {
                     const int ua = (int)(((float)u + 0.5f) * rcp), ub = u - ua * nLB;
                     const uint32_t la = idA ? ((uint32_t)ua * 129u | (((uint32_t)__popc(spat[ua] & A.w) & 1u) << 14)) : (uint32_t)slist[A.x + ua];
                     const uint32_t lb = idB ? ((uint32_t)ub * 129u | (((uint32_t)__popc(spat[nAl + ub] & B.w) & 1u) << 14)) : (uint32_t)slist[B.x + ub];
@@ -519,29 +539,30 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
                     sp[e0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
                     sp[e1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
                 }
-                if (ADJ) {
-                    // lanes >= npairs hold zero: only the butterfly stages below npairs matter
+                if (ADJ && npairs > wt * 32) {                    // uniform over the warp: this warp had pairs
+                    // lanes beyond the warp's share hold zero: only the butterfly stages below it matter
+                    const int mine = min(32, npairs - wt * 32);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) if (npairs > o) gacc += __shfl_xor_sync(0xffffffffu, gacc, o);
+                    for (int o = 16; o > 0; o >>= 1) if (mine > o || TW > 1) gacc += __shfl_xor_sync(0xffffffffu, gacc, o);
                     if (lane == 0) gw[hfi[fc]] += gacc;
                 }
-                __syncwarp();
+                team_sync<TW>(team);
             }
         }
-        if (nf == 0) { cp_async_wait_all(); __syncwarp(); }
+        if (nf == 0) { cp_async_wait_all(); team_sync<TW>(team); }
         // ---- store --------------------------------------------------------------------------
         // a re-layout pass moves the elements to other addresses of the same tile: clear the
         // addresses they came from first (everything outside the sector stays exactly zero)
         if (P.has_perm) {
-            for (int e = lane; e < cnt; e += 32) {
+            for (int e = tl; e < cnt; e += TT) {
                 const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
                 const u64 g = sdl[ja] | sdl[nAl + jb];
                 *peer_psi(PR, g) = make_double2(0.0, 0.0);
                 if (ADJ) *peer_lam(PR, g) = make_double2(0.0, 0.0);
             }
-            __syncwarp();
+            team_sync<TW>(team);
         }
-        for (int e = lane; e < cnt; e += 32) {
+        for (int e = tl; e < cnt; e += TT) {
             const int ja = (int)(((float)e + 0.5f) * rcpB), jb = e - ja * nBl;
             const u64 g = sds[ja] | sds[nAl + jb];
             *peer_psi(PR, g) = sp[e];
@@ -551,17 +572,19 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
     if (ADJ) {
         // CTA-level sum of the warps' partials, then one global atomic per (CTA, factor)
         __syncthreads();
+        const double* gall = reinterpret_cast<const double*>(smem_raw + (size_t)n_teams * per_team);
         for (int i = threadIdx.x; i < nf; i += blockDim.x) {
             double g = 0.0;
-            for (int w = 0; w < W; ++w) g += *reinterpret_cast<double*>(smem_raw + (size_t)w * per_warp + (per_warp - gw_bytes) + (size_t)i * sizeof(double));
+            for (int w = 0; w < W; ++w) g += gall[(size_t)w * (gw_bytes / sizeof(double)) + i];
             if (g != 0.0) atomicAdd(grad + tf[P.f0 + i].theta, 2.0 * g);
         }
     }
 }
 
-static inline size_t mqc_sp2_smem_bytes(const MqcSpPass& SP, int nf, bool adj, int warps) {
+static inline size_t mqc_sp2_smem_bytes(const MqcSpPass& SP, int nf, bool adj, int warps, int team_warps) {
     const size_t gw_bytes = adj ? (((size_t)nf * sizeof(double) + 15) & ~(size_t)15) : 0;
-    return (size_t)warps * ((size_t)(adj ? 2 : 1) * SP.cap * sizeof(double2) + MQC_SP2_HDR_BYTES + mqc_sp2_dep_bytes(SP) + gw_bytes);
+    const size_t per_team = (size_t)(adj ? 2 : 1) * SP.cap * sizeof(double2) + MQC_SP2_HDR_BYTES + mqc_sp2_dep_bytes(SP);
+    return (size_t)(warps / team_warps) * per_team + (size_t)warps * gw_bytes;
 }
 
 static inline size_t mqc_sparse_smem_bytes(int K, int cap, bool adj) {
