@@ -165,9 +165,12 @@ static inline MqcSigmaHost mqc_sigma_build(int n_orb, int na, int nb, const std:
         S.sa_b4[i] = mqc_sg_spin_part(zb, 0, n_orb); sb_b4[i] = mqc_sg_spin_part(zb, 1, n_orb);
     }
     S.w22.assign((size_t)M2 * M2 * 4, 0.0);
-    S.w4a.assign((size_t)M4 * 6, 0.0); S.w4b.assign((size_t)M4 * 6, 0.0);
+    // one extra all-zero mask index (n_m2 / n_m4) is what the padding entries of the beta ELL
+    // tables point to: the hot loops need no validity test
+    S.w4a.assign((size_t)M4 * 6, 0.0); S.w4b.assign((size_t)(M4 + 1) * 6, 0.0);
     S.ta1.assign((size_t)M2 * S.n_a, 0.0); S.tb1.assign((size_t)M2 * 2 * S.n_b, 0.0);
-    S.tab.assign((size_t)M2 * 2 * S.n_a, 0.0); S.tbb.assign((size_t)M2 * S.n_b, 0.0);
+    S.tab.assign((size_t)M2 * 2 * S.n_a, 0.0); S.tbb.assign((size_t)(M2 + 1) * S.n_b, 0.0);
+    S.sa_b4.push_back(0);
 
     // ---- group the terms by (ma, mb) ---------------------------------------------------------
     const u64 amask_q = mqc_sg_spread((1u << n_orb) - 1u, 0, n_orb), bmask_q = amask_q << 1;
@@ -314,7 +317,7 @@ static inline MqcSigmaHost mqc_sigma_build(int n_orb, int na, int nb, const std:
         }
         S.cls_off[c + 1] = S.cls_off[c] + (int)emax;
         const size_t base = S.ell_b1.size();
-        S.ell_b1.resize(base + emax * S.n_b, MQC_SG_INVALID);
+        S.ell_b1.resize(base + emax * S.n_b, (unsigned)S.n_m2 << 16);
         for (unsigned j = 0; j < S.n_b; ++j)
             for (size_t e = 0; e < rows[j].size(); ++e) S.ell_b1[base + e * S.n_b + j] = rows[j][e];
     }
@@ -339,7 +342,7 @@ static inline MqcSigmaHost mqc_sigma_build(int n_orb, int na, int nb, const std:
         }
         for (auto& r : rows) emax = std::max(emax, r.size());
         S.e2b = (int)emax;
-        S.ell_b2.assign(std::max<size_t>(1, emax * S.n_b), MQC_SG_INVALID);
+        S.ell_b2.assign(std::max<size_t>(1, emax * S.n_b), (unsigned)S.n_m4 << 16);
         for (unsigned j = 0; j < S.n_b; ++j)
             for (size_t e = 0; e < rows[j].size(); ++e) S.ell_b2[e * S.n_b + j] = rows[j][e];
     }
@@ -392,7 +395,7 @@ static inline MqcSigmaHost mqc_sigma_build(int n_orb, int na, int nb, const std:
             for (size_t e = 0; e < r2[i].size(); ++e) S.lnk_a2[e * S.n_a + i] = r2[i][e];
         }
     }
-    if (S.ell_b1.empty()) S.ell_b1.push_back(MQC_SG_INVALID);
+    if (S.ell_b1.empty()) S.ell_b1.push_back((unsigned)S.n_m2 << 16);
     return S;
 }
 
@@ -418,8 +421,8 @@ static inline void mqc_sigma_apply_host(const MqcSigmaHost& S, const double2* C,
             const int c0 = S.cls_of_m2[S.n_m2];
             if (c0 >= 0) for (int e = S.cls_off[c0]; e < S.cls_off[c0 + 1]; ++e) {
                 const unsigned en = S.ell_b1[(size_t)e * nB + j];
-                if (en == MQC_SG_INVALID) continue;
                 const unsigned col = en & 0xffffu, ib = (en >> 16) & 0xffu, pbv = (en >> 24) & 1u, sg = (en >> 25) & 1u;
+                if (ib == (unsigned)S.n_m2) continue;                    // padding
                 const unsigned sx = __builtin_popcount(ap & S.sa_b2[ib]) & 1u;
                 double w = S.tab[((size_t)ib * 2 + pbv) * nA + i] + S.tbb[(size_t)ib * nB + col];
                 if ((sx + sg) & 1u) w = -w;
@@ -427,8 +430,8 @@ static inline void mqc_sigma_apply_host(const MqcSigmaHost& S, const double2* C,
             }
             for (int e = 0; e < S.e2b; ++e) {
                 const unsigned en = S.ell_b2[(size_t)e * nB + j];
-                if (en == MQC_SG_INVALID) continue;
                 const unsigned col = en & 0xffffu, i4 = (en >> 16) & 0xfffu, p6 = (en >> 28) & 7u, sg = en >> 31;
+                if (i4 == (unsigned)S.n_m4) continue;                    // padding
                 const unsigned sx = __builtin_popcount(ap & S.sa_b4[i4]) & 1u;
                 double w = S.w4b[(size_t)i4 * 6 + p6];
                 if ((sx + sg) & 1u) w = -w;
@@ -445,8 +448,8 @@ static inline void mqc_sigma_apply_host(const MqcSigmaHost& S, const double2* C,
                 const int c = S.cls_of_m2[ia];
                 for (int e = S.cls_off[c]; e < S.cls_off[c + 1]; ++e) {
                     const unsigned en = S.ell_b1[(size_t)e * nB + j];
-                    if (en == MQC_SG_INVALID) continue;
                     const unsigned col = en & 0xffffu, ib = (en >> 16) & 0xffu, pbv = (en >> 24) & 1u, sg = (en >> 25) & 1u;
+                    if (ib == (unsigned)S.n_m2) continue;                // padding
                     const unsigned mb = S.m2_mask[ib];
                     double w = S.w22[((size_t)ia * M2 + ib) * 4 + pav * 2 + pbv];
                     const unsigned sxa = __builtin_popcount(a & S.sa_b2[ib] & ~ma) & 1u;
@@ -511,79 +514,94 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
     extern __shared__ __align__(16) unsigned char sg_smem[];
     const unsigned nA = S.n_a, nB = S.n_b;
     const int M2 = S.n_m2 > 0 ? S.n_m2 : 1;
+    const int WS = 2 * (S.n_m2 + 1);                               // weight-table stride; last pair = 0 (padding)
     double2* srow = reinterpret_cast<double2*>(sg_smem);
     double* wl = reinterpret_cast<double*>(sg_smem + (STAGE ? (size_t)LB * nB * sizeof(double2) : 0));
-    double* sxd = wl + (size_t)LB * 2 * M2;
-    unsigned char* sg4 = reinterpret_cast<unsigned char*>(sxd + M2);
+    double* sxd = wl + (size_t)LB * WS;
+    unsigned char* sg4 = reinterpret_cast<unsigned char*>(sxd + (S.n_m2 + 1));
     __shared__ double red[2][MQC_SG_THREADS / 32];
 
     const int tid = threadIdx.x;
     const unsigned i = S.row0 + blockIdx.x;
     const unsigned ap = __ldg(S.aorb + i);
-    unsigned jb[MQC_SG_R], bp[MQC_SG_R];
+    unsigned jb[MQC_SG_R], jc[MQC_SG_R], bp[MQC_SG_R];              // jc: clamped column for loads of idle threads
     double ar[MQC_SG_R], ai[MQC_SG_R];
 #pragma unroll
     for (int r = 0; r < MQC_SG_R; ++r) {
         jb[r] = (blockIdx.y * MQC_SG_R + r) * MQC_SG_THREADS + tid;
-        bp[r] = jb[r] < nB ? __ldg(S.borb + jb[r]) : 0u;
+        jc[r] = jb[r] < nB ? jb[r] : nB - 1u;
+        bp[r] = __ldg(S.borb + jc[r]);
         ar[r] = 0.0; ai[r] = 0.0;
     }
 
     // ---- phase 0: beta-only part on the own row ---------------------------------------------
     {
         const int c0 = __ldg(S.cls_of_m2 + S.n_m2);
-        for (int k = tid; k < 2 * S.n_m2; k += MQC_SG_THREADS) {
+        for (int k = tid; k < WS; k += MQC_SG_THREADS) {
             const int ib = k >> 1, pbv = k & 1;
-            const unsigned sx = __popc(ap & __ldg(S.sa_b2 + ib)) & 1u;
-            wl[k] = mqc_sg_flip(__ldg(S.tab + ((size_t)ib * 2 + pbv) * nA + i), sx);
-            if (pbv == 0) sxd[ib] = sx ? -1.0 : 1.0;
+            double w = 0.0, sd = 0.0;
+            if (ib < S.n_m2) {
+                const unsigned sx = __popc(ap & __ldg(S.sa_b2 + ib)) & 1u;
+                w = mqc_sg_flip(__ldg(S.tab + ((size_t)ib * 2 + pbv) * nA + i), sx);
+                sd = sx ? -1.0 : 1.0;
+            }
+            wl[k] = w;
+            if (pbv == 0) sxd[ib] = sd;
         }
-        for (int k = tid; k < S.n_m4; k += MQC_SG_THREADS) sg4[k] = (unsigned char)(__popc(ap & __ldg(S.sa_b4 + k)) & 1u);
+        for (int k = tid; k <= S.n_m4; k += MQC_SG_THREADS) sg4[k] = (unsigned char)(__popc(ap & __ldg(S.sa_b4 + k)) & 1u);
         const double2* __restrict__ Crow = C + (size_t)i * nB;
         if (STAGE) for (unsigned j = tid; j < nB; j += MQC_SG_THREADS) srow[j] = Crow[j];
         __syncthreads();
         const double2* __restrict__ row = STAGE ? srow : Crow;
         if (c0 >= 0) {
             const int e0 = __ldg(S.cls_off + c0), e1 = __ldg(S.cls_off + c0 + 1);
+            unsigned nx[MQC_SG_R];
+#pragma unroll
+            for (int r = 0; r < MQC_SG_R; ++r) nx[r] = e0 < e1 ? __ldg(S.ell_b1 + (size_t)e0 * nB + jc[r]) : 0u;
             for (int e = e0; e < e1; ++e) {
+                unsigned en[MQC_SG_R];
+#pragma unroll
+                for (int r = 0; r < MQC_SG_R; ++r) { en[r] = nx[r]; if (e + 1 < e1) nx[r] = __ldg(S.ell_b1 + (size_t)(e + 1) * nB + jc[r]); }
 #pragma unroll
                 for (int r = 0; r < MQC_SG_R; ++r) {
-                    if (jb[r] >= nB) continue;
-                    const unsigned en = __ldg(S.ell_b1 + (size_t)e * nB + jb[r]);
-                    if (en == MQC_SG_INVALID) continue;
-                    const unsigned col = en & 0xffffu, ib = (en >> 16) & 0xffu;
-                    const unsigned widx = (ib << 1) | ((en >> 24) & 1u);
+                    const unsigned col = en[r] & 0xffffu, ib = (en[r] >> 16) & 0xffu;
+                    const unsigned widx = (ib << 1) | ((en[r] >> 24) & 1u);
                     double w = fma(sxd[ib], __ldg(S.tbb + (size_t)ib * nB + col), wl[widx]);
-                    w = mqc_sg_flip(w, (en >> 25) & 1u);
+                    w = mqc_sg_flip(w, (en[r] >> 25) & 1u);
                     const double2 v = row[col];
                     ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
                 }
             }
         }
-        for (int e = 0; e < S.e2b; ++e) {
+        {
+            unsigned nx[MQC_SG_R];
 #pragma unroll
-            for (int r = 0; r < MQC_SG_R; ++r) {
-                if (jb[r] >= nB) continue;
-                const unsigned en = __ldg(S.ell_b2 + (size_t)e * nB + jb[r]);
-                if (en == MQC_SG_INVALID) continue;
-                const unsigned col = en & 0xffffu, i4 = (en >> 16) & 0xfffu, p6 = (en >> 28) & 7u;
-                const double w = mqc_sg_flip(__ldg(S.w4b + (size_t)i4 * 6 + p6), (unsigned)sg4[i4] ^ (en >> 31));
-                const double2 v = row[col];
-                ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
+            for (int r = 0; r < MQC_SG_R; ++r) nx[r] = S.e2b > 0 ? __ldg(S.ell_b2 + jc[r]) : 0u;
+            for (int e = 0; e < S.e2b; ++e) {
+                unsigned en[MQC_SG_R];
+#pragma unroll
+                for (int r = 0; r < MQC_SG_R; ++r) { en[r] = nx[r]; if (e + 1 < S.e2b) nx[r] = __ldg(S.ell_b2 + (size_t)(e + 1) * nB + jc[r]); }
+#pragma unroll
+                for (int r = 0; r < MQC_SG_R; ++r) {
+                    const unsigned col = en[r] & 0xffffu, i4 = (en[r] >> 16) & 0xfffu, p6 = (en[r] >> 28) & 7u;
+                    const double w = mqc_sg_flip(__ldg(S.w4b + (size_t)i4 * 6 + p6), (unsigned)sg4[i4] ^ (en[r] >> 31));
+                    const double2 v = row[col];
+                    ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
+                }
             }
         }
 #pragma unroll
         for (int r = 0; r < MQC_SG_R; ++r) {
-            if (jb[r] >= nB) continue;
-            const double d = __ldg(S.hdiag + (size_t)(i - S.row0) * nB + jb[r]);
-            const double2 v = row[jb[r]];
+            const double d = __ldg(S.hdiag + (size_t)(i - S.row0) * nB + jc[r]);
+            const double2 v = row[jc[r]];
             ar[r] = fma(d, v.x, ar[r]); ai[r] = fma(d, v.y, ai[r]);
         }
     }
 
     // ---- phase 1: alpha single links (alpha-beta doubles + the alpha single groups) ----------
     // LB links per batch: their source rows are staged together and every ELL entry (column,
-    // weight index, sign) is loaded and decoded once for all of them.
+    // weight index, sign) is loaded and decoded once for all of them; the next entry is in
+    // flight while the current one is applied.
     for (int l0 = 0; l0 < S.e1a; l0 += LB) {
         unsigned src[LB], ia[LB], pav[LB], sga[LB], zb[LB];
         bool ok[LB];
@@ -604,12 +622,16 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
 #pragma unroll
         for (int l = 0; l < LB; ++l) {
             const unsigned a = __ldg(S.aorb + src[l]), ma = __ldg(S.m2_mask + ia[l]);
-            for (int k = tid; k < 2 * S.n_m2; k += MQC_SG_THREADS) {
+            for (int k = tid; k < WS; k += MQC_SG_THREADS) {
                 const int ib = k >> 1, pbv = k & 1;
-                const unsigned mb = __ldg(S.m2_mask + ib);
-                const unsigned dest = pbv ? (mb & (0u - mb)) : (mb & (mb - 1u));   // output string's bit on mb
-                const unsigned sx = (__popc(a & __ldg(S.sa_b2 + ib) & ~ma) + __popc(dest & zb[l])) & 1u;
-                wl[l * 2 * M2 + k] = ok[l] ? mqc_sg_flip(__ldg(S.w22 + ((size_t)ia[l] * M2 + ib) * 4 + pav[l] * 2 + pbv), sx) : 0.0;
+                double w = 0.0;
+                if (ok[l] && ib < S.n_m2) {
+                    const unsigned mb = __ldg(S.m2_mask + ib);
+                    const unsigned dest = pbv ? (mb & (0u - mb)) : (mb & (mb - 1u));   // output string's bit on mb
+                    const unsigned sx = (__popc(a & __ldg(S.sa_b2 + ib) & ~ma) + __popc(dest & zb[l])) & 1u;
+                    w = mqc_sg_flip(__ldg(S.w22 + ((size_t)ia[l] * M2 + ib) * 4 + pav[l] * 2 + pbv), sx);
+                }
+                wl[l * WS + k] = w;
             }
             if (STAGE) {
                 const double2* __restrict__ Crow = C + (size_t)src[l] * nB;
@@ -629,26 +651,29 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
             for (int r = 0; r < MQC_SG_R; ++r) {
                 const unsigned sg = (__popc(bp[r] & zb[l]) + sga[l]) & 1u;
                 sl[r] |= sg << l;
-                if (ok[l] && jb[r] < nB) {
-                    const double w = mqc_sg_flip(al + __ldg(S.tb1 + ((size_t)ia[l] * 2 + pav[l]) * nB + jb[r]), sg);
-                    const double2 v = row[l][jb[r]];
+                if (ok[l]) {
+                    const double w = mqc_sg_flip(al + __ldg(S.tb1 + ((size_t)ia[l] * 2 + pav[l]) * nB + jc[r]), sg);
+                    const double2 v = row[l][jc[r]];
                     ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
                 }
             }
         }
         const int e0 = __ldg(S.cls_off + c), e1 = __ldg(S.cls_off + c + 1);
+        unsigned nx[MQC_SG_R];
+#pragma unroll
+        for (int r = 0; r < MQC_SG_R; ++r) nx[r] = e0 < e1 ? __ldg(S.ell_b1 + (size_t)e0 * nB + jc[r]) : 0u;
         for (int e = e0; e < e1; ++e) {
+            unsigned en[MQC_SG_R];
+#pragma unroll
+            for (int r = 0; r < MQC_SG_R; ++r) { en[r] = nx[r]; if (e + 1 < e1) nx[r] = __ldg(S.ell_b1 + (size_t)(e + 1) * nB + jc[r]); }
 #pragma unroll
             for (int r = 0; r < MQC_SG_R; ++r) {
-                if (jb[r] >= nB) continue;
-                const unsigned en = __ldg(S.ell_b1 + (size_t)e * nB + jb[r]);
-                if (en == MQC_SG_INVALID) continue;
-                const unsigned col = en & 0xffffu;
-                const unsigned widx = ((en >> 16) & 0xffu) * 2u + ((en >> 24) & 1u);
-                const unsigned sg = (en >> 25) & 1u;
+                const unsigned col = en[r] & 0xffffu;
+                const unsigned widx = ((en[r] >> 16) & 0xffu) * 2u + ((en[r] >> 24) & 1u);
+                const unsigned sg = (en[r] >> 25) & 1u;
 #pragma unroll
                 for (int l = 0; l < LB; ++l) {
-                    const double w = mqc_sg_flip(wl[l * 2 * M2 + widx], sg ^ (sl[r] >> l));
+                    const double w = mqc_sg_flip(wl[l * WS + widx], sg ^ (sl[r] >> l));
                     const double2 v = row[l][col];
                     ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
                 }
@@ -657,19 +682,22 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
     }
 
     // ---- phase 2: alpha-alpha double links (diagonal in beta, coalesced row reads) -----------
-    for (int l = 0; l < S.e2a; ++l) {
-        const unsigned ln = __ldg(S.lnk_a2 + (size_t)l * nA + i);
-        if (ln == MQC_SG_INVALID) continue;
-        const unsigned src = ln & 0xffffu, i4 = (ln >> 16) & 0xfffu, p6 = (ln >> 28) & 7u, sga = ln >> 31;
-        const double w = __ldg(S.w4a + (size_t)i4 * 6 + p6);
-        const unsigned zb = __ldg(S.sb_a4 + i4);
-        const double2* __restrict__ Crow = C + (size_t)src * nB;
+    {
+        unsigned lnx = S.e2a > 0 ? __ldg(S.lnk_a2 + i) : MQC_SG_INVALID;
+        for (int l = 0; l < S.e2a; ++l) {
+            const unsigned ln = lnx;
+            if (l + 1 < S.e2a) lnx = __ldg(S.lnk_a2 + (size_t)(l + 1) * nA + i);
+            if (ln == MQC_SG_INVALID) continue;
+            const unsigned src = ln & 0xffffu, i4 = (ln >> 16) & 0xfffu, p6 = (ln >> 28) & 7u, sga = ln >> 31;
+            const double w = __ldg(S.w4a + (size_t)i4 * 6 + p6);
+            const unsigned zb = __ldg(S.sb_a4 + i4);
+            const double2* __restrict__ Crow = C + (size_t)src * nB;
 #pragma unroll
-        for (int r = 0; r < MQC_SG_R; ++r) {
-            if (jb[r] >= nB) continue;
-            const double2 v = Crow[jb[r]];
-            const double ws = mqc_sg_flip(w, (__popc(bp[r] & zb) + sga) & 1u);
-            ar[r] = fma(ws, v.x, ar[r]); ai[r] = fma(ws, v.y, ai[r]);
+            for (int r = 0; r < MQC_SG_R; ++r) {
+                const double2 v = Crow[jc[r]];
+                const double ws = mqc_sg_flip(w, (__popc(bp[r] & zb) + sga) & 1u);
+                ar[r] = fma(ws, v.x, ar[r]); ai[r] = fma(ws, v.y, ai[r]);
+            }
         }
     }
 
@@ -705,8 +733,9 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
 static inline size_t mqc_sigma_smem_bytes(const MqcSigmaDev& S, bool stage, int lb) {
     const int M2 = S.n_m2 > 0 ? S.n_m2 : 1;
     size_t b = stage ? (size_t)lb * S.n_b * sizeof(double2) : 0;
-    b += (size_t)(2 * lb + 1) * M2 * sizeof(double);
-    b += (size_t)(S.n_m4 > 0 ? S.n_m4 : 1);
+    (void)M2;
+    b += ((size_t)lb * 2 * (S.n_m2 + 1) + (size_t)(S.n_m2 + 1)) * sizeof(double);
+    b += (size_t)S.n_m4 + 1;
     return (b + 15) & ~(size_t)15;
 }
 #endif
