@@ -21,7 +21,8 @@ def raw(rep):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     return rows[0], rows[1], rows[2:]
-for name in ("tile_fwd", "tile_adj", "happly", "dense_fwd"):
+traffic = {}
+for name in ("tile_fwd", "tile_adj", "happly", "dense_fwd", "sp2f", "sp2a", "sp2", "sigma"):
     rep = "gpurun_out/%s_%s.ncu-rep" % (R, name)
     if not os.path.exists(rep):
         continue
@@ -50,6 +51,15 @@ for name in ("tile_fwd", "tile_adj", "happly", "dense_fwd"):
             g("sm__throughput.avg.pct_of_peak_sustained_elapsed"), g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
             g("sm__warps_active.avg.pct_of_peak_sustained_active"), g("smsp__inst_executed.sum"),
             g("smsp__thread_inst_executed_per_inst_executed.ratio")))
+        try:
+            def _b(k):
+                v = float(g(k).replace(",", "")); un = u(k).lower()
+                return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(un, 1)
+            key = kn.replace("void ", "").split("<")[0] + ("<true>" if ("<1" in kn or "(bool)1" in kn) else ("<false>" if ("<0" in kn or "(bool)0" in kn) else ""))
+            t = traffic.setdefault(key, [])
+            t.append(_b("dram__bytes_read.sum") + _b("dram__bytes_write.sum"))
+        except Exception:
+            pass
         top = sorted(((float(r[hdr.index(s)] or 0), s) for s in stall), reverse=True)[:4]
         lines.append("  * top stalls (warps per issue): " + ", ".join(
             "%s %.2f" % (s.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v) for v, s in top))
@@ -77,5 +87,14 @@ if os.path.exists(ll):
     lines.append("")
     with open(os.path.join(OUT, "launches_%s.csv" % R), "w") as f:
         f.write(txt[start:])
+if traffic:
+    tj = os.path.join(OUT, "traffic.json")
+    cur = json.load(open(tj)) if os.path.exists(tj) else {}
+    for k, v in traffic.items():
+        cur[k] = {"dram_bytes_per_launch": sum(v) / len(v), "launches_captured": len(v),
+                  "source": "ncu --set full, %s (cold cache, serialised)" % R}
+    json.dump(cur, open(tj, "w"), indent=1, sort_keys=True)
+if len(sys.argv) > 2:
+    lines += ["", open(sys.argv[2]).read()]
 open(os.path.join(OUT, "%s_summary.md" % R), "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
