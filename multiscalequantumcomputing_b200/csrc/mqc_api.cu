@@ -143,7 +143,10 @@ struct mqc_solver {
     // options
     int tile_bits = 14, low_bits = 3, grad_tile_bits = 14, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
 
-    DevBuf<double2> psi, lam, cs, scratch_state, csec, lsec;
+    DevBuf<double2> psi, lam, cs, scratch_state, csec, lsec, cown, cblk;
+    double2* peer_cown[MQC_MAX_RANKS] = {};
+    int sigma_blocked = -1;          // -1 auto, 0 replicate C on every rank, 1 distribute its rows
+    bool blocked = false, connected_cown = false;
     DevBuf<double> theta, mail, red, rdm_acc;
     DevBuf<int> theta_index, err;
     DevBuf<MqcTileFactor> tf[2];
@@ -464,6 +467,11 @@ static double binom_d(int n, int k) {
     return r;
 }
 
+static void sector_dims_pre(const mqc_solver* s, unsigned& nA, unsigned& nB) {
+    nA = (unsigned)(binom_d((s->n + 1) / 2, s->na) + 0.5);
+    nB = (unsigned)(binom_d(s->n / 2, s->nb) + 0.5);
+}
+
 static u64 logical_to_qubit(u64 m, int n) {
     u64 out = 0;
     for (int q = 0; q < n; ++q) if ((m >> (n - 1 - q)) & 1ull) out |= 1ull << q;
@@ -705,8 +713,101 @@ static void forward(mqc_solver* L, int which, const double* theta) {
 
 // lambda = H psi (optional) and this group's energy partials in every member's scalars
 struct HamView { const HamTables* T; const SecHamTables* ST; const SigmaTables* SG; };
+static void sector_dims(const mqc_solver* s, unsigned& nA, unsigned& nB) {
+    nA = (unsigned)(binom_d((s->n + 1) / 2, s->na) + 0.5);
+    nB = (unsigned)(binom_d(s->n / 2, s->nb) + 0.5);
+}
+static void rank_rows(int n_ranks, int rank, unsigned n_rows, unsigned& r0, unsigned& r1) {
+    r0 = (unsigned)(((u64)n_rows * rank) / n_ranks);
+    r1 = (unsigned)(((u64)n_rows * (rank + 1)) / n_ranks);
+}
+// row-distributed sector matrix: every rank keeps only its own rows of C (and of Lambda)
+static void alloc_blocked(mqc_solver* s) {
+    unsigned nA, nB, r0, r1;
+    sector_dims(s, nA, nB);
+    rank_rows(s->n_ranks, s->rank, nA, r0, r1);
+    unsigned maxrows = 0;
+    for (int r = 0; r < s->n_ranks; ++r) { unsigned a, b2; rank_rows(s->n_ranks, r, nA, a, b2); maxrows = std::max(maxrows, b2 - a); }
+    CK(cudaSetDevice(s->device));
+    if (!s->cown.p) s->cown.alloc(std::max<u64>(1, (u64)(r1 - r0) * nB));
+    if (!s->cblk.p) s->cblk.alloc(std::max<u64>(1, (u64)maxrows * nB));
+}
+
+static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Cown, const double2* Csrc, double2* Lp,
+                         unsigned nB, unsigned r0, unsigned r1, unsigned src_lo, unsigned src_hi, unsigned own_lo,
+                         unsigned l_lo, int accumulate) {
+    MqcSigmaDev D = SG->dev;
+    D.src_lo = src_lo; D.src_hi = src_hi; D.own_lo = own_lo; D.l_lo = l_lo; D.accumulate = accumulate;
+    const bool stage = s->sigma_stage && (size_t)MQC_SG_LB * nB * sizeof(double2) <= 98304;
+    const size_t smem = mqc_sigma_smem_bytes(D, stage, MQC_SG_LB);
+    dim3 grid(r1 - r0, (nB + MQC_SG_THREADS * MQC_SG_R - 1) / (MQC_SG_THREADS * MQC_SG_R));
+    if (stage) k_sigma<true, MQC_SG_LB><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p());
+    else k_sigma<false, MQC_SG_LB><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p());
+    s->counters[0]++;
+}
+
 static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, bool want_lam) {
     const bool sec = L->conserving && L->use_sector && views[0].ST;
+    const bool blocked = sec && L->blocked;
+    if (blocked) {
+        // Row-distributed C: gather the own rows, then G rounds - round b applies the links whose
+        // source rows belong to rank (rank + b) % G, whose block is copied over NVLink first.
+        for (size_t i = 0; i < L->members.size(); ++i) {
+            const SigmaTables* SG = views[i].SG;
+            if (!SG || !SG->ready || SG->n_fallback)
+                throw MqcError("row-distributed H|psi> needs a Hamiltonian the link tables cover completely (option sigma_blocked=0 replicates C)");
+        }
+        for (mqc_solver* s : L->members) {
+            LayoutTables& Lt = s->lay[which];
+            unsigned nA = (unsigned)Lt.astr.n, nB = (unsigned)Lt.bstr.n, r0, r1;
+            rank_rows(s->n_ranks, s->rank, nA, r0, r1);
+            alloc_blocked(s);
+            if (!s->connected_cown) throw MqcError("row-distributed H|psi>: peers' row blocks are not mapped (set sigma_blocked before mqc_shard_export)");
+            CK(cudaSetDevice(s->device));
+            CK(cudaMemsetAsync(s->scalars_p(), 0, 4 * sizeof(double), s->stream));
+            const u64 cnt = (u64)(r1 - r0) * nB;
+            if (cnt) k_sector_gather<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(peers_of(s), s->cown.p, Lt.astr.p, Lt.bstr.p, r0, r1, nB, r0);
+            if (want_lam) {
+                if (s->lsec.n < std::max<u64>(1, cnt)) s->lsec.alloc(std::max<u64>(1, cnt));
+                CK(cudaMemsetAsync(s->lam.p, 0, sizeof(double2) * s->dim, s->stream));
+            }
+            s->counters[0]++;
+        }
+        group_sync(L);      // every rank's rows are complete
+        for (int b = 0; b < L->n_ranks; ++b) {
+            for (size_t i = 0; i < L->members.size(); ++i) {
+                mqc_solver* s = L->members[i];
+                LayoutTables& Lt = s->lay[which];
+                unsigned nA = (unsigned)Lt.astr.n, nB = (unsigned)Lt.bstr.n, r0, r1, q0, q1;
+                rank_rows(s->n_ranks, s->rank, nA, r0, r1);
+                const int owner = (s->rank + b) % s->n_ranks;
+                rank_rows(s->n_ranks, owner, nA, q0, q1);
+                if (r1 == r0 || q1 == q0) continue;
+                CK(cudaSetDevice(s->device));
+                const double2* src = s->cown.p;
+                if (owner != s->rank) {
+                    CK(cudaMemcpyAsync(s->cblk.p, s->peer_cown[owner], sizeof(double2) * (size_t)(q1 - q0) * nB, cudaMemcpyDeviceToDevice, s->stream));
+                    src = s->cblk.p;
+                }
+                launch_sigma(s, views[i].SG, s->cown.p, src, want_lam ? s->lsec.p : nullptr, nB, r0, r1, q0, q1, r0, r0, b > 0 ? 1 : 0);
+            }
+        }
+        if (want_lam) {
+            group_sync(L);  // all shards of lambda cleared
+            for (mqc_solver* s : L->members) {
+                LayoutTables& Lt = s->lay[which];
+                unsigned nA = (unsigned)Lt.astr.n, nB = (unsigned)Lt.bstr.n, r0, r1;
+                rank_rows(s->n_ranks, s->rank, nA, r0, r1);
+                if (r1 == r0) continue;
+                CK(cudaSetDevice(s->device));
+                const u64 cnt = (u64)(r1 - r0) * nB;
+                k_sector_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(peers_of(s), s->lsec.p, Lt.astr.p, Lt.bstr.p, r0, r1, nB, r0);
+                s->counters[0]++;
+            }
+        }
+        group_sync(L);      // peers are done reading this rank's rows
+        return;
+    }
     for (size_t i = 0; i < L->members.size(); ++i) {
         mqc_solver* s = L->members[i];
         LayoutTables& Lt = s->lay[which];
@@ -716,22 +817,17 @@ static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, 
         if (sec) {
             const unsigned nA = (unsigned)Lt.astr.n, nB = (unsigned)Lt.bstr.n;
             const u64 cnt = (u64)nA * nB;
-            if (s->csec.n < cnt) { s->csec.alloc(cnt); s->lsec.alloc(cnt); }
+            if (s->csec.n < cnt) s->csec.alloc(cnt);
+            if (want_lam && s->lsec.n < cnt) s->lsec.alloc(cnt);
             const unsigned gl = (unsigned)((cnt + 255) / 256);
-            k_sector_gather<<<gl, 256, 0, s->stream>>>(PR, s->csec.p, Lt.astr.p, Lt.bstr.p, 0u, nA, nB);
+            k_sector_gather<<<gl, 256, 0, s->stream>>>(PR, s->csec.p, Lt.astr.p, Lt.bstr.p, 0u, nA, nB, 0u);
             unsigned r0, r1;
             row_slice(s, nA, r0, r1);
             if (r1 > r0) {
                 const SigmaTables* SG = views[i].SG;
                 bool have = false;
                 if (SG && SG->ready) {
-                    MqcSigmaDev D = SG->dev;
-                    const bool stage = s->sigma_stage && (size_t)MQC_SG_LB * nB * sizeof(double2) <= 98304;
-                    const size_t smem = mqc_sigma_smem_bytes(D, stage, MQC_SG_LB);
-                    dim3 grid(r1 - r0, (nB + MQC_SG_THREADS * MQC_SG_R - 1) / (MQC_SG_THREADS * MQC_SG_R));
-                    if (stage) k_sigma<true, MQC_SG_LB><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
-                    else k_sigma<false, MQC_SG_LB><<<grid, MQC_SG_THREADS, smem, s->stream>>>(s->csec.p, want_lam ? s->lsec.p : nullptr, D, s->scalars_p());
-                    s->counters[0]++;
+                    launch_sigma(s, SG, s->csec.p, s->csec.p, want_lam ? s->lsec.p : nullptr, nB, r0, r1, 0u, nA, 0u, 0u, 0);
                     have = true;
                 }
                 if (!have || SG->n_fallback) {
@@ -763,7 +859,7 @@ static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, 
             if (r1 == r0) continue;
             CK(cudaSetDevice(s->device));
             const u64 cnt = (u64)(r1 - r0) * nB;
-            k_sector_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(peers_of(s), s->lsec.p, Lt.astr.p, Lt.bstr.p, r0, r1, nB);
+            k_sector_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(peers_of(s), s->lsec.p, Lt.astr.p, Lt.bstr.p, r0, r1, nB, 0u);
             s->counters[0]++;
         }
     }
@@ -863,7 +959,7 @@ static void connect_group(mqc_solver* L, bool want_lam) {
     bool need = !L->connected;
     for (mqc_solver* s : L->members) if (!s->psi.p || (want_lam && !s->lam.p)) need = true;
     if (!need) return;
-    for (mqc_solver* s : L->members) alloc_state(s, want_lam);
+    for (mqc_solver* s : L->members) { alloc_state(s, want_lam); if (s->blocked) alloc_blocked(s); }
     for (mqc_solver* s : L->members) {
         CK(cudaSetDevice(s->device));
         for (mqc_solver* q : L->members) {
@@ -878,8 +974,10 @@ static void connect_group(mqc_solver* L, bool want_lam) {
             s->peer_psi[q->rank] = q->psi.p;
             s->peer_lam[q->rank] = q->lam.p;
             s->peer_mail[q->rank] = q->mail.p;
+            s->peer_cown[q->rank] = q->cown.p;
         }
         s->connected = true;
+        s->connected_cown = s->blocked;
     }
 }
 
@@ -984,6 +1082,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sparse_threads") s->sparse_threads = (int)value;
     else if (k == "sigma") s->use_sigma = (int)value;
     else if (k == "sigma_stage") s->sigma_stage = (int)value;
+    else if (k == "sigma_blocked") s->sigma_blocked = (int)value;
     else if (k == "sp2") s->sp2 = (int)value;
     else if (k == "sp2_list") s->sp2_list = (int)value;
     else if (k == "sp2_team") { if (value != 0 && value != 1 && value != 2 && value != 4) throw MqcError("sp2_team must be 0 (auto), 1, 2 or 4"); s->sp2_team = (int)value; }
@@ -1071,6 +1170,15 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
     s->na = s->nb = 0;
     for (int q = 0; q < n; ++q)
         if ((ref_index >> (n - 1 - q)) & 1ull) { if (q & 1) s->nb++; else s->na++; }
+    {
+        unsigned nA, nB;
+        sector_dims_pre(s, nA, nB);
+        const double full_c = 16.0 * (double)nA * (double)nB;
+        s->blocked = s->n_ranks > 1 && s->conserving && s->use_sector && s->use_sigma &&
+                     (s->sigma_blocked == 1 || (s->sigma_blocked < 0 && full_c > 24e9));
+        s->connected_cown = false;
+        s->cown.release(); s->cblk.release();
+    }
     for (int w = 0; w < 2; ++w) {
         if (copy_from) s->plan[w] = copy_from->plan[w];
         else if (s->conserving && s->mode == 1) s->plan[w] = mqc_build_sparse_plan(s->sched[w], s->na, s->nb);
@@ -1167,11 +1275,12 @@ int mqc_shard_export(mqc_solver_t* s, int32_t want_lambda, void* blob, int64_t b
     if (s->comm_mode != 2) throw MqcError("not a per-process shard handle (mqc_shard_create with n_ranks > 1)");
     if (!s->have_ansatz) throw MqcError("call mqc_set_ansatz before mqc_shard_export");
     alloc_state(s, want_lambda != 0);
+    if (s->blocked) alloc_blocked(s);
     CK(cudaStreamSynchronize(s->stream));
-    BlobEntry e[3];
+    BlobEntry e[4];
     std::memset(e, 0, sizeof(e));
-    void* ptrs[3] = {s->psi.p, s->lam.p, s->mail.p};
-    for (int i = 0; i < 3; ++i) {
+    void* ptrs[4] = {s->psi.p, s->lam.p, s->mail.p, s->blocked ? s->cown.p : nullptr};
+    for (int i = 0; i < 4; ++i) {
         if (!ptrs[i]) continue;
         void* base; size_t off;
         base_of(ptrs[i], &base, &off);
@@ -1189,11 +1298,11 @@ int mqc_shard_connect(mqc_solver_t* s, const void* blobs, int64_t blobs_bytes) {
     if (s->comm_mode != 2) throw MqcError("not a per-process shard handle");
     if (!blobs || blobs_bytes < (int64_t)MQC_BLOB_BYTES * s->n_ranks) throw MqcError("need one blob per rank");
     for (int r = 0; r < s->n_ranks; ++r) {
-        if (r == s->rank) { s->peer_psi[r] = s->psi.p; s->peer_lam[r] = s->lam.p; s->peer_mail[r] = s->mail.p; continue; }
-        BlobEntry e[3];
+        if (r == s->rank) { s->peer_psi[r] = s->psi.p; s->peer_lam[r] = s->lam.p; s->peer_mail[r] = s->mail.p; s->peer_cown[r] = s->cown.p; continue; }
+        BlobEntry e[4];
         std::memcpy(e, (const char*)blobs + (size_t)r * MQC_BLOB_BYTES, sizeof(e));
-        void* out[3] = {nullptr, nullptr, nullptr};
-        for (int i = 0; i < 3; ++i) {
+        void* out[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int i = 0; i < 4; ++i) {
             if (!e[i].valid) continue;
             const std::string key((const char*)&e[i].h, sizeof(cudaIpcMemHandle_t));
             void* base = nullptr;
@@ -1205,9 +1314,11 @@ int mqc_shard_connect(mqc_solver_t* s, const void* blobs, int64_t blobs_bytes) {
             out[i] = (char*)base + e[i].offset;
         }
         s->peer_psi[r] = (double2*)out[0]; s->peer_lam[r] = (double2*)out[1]; s->peer_mail[r] = (double*)out[2];
-        if (!out[0] || !out[2]) throw MqcError("peer blob is incomplete");
+        s->peer_cown[r] = (double2*)out[3];
+        if (!out[0] || !out[2] || (s->blocked && !out[3])) throw MqcError("peer blob is incomplete");
     }
     s->connected = true;
+    s->connected_cown = s->blocked;
     MQC_CATCH
 }
 

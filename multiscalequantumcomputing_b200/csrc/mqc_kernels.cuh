@@ -922,22 +922,23 @@ struct MqcSecHamDev {
 
 // rows [ia0, ia1) of the sector matrix; the state is read through the peer table, so on a
 // sharded state every rank can assemble whatever rows it needs
+// (C / L hold rows starting at row `buf_row0`)
 __global__ void k_sector_gather(const __grid_constant__ MqcPeers PR, double2* __restrict__ C,
                                 const u64* __restrict__ astr, const u64* __restrict__ bstr,
-                                const unsigned ia0, const unsigned ia1, const unsigned n_b) {
+                                const unsigned ia0, const unsigned ia1, const unsigned n_b, const unsigned buf_row0) {
     const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (u64)(ia1 - ia0) * n_b) return;
     const unsigned ia = ia0 + (unsigned)(tid / n_b), ib = (unsigned)(tid % n_b);
-    C[(u64)ia * n_b + ib] = *peer_psi(PR, astr[ia] | bstr[ib]);
+    C[(u64)(ia - buf_row0) * n_b + ib] = *peer_psi(PR, astr[ia] | bstr[ib]);
 }
 
 __global__ void k_sector_scatter(const __grid_constant__ MqcPeers PR, const double2* __restrict__ L,
                                  const u64* __restrict__ astr, const u64* __restrict__ bstr,
-                                 const unsigned ia0, const unsigned ia1, const unsigned n_b) {
+                                 const unsigned ia0, const unsigned ia1, const unsigned n_b, const unsigned buf_row0) {
     const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (u64)(ia1 - ia0) * n_b) return;
     const unsigned ia = ia0 + (unsigned)(tid / n_b), ib = (unsigned)(tid % n_b);
-    *peer_lam(PR, astr[ia] | bstr[ib]) = L[(u64)ia * n_b + ib];
+    *peer_lam(PR, astr[ia] | bstr[ib]) = L[(u64)(ia - buf_row0) * n_b + ib];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -72,6 +72,11 @@ struct MqcSigmaDev {
     const unsigned* borb;          // [n_b]
     const double* hdiag;           // [rows of this rank][n_b]
     unsigned row0;                 // first row of hdiag / of this launch
+    // Row-distributed sector matrix: the launch applies only the links whose SOURCE row lies in
+    // [src_lo, src_hi) (the block `Csrc` holds, first row src_lo); own rows come from `Cown`
+    // (first row own_lo).  Replicated matrix: one block [0, n_a), all three offsets 0.
+    unsigned src_lo, src_hi, own_lo, l_lo;
+    int accumulate;                // L += instead of L =  (rounds after the first)
 };
 
 // ---- host side -----------------------------------------------------------------------------
@@ -509,9 +514,10 @@ __device__ __forceinline__ double mqc_sg_flip(double w, unsigned s) {      // s 
 // the gathers go to L1/L2 directly.
 template <bool STAGE, int LB>
 __global__ void __launch_bounds__(MQC_SG_THREADS)
-k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_constant__ MqcSigmaDev S,
-        double* __restrict__ e_out) {
+k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, double2* __restrict__ L,
+        const __grid_constant__ MqcSigmaDev S, double* __restrict__ e_out) {
     extern __shared__ __align__(16) unsigned char sg_smem[];
+    const double2* __restrict__ C = Csrc - (size_t)S.src_lo * S.n_b;      // C[src * nB + j] for src in the block
     const unsigned nA = S.n_a, nB = S.n_b;
     const int M2 = S.n_m2 > 0 ? S.n_m2 : 1;
     const int WS = 2 * (S.n_m2 + 1);                               // weight-table stride; last pair = 0 (padding)
@@ -535,7 +541,7 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
     }
 
     // ---- phase 0: beta-only part on the own row ---------------------------------------------
-    {
+    if (i >= S.src_lo && i < S.src_hi) {                          // uniform over the CTA
         const int c0 = __ldg(S.cls_of_m2 + S.n_m2);
         for (int k = tid; k < WS; k += MQC_SG_THREADS) {
             const int ib = k >> 1, pbv = k & 1;
@@ -610,8 +616,8 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
 #pragma unroll
         for (int l = 0; l < LB; ++l) {
             const unsigned ln = __ldg(S.lnk_a1 + (size_t)(l0 + l) * nA + i);
-            ok[l] = ln != MQC_SG_INVALID;
-            src[l] = ok[l] ? (ln & 0xffffu) : i;
+            ok[l] = ln != MQC_SG_INVALID && (ln & 0xffffu) >= S.src_lo && (ln & 0xffffu) < S.src_hi;
+            src[l] = ok[l] ? (ln & 0xffffu) : S.src_lo;
             ia[l] = ok[l] ? ((ln >> 16) & 0xffu) : 0u;
             pav[l] = (ln >> 24) & 1u; sga[l] = (ln >> 25) & 1u;
             zb[l] = __ldg(S.sb_a2 + ia[l]);
@@ -689,6 +695,7 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
             if (l + 1 < S.e2a) lnx = __ldg(S.lnk_a2 + (size_t)(l + 1) * nA + i);
             if (ln == MQC_SG_INVALID) continue;
             const unsigned src = ln & 0xffffu, i4 = (ln >> 16) & 0xfffu, p6 = (ln >> 28) & 7u, sga = ln >> 31;
+            if (src < S.src_lo || src >= S.src_hi) continue;
             const double w = __ldg(S.w4a + (size_t)i4 * 6 + p6);
             const unsigned zb = __ldg(S.sb_a4 + i4);
             const double2* __restrict__ Crow = C + (size_t)src * nB;
@@ -706,9 +713,12 @@ k_sigma(const double2* __restrict__ C, double2* __restrict__ L, const __grid_con
 #pragma unroll
     for (int r = 0; r < MQC_SG_R; ++r) {
         if (jb[r] < nB) {
-            const size_t o = (size_t)i * nB + jb[r];
-            if (L) L[o] = make_double2(ar[r], ai[r]);
-            const double2 py = C[o];
+            if (L) {
+                const size_t o = (size_t)(i - S.l_lo) * nB + jb[r];
+                if (S.accumulate) { const double2 o0 = L[o]; L[o] = make_double2(o0.x + ar[r], o0.y + ai[r]); }
+                else L[o] = make_double2(ar[r], ai[r]);
+            }
+            const double2 py = Cown[(size_t)(i - S.own_lo) * nB + jb[r]];
             er += py.x * ar[r] + py.y * ai[r];
             ei += py.x * ai[r] - py.y * ar[r];
         }

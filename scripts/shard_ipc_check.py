@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-orb", type=int, default=7)
+    ap.add_argument("--blocked", action="store_true", help="row-distributed sector matrix in H|psi>")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -35,6 +36,8 @@ def main():
     h = _lib.ShardRank(2 * n, local, rank, world)
     h.set_option("tile_bits", min(12, 2 * n - 4))
     h.set_option("grad_tile_bits", min(12, 2 * n - 4))
+    if args.blocked:
+        h.set_option("sigma_blocked", 1)
     h.set_hamiltonian(*tab)
     h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
     h.connect(want_lambda=True)

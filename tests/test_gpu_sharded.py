@@ -54,6 +54,9 @@ CASES = [
     (8, 8, 8, "blocked", {}),                                                           # 16 qubits, 13 local bits
     (8, 8, 2, "blocked", {"sparse_tiles": 0}),
     (7, 6, 4, "blocked", {"tile_bits": 9, "grad_tile_bits": 8, "sp2": 0, "sigma": 0}),  # first-generation kernels
+    (7, 6, 4, "blocked", {"tile_bits": 9, "grad_tile_bits": 8, "sigma_blocked": 1}),     # row-distributed sector matrix
+    (8, 8, 8, "blocked", {"sigma_blocked": 1, "sigma_stage": 0}),
+    (6, 4, 2, "lex", {"tile_bits": 8, "grad_tile_bits": 8, "sigma_blocked": 1}),
 ]
 
 
@@ -73,9 +76,10 @@ def test_sharded_state_energy_gradient(n, ne, ranks, order, opts):
     h.close()
 
 
-def test_sharded_rdm_and_expectation():
+@pytest.mark.parametrize("blocked", [0, 1])
+def test_sharded_rdm_and_expectation(blocked):
     n, ne = 6, 6
-    h, orc, F, tab, th = _setup(n, ne, 4, "blocked", {"tile_bits": 8, "grad_tile_bits": 7})
+    h, orc, F, tab, th = _setup(n, ne, 4, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "sigma_blocked": blocked})
     h.prepare(th)
     psi = orc.state(th)
     r1, r2 = h.rdm12(n, ne // 2, ne // 2)
@@ -112,6 +116,7 @@ def test_ipc_ranks_under_torchrun():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29571",
            os.path.join(ROOT, "scripts", "shard_ipc_check.py"), "--n-orb", "7"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "shard ipc ok" in res.stdout
+    for extra in ([], ["--blocked"]):
+        res = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        assert "shard ipc ok" in res.stdout
