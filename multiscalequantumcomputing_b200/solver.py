@@ -48,8 +48,9 @@ class imp_optimizer:
         self.verbose = opt.get("verbose", False)
 
     def check_converged(self, ansatz, result):
-        # a fixed ansatz has nothing to grow: converged once the inner minimisation returns
-        return True
+        # a fixed ansatz has nothing to grow: converged once the inner minimisation returns;
+        # ADAPT: converged when the last update found no pool gradient above its threshold
+        return getattr(ansatz, "converged", True)
 
     def print_info(self, ansatz, result):
         if self.verbose:
@@ -65,9 +66,10 @@ class imp_optimizer:
         result = None
         for niter in range(self._maxiter):
             params = ansatz.update(params, niter)
-            result = minimize(ansatz.energy, params, method=self._method, jac=ansatz.gradient,
-                              options=options, callback=ansatz.callback)
-            params = result["x"]
+            if len(params):
+                result = minimize(ansatz.energy, params, method=self._method, jac=ansatz.gradient,
+                                  options=options, callback=ansatz.callback)
+                params = result["x"]
             converged = self.check_converged(ansatz, result)
             if converged:
                 self.print_info(ansatz, result)
@@ -153,8 +155,18 @@ def solve(oei_mo, one_body_mo, two_body_mo, n_imp: int, n_imp_orbs: int, chempot
     n_qubits = 2 * n_orb
     if verbose:
         print("running %d qubit uccsd calculation" % n_qubits)
-    make = _ansatz_factory or (lambda nq, tab, fac: UCCSDAnsatz(nq, tab, fac, device=device, options=(options or {}).get("gpu")))
-    ansatz = make(n_qubits, prob["table"], factors)
+    kind = (options or {}).get("ansatz", "uccsd")
+    if kind == "adapt":
+        # the reference's default: ADAPT-VQE, Nu operators per macro iteration (dmet_solver_vqechem.py:35-41)
+        from .adapt import ADAPTAnsatz
+        aopt = (options or {}).get("adapt", {})
+        ansatz = ADAPTAnsatz(n_qubits, prob["table"], n_elec, device=device, options=(options or {}).get("gpu"),
+                             nu=aopt.get("nu", 10), eps=aopt.get("eps", 1e-5), max_ops=aopt.get("max_ops", 200),
+                             backend=_ansatz_factory)
+        warm_start = False
+    else:
+        make = _ansatz_factory or (lambda nq, tab, fac: UCCSDAnsatz(nq, tab, fac, device=device, options=(options or {}).get("gpu")))
+        ansatz = make(n_qubits, prob["table"], factors)
     key = (n_orb, n_elec, n_imp_orbs, device)
     if theta0 is None and warm_start and key in _WARM and len(_WARM[key]) == factors.n_theta:
         theta0 = _WARM[key]
@@ -178,7 +190,7 @@ def solve(oei_mo, one_body_mo, two_body_mo, n_imp: int, n_imp_orbs: int, chempot
     if return_details:
         e_bare = ansatz.expectation(prob["table_bare"]).real
         det = SolveDetails(e_imp=e_imp, rdm1=rdm1, rdm2=rdm2, e_uccsd=e_bare, theta=np.array(params),
-                           n_evals=getattr(ansatz, "n_evals", 0), n_theta=factors.n_theta,
+                           n_evals=getattr(ansatz, "n_evals", 0), n_theta=ansatz.get_nparams_opt(),
                            n_terms=len(prob["table"][0]), mo_coeff=prob["C"],
                            t_setup=t1 - t0, t_opt=t2 - t1, t_rdm=t3 - t2)
         if hasattr(ansatz, "close"):

@@ -36,3 +36,33 @@ def test_dmet_with_uccsd_solver_close_to_fci_logs(golden):
     run = DMETRun(ints, atom_clusters(10, 2), solver=lambda *a: solve(*a, **ORACLE), trans_inv=True)
     e = run.run()
     assert abs(e - golden["ring_fci"]["dmet_energy"]) < 2e-4
+
+
+def test_adapt_reaches_fci(golden):
+    """ADAPT-VQE (the reference's default ansatz) driven through the same
+    optimiser loop: pool gradients from one adjoint evaluation of "ansatz + pool at zero angle",
+    energy converges to the logged FCI value of the fragment (test/testlog_fci:8,100)."""
+    ints = local_integrals(hydrogen_ring(10, 1.0))
+    p = fragment_problems(ints, atom_clusters(10, 2), 0.0, True)[0]
+    e_imp, rdm1, det = solve(p.oei, p.fock, p.tei, p.nelec, p.n_imp_orbs, 0.0, return_details=True,
+                             options={"ansatz": "adapt", "adapt": {"nu": 10, "eps": 1e-6}}, **ORACLE)
+    assert abs(det.e_uccsd - golden["ring_fci"]["e_fci"][0]) < 1e-8
+    assert abs(e_imp - golden["ring_fci"]["e_imp"][0]) < 1e-7
+    assert det.n_theta <= 80
+
+
+def test_adapt_pool_gradient_is_the_commutator():
+    """Pool gradient of operator k = dE/dtheta_k at zero angle = finite difference of the energy of
+    the ansatz with that one operator appended."""
+    from multiscalequantumcomputing_b200.adapt import ADAPTAnsatz
+    ints = local_integrals(hydrogen_chain(6, 0.9))
+    p = fragment_problems(ints, atom_clusters(6, 2), 0.0, False)[1]
+    prob = prepare_problem(p.fock, p.tei, p.nelec, p.n_imp_orbs, 0.0)
+    a = ADAPTAnsatz(2 * prob["n_orb"], prob["table"], p.nelec, backend=lambda nq, tab, fac: OracleAnsatz(nq, tab, fac))
+    e0, pg = a.pool_gradients(np.zeros(0))
+    k = int(np.argmax(np.abs(pg)))
+    a.chosen = [k]
+    a._program(a._factors(with_pool=False))
+    d = 1e-5
+    fd = (a.energy(np.array([d])) - a.energy(np.array([-d]))) / (2 * d)
+    assert abs(fd - pg[k]) < 1e-7 and abs(pg[k]) > 1e-3
