@@ -36,7 +36,7 @@ N_ELEC = 12
 BOND = 1.0
 THETA_SEED = 4321
 THETA_SIGMA = 0.05
-BLOCK_ORBS = int(os.environ.get("MQC_BLOCK_ORBS", "6"))
+BLOCK_ORBS = int(os.environ.get("MQC_BLOCK_ORBS", "7"))
 
 
 def workload():

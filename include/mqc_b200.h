@@ -74,7 +74,7 @@ int mqc_shard_read(mqc_solver_t* s, const double* theta, int32_t member, double*
                    int64_t n_amplitudes, int32_t* phys_of_logical);
 
 /* Options (before mqc_set_ansatz): "tile_bits" (default 14; dense tiles are clamped to 13),
- * "low_bits" (3), "grad_tile_bits" (14; dense: 12), "mode" (1 = fused tile sweep, 0 = one
+ * "low_bits" (-1 = automatic: 3 for dense tiles, 0 for sector tiles), "grad_tile_bits" (14; dense: 12), "mode" (1 = fused tile sweep, 0 = one
  * factor per pass), "sp2" (1 = warp-per-tile compressed-sector sweep k_tile_sp2, 0 = first
  * generation), "sp2_warps" (4), "sp2_list" (1 = host-built lists of the non-empty tiles),
  * "sp2_smem_kb" (220), "sigma_stage" (1 = stage source rows of H|psi> in shared memory),

@@ -141,7 +141,7 @@ struct mqc_solver {
     int n_sm = 148, sp2_carveout_set = -1;
 
     // options
-    int tile_bits = 14, low_bits = 3, grad_tile_bits = 14, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
+    int tile_bits = 14, low_bits = -1, grad_tile_bits = 14, mode = 1, use_sector = 1, tile_threads = 256, sparse_tiles = 1, sparse_threads = 128;
 
     DevBuf<double2> psi, lam, cs, scratch_state, csec, lsec, cown, cblk;
     double2* peer_cown[MQC_MAX_RANKS] = {};
@@ -1091,7 +1091,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else throw MqcError("unknown option: " + k);
     if (s->tile_bits < 5 || s->tile_bits > 14 || s->grad_tile_bits < 5 || s->grad_tile_bits > 14)
         throw MqcError("tile_bits and grad_tile_bits must be in [5,14] (dense tiles: <= 13 / 12)");
-    if (s->low_bits < 0 || s->low_bits > 6) throw MqcError("low_bits must be in [0,6]");
+    if (s->low_bits < -1 || s->low_bits > 6) throw MqcError("low_bits must be in [0,6] (-1: 3 for dense tiles, 0 for sector tiles)");
     if (s->tile_threads < 32 || s->tile_threads > 512 || (s->tile_threads & (s->tile_threads - 1)))
         throw MqcError("tile_threads must be a power of two in [32,512]");
     if (s->sparse_threads < 32 || s->sparse_threads > 256 || (s->sparse_threads & (s->sparse_threads - 1)))
@@ -1154,8 +1154,11 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         for (int w = 0; w < 2; ++w) {
             int kb = (w == 0) ? s->tile_bits : s->grad_tile_bits;
             if (!sector_tiles) kb = std::min(kb, 12);
+            // dense tiles want 128-byte runs (3 low bits always active); sector tiles touch
+            // isolated amplitudes anyway and fuse better without the constraint
+            const int lb = s->low_bits >= 0 ? s->low_bits : (sector_tiles ? 0 : 3);
             if (s->mode == 1) {
-                s->sched[w] = mqc_build_schedule(n, kb, s->low_bits, s->fac, MQC_MAX_PASS_FACTORS, s->n_global);
+                s->sched[w] = mqc_build_schedule(n, kb, lb, s->fac, MQC_MAX_PASS_FACTORS, s->n_global);
             } else {
                 s->sched[w] = MqcSchedule();
                 s->sched[w].n_bits = n;

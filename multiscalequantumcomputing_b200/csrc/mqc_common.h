@@ -26,7 +26,7 @@
 typedef unsigned long long u64;
 
 #define MQC_MAX_TILE_BITS 13
-#define MQC_MAX_PASS_FACTORS 160
+#define MQC_MAX_PASS_FACTORS 320
 
 struct MqcFactor {          // one excitation factor in some bit coordinate system
     u64 m;                  // flip mask (2 or 4 bits)

@@ -83,11 +83,11 @@ def _pair_cover(items, size):
     return fam
 
 
-def uccsd_factors(n_orb: int, n_elec: int, order: str = "blocked", block_orbs: int = 6) -> FactorList:
+def uccsd_factors(n_orb: int, n_elec: int, order: str = "blocked", block_orbs: int = 7) -> FactorList:
     """All spin-conserving singles and doubles from the closed-shell reference.
 
-    ``block_orbs``: spatial orbitals per block (occupied + virtual); 6 spatial = 12 qubits
-    matches the 12-bit shared-memory tile of the sweep kernel."""
+    ``block_orbs``: spatial orbitals per block (occupied + virtual); 7 spatial = 14 qubits
+    matches the 14-bit compressed-sector tile of the sweep kernel (6 for 12-bit dense tiles)."""
     nq = 2 * n_orb
     singles, doubles = _all_excitations(n_orb, n_elec)
     if order == "lex":

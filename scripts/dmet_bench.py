@@ -13,6 +13,7 @@ from multiscalequantumcomputing_b200.synth.dmet_loop import DMETRun, atom_cluste
 
 which = sys.argv[1] if len(sys.argv) > 1 else "chain"
 ngpu = int(sys.argv[2]) if len(sys.argv) > 2 else _lib.device_count()
+ansatz = sys.argv[3] if len(sys.argv) > 3 else "uccsd"          # "adapt": the reference's default solver
 geom = hydrogen_chain(10, 0.6) if which == "chain" else hydrogen_ring(12, 1.0)
 n = len(geom)
 ints = local_integrals(geom)
@@ -20,7 +21,8 @@ cl = atom_clusters(n, 2)
 devs = list(range(ngpu))
 for rep in range(3):
     clear_warm_start()
-    run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=devs, warm_start=False))
+    run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=devs, warm_start=False,
+                                                                     options={"ansatz": ansatz, "adapt": {"eps": 1e-6}}))
     t = time.perf_counter(); e = run.run(); dt = time.perf_counter() - t
-    print(json.dumps({"metric": "dmet_iteration_wall_s", "system": which, "fragments": len(cl), "gpus": ngpu,
+    print(json.dumps({"metric": "dmet_iteration_wall_s", "system": which, "fragments": len(cl), "gpus": ngpu, "ansatz": ansatz,
                       "solves": run.n_solves, "mu_steps": len(run.history), "wall_s": dt, "energy": e, "mu": run.mu}), flush=True)
