@@ -513,7 +513,7 @@ __device__ __forceinline__ double mqc_sg_flip(double w, unsigned s) {      // s 
 // STAGE: the source row of C is copied to shared memory per link (rows up to 64 KB); otherwise
 // the gathers go to L1/L2 directly.
 template <bool STAGE, int LB>
-__global__ void __launch_bounds__(MQC_SG_THREADS)
+__global__ void __launch_bounds__(MQC_SG_THREADS, 3)
 k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, double2* __restrict__ L,
         const __grid_constant__ MqcSigmaDev S, double* __restrict__ e_out) {
     extern __shared__ __align__(16) unsigned char sg_smem[];
