@@ -123,7 +123,8 @@ _SEC = None
 
 def cpu_sample(table, factors, theta, n_fac=32, n_terms=1500):
     global _CPU_REF, _SEC
-    from oracle.cref import CRefUCCSD, num_threads
+    from oracle.cref import CRefUCCSD, num_threads, use_all_cores
+    use_all_cores()
     if _CPU_REF is None:
         _CPU_REF = CRefUCCSD(factors.n_qubits, factors.kind, factors.idx, factors.theta_index, factors.n_theta,
                              factors.ref_index, table)
@@ -280,6 +281,8 @@ def run_ours(args):
         # sweeps) measured live on the same workload: 2 S bytes per launch.
         streaming = None
         try:
+            if world > 1:
+                raise RuntimeError("reported at N=1 only")
             hd = _lib.Handle(factors.n_qubits, local)
             hd.set_option("sparse_tiles", 0)
             hd.set_hamiltonian(*table)
@@ -308,11 +311,14 @@ def run_ours(args):
         except Exception as exc:
             streaming = {"unavailable": str(exc)}
         cpu = None
-        try:
-            v, cores, sample = cpu_sample(table, factors, theta)
-            cpu = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample}
-        except Exception as exc:  # the checker could not be built on this box
-            cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % exc}
+        if world > 1:
+            cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "reported at N=1 only"}
+        else:
+            try:
+                v, cores, sample = cpu_sample(table, factors, theta)
+                cpu = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample}
+            except Exception as exc:  # the checker could not be built on this box
+                cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % exc}
         out = {"metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",

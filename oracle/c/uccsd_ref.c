@@ -24,6 +24,14 @@
 typedef double complex cplx;
 typedef uint64_t u64;
 
+void orc_set_num_threads(int n) {          /* torchrun exports OMP_NUM_THREADS=1: the CPU baseline undoes that */
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

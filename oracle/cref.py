@@ -50,6 +50,18 @@ def num_threads():
     return load().orc_num_threads()
 
 
+def use_all_cores():
+    """The CPU baseline uses every host core, also under torchrun (which exports OMP_NUM_THREADS=1)."""
+    import os
+    lib = load()
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    lib.orc_set_num_threads(C.c_int(n))
+    return lib.orc_num_threads()
+
+
 class CRefUCCSD:
     """Same role as oracle.statevector.UCCSDOracle, in C."""
 
