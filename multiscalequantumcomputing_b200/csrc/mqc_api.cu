@@ -150,6 +150,7 @@ struct mqc_solver {
     DevBuf<double> theta, mail, red, rdm_acc;
     DevBuf<int> theta_index, err;
     DevBuf<MqcTileFactor> tf[2];
+    DevBuf<uint16_t> dlut[2];       // pair-address tables of the dense tile kernel
     MqcSparsePlan plan[2];          // compressed-sector tile plan per schedule (host copy of the pass records)
     DevBuf<u64> pl_dep[2], pl_depp[2];
     DevBuf<uint32_t> pl_lists[2];
@@ -662,9 +663,9 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
     const size_t smem = mqc_tile_smem_bytes(P.k, nf, adj, nthr);
     if (smem > 232448) throw MqcError("tile does not fit shared memory; lower tile_bits / grad_tile_bits");
     if (adj)
-        k_tile_sweep<true><<<grid, nthr, smem, s->stream>>>(PR, P, s->tf[which].p, s->cs.p, s->grad_p(), reverse);
+        k_tile_sweep<true><<<grid, nthr, smem, s->stream>>>(PR, P, s->tf[which].p, s->dlut[which].p, s->cs.p, s->grad_p(), reverse);
     else
-        k_tile_sweep<false><<<grid, nthr, smem, s->stream>>>(PR, P, s->tf[which].p, s->cs.p, nullptr, reverse);
+        k_tile_sweep<false><<<grid, nthr, smem, s->stream>>>(PR, P, s->tf[which].p, s->dlut[which].p, s->cs.p, nullptr, reverse);
     s->counters[0]++;
 }
 
@@ -1230,6 +1231,7 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
                 }
             }
             s->tf[w].upload(s->sched[w].tf, s->stream);
+            if (s->mode == 1 && s->sched[w].k <= 13) s->dlut[w].upload(mqc_build_dense_luts(s->sched[w]), s->stream);
             std::vector<int> ph = s->lay[w].phys;
             s->lay[w].phys_dev.upload(ph, s->stream);
         }

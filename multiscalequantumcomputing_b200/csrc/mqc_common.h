@@ -76,6 +76,12 @@ struct MqcSpPass {
 };
 // pair list entry: lo pattern rank (12) | hi pattern rank << 12 | in-tile parity << 24
 
+// bank swizzle of the dense tile (see mqc_kernels.cuh): GF(2)-linear image of the high bits
+#define MQC_SWZ_M0 0x74E8u
+#define MQC_SWZ_M1 0x9D38u
+#define MQC_SWZ_M2 0x3A70u
+#define MQC_LUT_STRIDE 64       // u16 per factor: A[32] B[8] C[8] swz(m) log2(pairs) pad
+
 // insert zero bits at the (ascending) positions pos[0..npos)
 MQC_HD u64 mqc_insert_zeros(u64 u, const int32_t* pos, int npos) {
     for (int i = 0; i < npos; ++i) {

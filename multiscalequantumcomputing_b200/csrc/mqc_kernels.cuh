@@ -117,9 +117,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // columns are successive powers of a primitive element of GF(8) (1,2,4,3,6,7,5,...): any
 // three consecutive bit positions - and most other triples - map to independent vectors,
 // i.e. eight distinct bank groups.  Linear, so swz(x ^ m) = swz(x) ^ swz(m).
-#define MQC_SWZ_M0 0x74E8u
-#define MQC_SWZ_M1 0x9D38u
-#define MQC_SWZ_M2 0x3A70u
 __device__ __forceinline__ uint32_t swz(uint32_t t) {
     return t ^ ((uint32_t)__popc(t & MQC_SWZ_M0) & 1u) ^ (((uint32_t)__popc(t & MQC_SWZ_M1) & 1u) << 1) ^
            (((uint32_t)__popc(t & MQC_SWZ_M2) & 1u) << 2);
@@ -603,16 +600,16 @@ static inline size_t mqc_sparse_smem_bytes(int K, int cap, bool adj) {
 // Per-factor pair addressing.  For a factor with flip mask m the lower partner of pair u is
 //   xl(u) = ins(u) | v      (u with zero bits inserted at the positions of m)
 // and both ins() and the bank swizzle are GF(2)-linear, as is the parity popc(xl & z).  So
-//   [ swz(xl(u)) | sign(u) << 15 ] = A[u & 31] ^ B[(u >> 5) & 7] ^ C[u >> 8]
-// with three tiny tables per factor (48 x u16) that fold in v and the per-tile sign.  They are
-// rebuilt per chunk of MQC_FCHUNK factors, which costs ~6 instructions per factor and thread
-// and replaces ~100 instructions of per-pair bit arithmetic.
-#define MQC_LUT_PER_FACTOR 48
-
+//   [ swz(xl(u)) | parity(u) << 15 ] = A[u & 31] ^ B[(u >> 5) & 7] ^ C[u >> 8]
+// with three tiny tables per factor (48 x u16; v folded into A).  They do not depend on the
+// tile, so the HOST builds them once per schedule (mqc_build_dense_luts, 128 bytes per factor,
+// entries 48 / 49: swz(m) and log2(#pairs)) and a CTA only copies the chunk's tables; the
+// per-tile Jordan-Wigner sign goes into the sign of sin(theta) instead.  A thread's A and B
+// entries are loop invariants (u & 31 = lane, (u >> 5) & 7 = warp & 7 for 256 / 512 threads).
 template <bool ADJ>
 __global__ void __launch_bounds__(512)
 k_tile_sweep(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass P,
-             const MqcTileFactor* __restrict__ tf, const double2* __restrict__ cs,
+             const MqcTileFactor* __restrict__ tf, const uint16_t* __restrict__ lutg, const double2* __restrict__ cs,
              double* __restrict__ grad, const int reverse) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = P.k;
@@ -630,11 +627,11 @@ k_tile_sweep(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPas
     double2* scs = reinterpret_cast<double2*>(q);       q += MQC_FCHUNK * sizeof(double2);
     double* gpart = reinterpret_cast<double*>(q);       q += (ADJ ? 16 * MQC_FCHUNK : 0) * sizeof(double);
     int* stheta = reinterpret_cast<int*>(q);            q += MQC_FCHUNK * sizeof(int);
-    uint16_t* slut = reinterpret_cast<uint16_t*>(q);    q += MQC_FCHUNK * MQC_LUT_PER_FACTOR * sizeof(uint16_t);
-    uint16_t* sswm = reinterpret_cast<uint16_t*>(q);    q += MQC_FCHUNK * sizeof(uint16_t);
-    uint16_t* slg = reinterpret_cast<uint16_t*>(q);     q += MQC_FCHUNK * sizeof(uint16_t);
-    uint16_t* prm_lo = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);
-    uint16_t* prm_hi = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);
+    uint16_t* slut = reinterpret_cast<uint16_t*>(q);    q += MQC_FCHUNK * MQC_LUT_STRIDE * sizeof(uint16_t);
+    uint16_t* swl_lo = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);     // swizzled slot of an element
+    uint16_t* swl_hi = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);     //   in the load layout,
+    uint16_t* sws_lo = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);     //   in the store layout
+    uint16_t* sws_hi = reinterpret_cast<uint16_t*>(q);  q += 128 * sizeof(uint16_t);
     int* spos = reinterpret_cast<int*>(q);              q += 16 * sizeof(int);
     int* sperm = reinterpret_cast<int*>(q);             q += 16 * sizeof(int);
 
@@ -646,26 +643,31 @@ k_tile_sweep(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPas
         spos[tid] = pv; sperm[tid] = qv;
     }
     __syncthreads();
+    // the tile is held in the forward pass's LOAD layout in both directions; the other layout's
+    // index of element t is perm(t); the swizzle is linear, so both split into low / high halves
+    const bool perm_load = reverse && P.has_perm;
+    const bool perm_store = (!reverse) && P.has_perm;
     for (int t = tid; t < (1 << h0); t += nthr) {
         u64 d = 0; uint32_t pm = 0;
-        for (int j = 0; j < h0; ++j) { const u64 b = ((u64)t >> j) & 1ull; d |= b << spos[j]; pm |= (uint32_t)b << sperm[j]; }
-        dep_lo[t] = d; prm_lo[t] = (uint16_t)pm;
+        for (int j = 0; j < h0; ++j) { const u64 bb = ((u64)t >> j) & 1ull; d |= bb << spos[j]; pm |= (uint32_t)bb << sperm[j]; }
+        dep_lo[t] = d;
+        swl_lo[t] = (uint16_t)swz(perm_load ? pm : (uint32_t)t);
+        sws_lo[t] = (uint16_t)swz(perm_store ? pm : (uint32_t)t);
     }
     for (int t = tid; t < (1 << h1); t += nthr) {
         u64 d = 0; uint32_t pm = 0;
-        for (int j = 0; j < h1; ++j) { const u64 b = ((u64)t >> j) & 1ull; d |= b << spos[h0 + j]; pm |= (uint32_t)b << sperm[h0 + j]; }
-        dep_hi[t] = d; prm_hi[t] = (uint16_t)pm;
+        for (int j = 0; j < h1; ++j) { const u64 bb = ((u64)t >> j) & 1ull; d |= bb << spos[h0 + j]; pm |= (uint32_t)bb << sperm[h0 + j]; }
+        dep_hi[t] = d;
+        swl_hi[t] = (uint16_t)swz(perm_load ? pm : ((uint32_t)t << h0));
+        sws_hi[t] = (uint16_t)swz(perm_store ? pm : ((uint32_t)t << h0));
     }
     const u64 base = mqc_deposit_complement((u64)blockIdx.x | PR.tau_hi, P.act_mask, PR.n_local) | PR.fixed_bits;
     __syncthreads();
 
     // ---- load (cp.async: whole tile in flight, no register staging) -------------------
-    const bool perm_load = reverse && P.has_perm;
-    const bool perm_store = (!reverse) && P.has_perm;
     for (uint32_t t = tid; t < T; t += nthr) {
         const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
-        const uint32_t st = perm_load ? (uint32_t)(prm_lo[t & lo_mask] | prm_hi[t >> h0]) : t;
-        const uint32_t sw = swz(st);
+        const uint32_t sw = (uint32_t)swl_lo[t & lo_mask] ^ (uint32_t)swl_hi[t >> h0];
         cp_async16(sp + sw, peer_psi(PR, g));
         if (ADJ) cp_async16(sl + sw, peer_lam(PR, g));
     }
@@ -673,74 +675,52 @@ k_tile_sweep(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPas
     // ---- factors, in chunks ---------------------------------------------------------
     const int warp = tid >> 5, lane = tid & 31;
     const int nw = nthr >> 5;
+    const bool fixed_b = (nthr & 255) == 0;                 // (u >> 5) & 7 does not change along a thread's pairs
     for (int c0 = 0; c0 < nf; c0 += MQC_FCHUNK) {
         const int nc = min(MQC_FCHUNK, nf - c0);
-        // chunk tables: entry e of factor fc;  e < 32: A, 32..39: B, 40..47: C
-        for (int w = tid; w < nc * MQC_LUT_PER_FACTOR; w += nthr) {
-            const int fc = w / MQC_LUT_PER_FACTOR, e = w - fc * MQC_LUT_PER_FACTOR;
+        // chunk tables: 64 u16 per factor, copied as 32 words
+        for (int w = tid; w < nc * (MQC_LUT_STRIDE / 2); w += nthr) {
+            const int fc = w >> 5, e = w & 31;
             const int f = reverse ? (nf - 1 - (c0 + fc)) : (c0 + fc);
-            const MqcTileFactor* Fp = tf + P.f0 + f;
-            const uint32_t npos = Fp->npos;
-            const uint32_t pos4 = *reinterpret_cast<const uint32_t*>(Fp->pos);
-            const uint32_t up = (e < 32) ? (uint32_t)e : (e < 40 ? (uint32_t)(e - 32) << 5 : (uint32_t)(e - 40) << 8);
-            uint32_t xl = ins0(ins0(up, pos4 & 0xffu), (pos4 >> 8) & 0xffu);
-            if (npos == 4) xl = ins0(ins0(xl, (pos4 >> 16) & 0xffu), pos4 >> 24);
-            const uint32_t fz = Fp->z;
-            uint32_t val = 0;
-            if (xl < T) val = swz(xl) | (((uint32_t)__popc(xl & fz) & 1u) << 15);
-            if (e < 32) {                                       // v and the per-tile sign ride on table A
-                const uint32_t fv = Fp->v;
-                const uint32_t sg = ((uint32_t)__popc(fv & fz) + (uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;
-                val ^= swz(fv) | (sg << 15);
-            }
-            slut[w] = (uint16_t)val;
+            reinterpret_cast<uint32_t*>(slut)[w] = __ldg(reinterpret_cast<const uint32_t*>(lutg) + (size_t)(P.f0 + f) * (MQC_LUT_STRIDE / 2) + e);
         }
         for (int fc = tid; fc < nc; fc += nthr) {
             const int f = reverse ? (nf - 1 - (c0 + fc)) : (c0 + fc);
             const MqcTileFactor* Fp = tf + P.f0 + f;
             const double2 v = cs[Fp->slot];
-            scs[fc] = make_double2(v.x, reverse ? -v.y : v.y);
-            sswm[fc] = (uint16_t)swz(Fp->m);
-            slg[fc] = (uint16_t)(K - Fp->npos);
-            stheta[fc] = Fp->theta;
+            const uint32_t sg = ((uint32_t)__popcll(base & Fp->z_out) + Fp->sign0) & 1u;   // per-tile JW sign
+            const double sn = reverse ? -v.y : v.y;
+            scs[fc] = make_double2(v.x, sg ? -sn : sn);
+            stheta[fc] = Fp->theta | (int)(sg << 30);       // the gradient needs the sign once more
         }
         if (c0 == 0) cp_async_wait_all();
         __syncthreads();
 
         for (int fc = 0; fc < nc; ++fc) {
-            const uint16_t* lut = slut + fc * MQC_LUT_PER_FACTOR;
-            const uint32_t swm = sswm[fc];
-            const uint32_t npairs = 1u << slg[fc];
+            const uint16_t* lut = slut + fc * MQC_LUT_STRIDE;
+            const uint32_t swm = lut[48];
+            const uint32_t npairs = 1u << lut[49];
             const double2 csv = scs[fc];
             const double c = csv.x, sn = csv.y;
+            const uint32_t vab = (uint32_t)lut[lane] ^ (fixed_b ? (uint32_t)lut[32 + (warp & 7)] : 0u);
             double gacc = 0.0;
             for (uint32_t u = tid; u < npairs; u += nthr) {
-                const uint32_t val = (uint32_t)lut[u & 31u] ^ (uint32_t)lut[32u + ((u >> 5) & 7u)] ^ (uint32_t)lut[40u + (u >> 8)];
+                uint32_t val = vab ^ (uint32_t)lut[40u + (u >> 8)];
+                if (!fixed_b) val ^= (uint32_t)lut[32u + ((u >> 5) & 7u)];
                 const uint32_t x0 = val & 0x7fffu;
                 const uint32_t x1 = x0 ^ swm;
                 const bool neg = (val & 0x8000u) != 0u;
+                const double ssn = neg ? -sn : sn;
                 const double2 a = sp[x0], b = sp[x1];
                 if (ADJ) {
                     const double2 la = sl[x0], lb = sl[x1];
-                    const bool nz = (a.x != 0.0) | (a.y != 0.0) | (b.x != 0.0) | (b.y != 0.0) |
-                                    (la.x != 0.0) | (la.y != 0.0) | (lb.x != 0.0) | (lb.y != 0.0);
-                    if (nz) {
-                        const double ssn = neg ? -sn : sn;
-                        const double gv = lb.x * a.x + lb.y * a.y - la.x * b.x - la.y * b.y;
-                        gacc += neg ? -gv : gv;
-                        sl[x0] = make_double2(c * la.x - ssn * lb.x, c * la.y - ssn * lb.y);
-                        sl[x1] = make_double2(c * lb.x + ssn * la.x, c * lb.y + ssn * la.y);
-                        sp[x0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
-                        sp[x1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
-                    }
-                } else {
-                    const bool nz = (a.x != 0.0) | (a.y != 0.0) | (b.x != 0.0) | (b.y != 0.0);
-                    if (nz) {
-                        const double ssn = neg ? -sn : sn;
-                        sp[x0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
-                        sp[x1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
-                    }
+                    const double gv = lb.x * a.x + lb.y * a.y - la.x * b.x - la.y * b.y;
+                    gacc += neg ? -gv : gv;
+                    sl[x0] = make_double2(c * la.x - ssn * lb.x, c * la.y - ssn * lb.y);
+                    sl[x1] = make_double2(c * lb.x + ssn * la.x, c * lb.y + ssn * la.y);
                 }
+                sp[x0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
+                sp[x1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
             }
             if (ADJ) {
                 gacc = warp_sum(gacc);
@@ -752,7 +732,8 @@ k_tile_sweep(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPas
             for (int fc = tid; fc < nc; fc += nthr) {
                 double g = 0.0;
                 for (int w = 0; w < nw; ++w) g += gpart[w * MQC_FCHUNK + fc];
-                if (g != 0.0) atomicAdd(grad + stheta[fc], 2.0 * g);
+                const int th = stheta[fc];
+                if (g != 0.0) atomicAdd(grad + (th & 0x3fffffff), (th >> 30) & 1 ? -2.0 * g : 2.0 * g);
             }
             __syncthreads();
         }
@@ -762,8 +743,7 @@ k_tile_sweep(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPas
     // ---- store ----------------------------------------------------------------------
     for (uint32_t t = tid; t < T; t += nthr) {
         const u64 g = base | dep_lo[t & lo_mask] | dep_hi[t >> h0];
-        const uint32_t st = perm_store ? (uint32_t)(prm_lo[t & lo_mask] | prm_hi[t >> h0]) : t;
-        const uint32_t sw = swz(st);
+        const uint32_t sw = (uint32_t)sws_lo[t & lo_mask] ^ (uint32_t)sws_hi[t >> h0];
         st_stream(peer_psi(PR, g), sp[sw]);
         if (ADJ) st_stream(peer_lam(PR, g), sl[sw]);
     }
@@ -776,9 +756,8 @@ static inline size_t mqc_tile_smem_bytes(int K, int nf, bool adj, int nthreads) 
     b += MQC_FCHUNK * sizeof(double2);
     if (adj) b += 16 * MQC_FCHUNK * sizeof(double);
     b += MQC_FCHUNK * sizeof(int);
-    b += MQC_FCHUNK * MQC_LUT_PER_FACTOR * sizeof(uint16_t);
-    b += 2 * MQC_FCHUNK * sizeof(uint16_t);
-    b += 2 * 128 * sizeof(uint16_t) + 32 * sizeof(int);
+    b += MQC_FCHUNK * MQC_LUT_STRIDE * sizeof(uint16_t);
+    b += 4 * 128 * sizeof(uint16_t) + 32 * sizeof(int);
     return b;
 }
 

@@ -464,3 +464,32 @@ static inline MqcTileLists mqc_build_tile_lists(const MqcSchedule& S, const MqcS
     TL.ok = true;
     return TL;
 }
+
+// ---------------------------------------------------------------------------------------------
+// pair-address tables of the dense tile kernel (k_tile_sweep), one 64-entry row per tile factor
+// ---------------------------------------------------------------------------------------------
+static inline uint32_t mqc_swz_host(uint32_t t) {
+    return t ^ ((uint32_t)__builtin_popcount(t & MQC_SWZ_M0) & 1u) ^ (((uint32_t)__builtin_popcount(t & MQC_SWZ_M1) & 1u) << 1) ^
+           (((uint32_t)__builtin_popcount(t & MQC_SWZ_M2) & 1u) << 2);
+}
+static inline std::vector<uint16_t> mqc_build_dense_luts(const MqcSchedule& S) {
+    std::vector<uint16_t> L(std::max<size_t>(1, S.tf.size()) * MQC_LUT_STRIDE, 0);
+    const uint32_t T = 1u << S.k;
+    auto ins0 = [](uint32_t x, uint32_t p) { return ((x >> p) << (p + 1)) | (x & ((1u << p) - 1u)); };
+    for (size_t i = 0; i < S.tf.size(); ++i) {
+        const MqcTileFactor& F = S.tf[i];
+        uint16_t* row = &L[i * MQC_LUT_STRIDE];
+        for (int e = 0; e < 48; ++e) {
+            const uint32_t up = (e < 32) ? (uint32_t)e : (e < 40 ? (uint32_t)(e - 32) << 5 : (uint32_t)(e - 40) << 8);
+            uint32_t xl = up;
+            for (int k = 0; k < F.npos; ++k) xl = ins0(xl, F.pos[k]);
+            uint32_t val = 0;
+            if (xl < T) val = mqc_swz_host(xl) | (((uint32_t)__builtin_popcount(xl & F.z) & 1u) << 15);
+            if (e < 32) val ^= mqc_swz_host(F.v) | (((uint32_t)__builtin_popcount(F.v & F.z) & 1u) << 15);   // v rides on table A
+            row[e] = (uint16_t)val;
+        }
+        row[48] = (uint16_t)mqc_swz_host(F.m);
+        row[49] = (uint16_t)(S.k - F.npos);
+    }
+    return L;
+}
