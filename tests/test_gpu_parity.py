@@ -198,3 +198,48 @@ def test_dmet_with_adapt_matches_reference_fci_log(golden):
                   solver=lambda *a: solve(*a, warm_start=False, options={"ansatz": "adapt", "adapt": {"eps": 1e-6}}))
     e = run.run()
     assert abs(e - golden["ring_fci"]["dmet_energy"]) < 1e-6
+
+
+def test_properties_24_qubits_full_size():
+    """BASELINE.json configs[2] at its full size (24 qubits, 1 818 parameters), where no CPU oracle
+    finishes in seconds: size-independent properties.  Norm 1; gradient = central finite differences
+    of the energy; sector-tile path = dense-tile path = 4-rank sharded state; RDM traces; and the
+    energy contracted from the 1-/2-RDMs (K4) equals <H> from the Pauli-term kernel (K2)."""
+    from multiscalequantumcomputing_b200.synth.hydrogen import mo_integrals
+    n, ne = 12, 12
+    h_mo, eri_mo, e_nuc, e_rhf = mo_integrals(hydrogen_chain(n, 1.0), ne)
+    tab = fragment_term_table(h_mo, eri_mo, 0, 0.0, 0.25)
+    bare = fragment_term_table(h_mo, eri_mo, 0, 0.0, 0.0)
+    F = uccsd_factors(n, ne, "blocked")
+    th = np.random.default_rng(4321).normal(0, 0.05, F.n_theta)
+    h = _lib.Handle(2 * n)
+    h.set_hamiltonian(*tab)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    e, g = h.energy_grad(th)
+    ident = (np.zeros(1, np.uint64), np.zeros(1, np.uint64), np.ones(1))
+    assert abs(h.expectation(*ident).real - 1.0) < 1e-12
+    for k in (0, 911, F.n_theta - 1):
+        d = np.zeros_like(th); d[k] = 1e-4
+        fd = (h.energy(th + d) - h.energy(th - d)) / 2e-4
+        assert abs(fd - g[k]) < 2e-7
+    # K4 against K2
+    h.prepare(th)
+    e_bare = h.expectation(*bare).real
+    r1, r2 = h.rdm12(n, ne // 2, ne // 2)
+    assert abs(np.trace(r1) - ne) < 1e-10 and abs(np.einsum("iijj->", r2) - ne * (ne - 1)) < 1e-8
+    e_rdm = np.einsum("pq,pq->", h_mo, r1) + 0.5 * np.einsum("pqrs,pqrs->", eri_mo, r2)
+    assert abs(e_rdm - e_bare) < 1e-9
+    # other execution paths of the same evaluation
+    hd = _lib.Handle(2 * n)
+    hd.set_option("sparse_tiles", 0)
+    hd.set_hamiltonian(*tab)
+    hd.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    ed, gd = hd.energy_grad(th)
+    assert abs(ed - e) < E_TOL and abs(gd - g).max() < G_TOL
+    hd.close()
+    hs = _lib.ShardGroup(2 * n, [0, 0, 0, 0])
+    hs.set_hamiltonian(*tab)
+    hs.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    es, gs = hs.energy_grad(th)
+    assert abs(es - e) < E_TOL and abs(gs - g).max() < G_TOL
+    hs.close(); h.close()
