@@ -77,7 +77,9 @@ int mqc_shard_read(mqc_solver_t* s, const double* theta, int32_t member, double*
  * "low_bits" (-1 = automatic: 3 for dense tiles, 0 for sector tiles), "grad_tile_bits" (14; dense: 12), "mode" (1 = fused tile sweep, 0 = one
  * factor per pass), "sp2" (1 = warp-per-tile compressed-sector sweep k_tile_sp2, 0 = first
  * generation), "sp2_warps" (4), "sp2_list" (1 = host-built lists of the non-empty tiles),
- * "sp2_smem_kb" (220), "sigma_stage" (1 = stage source rows of H|psi> in shared memory),
+ * "sp2_smem_kb" (220), "sp2_team" (0 = automatic warps per tile), "sigma_stage" (1 = stage source
+ * rows of H|psi> in shared memory), "sigma_blocked" (-1 = automatic, 1 = row-distributed sector
+ * matrix on sharded states), "graph" (1 = replay evaluations as CUDA graphs on single-rank handles),
  * "sector" (1 = exploit particle-number/S_z conservation of the ansatz in H|psi>),
  * "sparse_tiles" (1 = compressed-sector tiles when the ansatz conserves N_alpha, N_beta),
  * "tile_threads" (256), "sparse_threads" (128), "sigma" (1 = link-table kernel for the sector

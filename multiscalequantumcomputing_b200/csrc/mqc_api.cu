@@ -166,6 +166,14 @@ struct mqc_solver {
     HamHost ham, ham_fb;            // all terms / the terms the link-table kernel leaves to k_happly_sector
     SigmaTables sig;
     int use_sigma = 1, sigma_stage = 1;
+    // The launch sequence of an evaluation depends on theta only through device buffers, so a
+    // single-rank handle replays it as a CUDA graph from the third call on (first call: eager,
+    // allocates; second: captured).  Any change of tables or options drops the graphs.
+    int use_graph = 1;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int eager_done[2] = {0, 0};
+    int64_t gcounters[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    bool capturing = false;
     bool have_ham = false, have_ansatz = false;
 
     std::vector<MqcFactor> fac;     // logical coordinates
@@ -183,6 +191,8 @@ struct mqc_solver {
     double ms[4] = {0, 0, 0, 0};
     int64_t counters[3] = {0, 0, 0};
 };
+
+static void invalidate_graphs(mqc_solver* s);
 
 // ---------------------------------------------------------------------------------------
 // host helpers
@@ -323,6 +333,7 @@ static void enum_strings(int n_orb, int k, int spin, int n, const std::vector<in
 
 static void build_sector_tables(mqc_solver* s, LayoutTables& L, int na, int nb) {
     if (L.na == na && L.nb == nb && L.astr.p) return;
+    invalidate_graphs(s);               // device tables move
     const int n = s->n, n_orb = n / 2;
     std::vector<u64> a, b;
     std::vector<unsigned> ao, bo, ra, rb;
@@ -525,14 +536,15 @@ static void ensure_layout_ready(mqc_solver* s, int which) {
     LayoutTables& L = s->lay[which];
     if (!s->have_ham) throw MqcError("mqc_set_hamiltonian has not been called");
     if (!L.ham_ready && !(s->conserving && s->use_sector)) {
+        invalidate_graphs(s);
         build_ham_tables(s, s->ham, L.phys, L.ham);
         L.ham_ready = true;
     }
     if (s->conserving && s->use_sector) {
         build_sector_tables(s, L, s->na, s->nb);
         const bool sigma = s->use_sigma && s->n / 2 <= 18;
-        if (sigma && !s->sig.ready) build_sigma(s, s->ham, s->na, s->nb, s->sig, s->ham_fb);
-        if (!L.sham_ready) { build_sec_ham(s, sigma ? s->ham_fb : s->ham, L.phys, L.sham); L.sham_ready = true; }
+        if (sigma && !s->sig.ready) { invalidate_graphs(s); build_sigma(s, s->ham, s->na, s->nb, s->sig, s->ham_fb); }
+        if (!L.sham_ready) { invalidate_graphs(s); build_sec_ham(s, sigma ? s->ham_fb : s->ham, L.phys, L.sham); L.sham_ready = true; }
     }
 }
 
@@ -542,6 +554,18 @@ static void ensure_layout_ready(mqc_solver* s, int which) {
 // Per-rank work is launched rank by rank on each rank's own stream; group_sync() orders the
 // ranks wherever one reads or writes another's shard.
 // ---------------------------------------------------------------------------------------
+static void invalidate_graphs(mqc_solver* s) {
+    for (int w = 0; w < 2; ++w) {
+        if (s->gexec[w]) { cudaGraphExecDestroy(s->gexec[w]); s->gexec[w] = nullptr; }
+        s->eager_done[w] = 0;
+    }
+}
+static void record_ev(mqc_solver* s, int i) {
+    CK(cudaSetDevice(s->device));
+    if (s->capturing) CK(cudaEventRecordWithFlags(s->ev[i], s->stream, cudaEventRecordExternal));
+    else CK(cudaEventRecord(s->ev[i], s->stream));
+}
+
 static double binom(int n, int k) {
     if (k < 0 || k > n) return 0.0;
     double r = 1.0;
@@ -1055,6 +1079,7 @@ static void destroy_rank(mqc_solver* s) {
         for (auto& e : s->ev) if (e) cudaEventDestroy(e);
         for (auto& e : s->user_ev) if (e) cudaEventDestroy(e);
         if (s->sync_ev) cudaEventDestroy(s->sync_ev);
+        invalidate_graphs(s);
         for (auto& kv : s->ipc_open) cudaIpcCloseMemHandle(kv.second);
     }
     cudaStream_t st = s->stream;
@@ -1083,6 +1108,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sparse_threads") s->sparse_threads = (int)value;
     else if (k == "sigma") s->use_sigma = (int)value;
     else if (k == "sigma_stage") s->sigma_stage = (int)value;
+    else if (k == "graph") s->use_graph = (int)value;
     else if (k == "sigma_blocked") s->sigma_blocked = (int)value;
     else if (k == "sp2") s->sp2 = (int)value;
     else if (k == "sp2_list") s->sp2_list = (int)value;
@@ -1102,7 +1128,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
 int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value) {
     MQC_TRY
     if (!s || !key) throw MqcError("null argument");
-    for (mqc_solver* m : s->members) set_option_rank(m, key, value);
+    for (mqc_solver* m : s->members) { invalidate_graphs(m); set_option_rank(m, key, value); }
     MQC_CATCH
 }
 
@@ -1122,6 +1148,7 @@ int mqc_set_hamiltonian(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask,
         s->lay[0].ham_ready = s->lay[1].ham_ready = false;
         s->lay[0].sham_ready = s->lay[1].sham_ready = false;
         s->sig.ready = false;
+        invalidate_graphs(s);
     }
     MQC_CATCH
 }
@@ -1195,6 +1222,7 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
     s->have_ansatz = true;
     s->state_layout = -1;
     s->sig.ready = false;
+    invalidate_graphs(s);
     s->connected = (s->n_ranks == 1);
     // device side is set up lazily so that schedules can be inspected without a GPU
     int cnt = 0;
@@ -1348,6 +1376,62 @@ int mqc_prepare(mqc_solver_t* s, const double* theta) {
     MQC_CATCH
 }
 
+// The launch sequence of one evaluation (which = 0: energy, 1: energy + adjoint gradient) on
+// the handle's stream(s), with the phase events.  theta == NULL: parameters already on the device.
+static void evaluation_body(mqc_solver* s, int which, const double* theta) {
+    record_ev(s, 0);
+    forward(s, which, theta);
+    record_ev(s, 1);
+    happly(s, which, own_views(s, which), which == 1);
+    if (which == 0) reduce_mail(s, 4);
+    record_ev(s, 2);
+    if (which == 1) {
+        reverse_sweep(s, which);
+        reduce_mail(s, MQC_MAIL_GRAD + s->n_theta);
+        record_ev(s, 3);
+    }
+}
+
+static void run_evaluation(mqc_solver* s, int which, const double* theta) {
+    const bool graphable = s->use_graph && s->n_ranks == 1 && s->mode == 1;
+    if (!graphable) { evaluation_body(s, which, theta); return; }
+    CK(cudaSetDevice(s->device));
+    if (theta) {
+        s->theta_host.assign(theta, theta + s->n_theta);
+        CK(cudaMemcpyAsync(s->theta.p, s->theta_host.data(), sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
+    }
+    if (s->gexec[which]) {
+        CK(cudaGraphLaunch(s->gexec[which], s->stream));
+        for (int i = 0; i < 3; ++i) s->counters[i] = s->gcounters[which][i];
+        for (mqc_solver* m : s->members) m->state_layout = which == 1 ? -1 : which;
+        return;
+    }
+    if (!s->eager_done[which]) {                  // first call: allocates its work buffers
+        evaluation_body(s, which, nullptr);
+        s->eager_done[which] = 1;
+        return;
+    }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    s->capturing = true;
+    try {
+        evaluation_body(s, which, nullptr);
+    } catch (...) {
+        s->capturing = false;
+        cudaStreamEndCapture(s->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        throw;
+    }
+    s->capturing = false;
+    CK(cudaStreamEndCapture(s->stream, &graph));
+    for (int i = 0; i < 3; ++i) s->gcounters[which][i] = s->counters[i];
+    const cudaError_t e = cudaGraphInstantiate(&s->gexec[which], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { s->gexec[which] = nullptr; cuda_check(e, "cudaGraphInstantiate"); }
+    CK(cudaGraphLaunch(s->gexec[which], s->stream));
+}
+
 int mqc_energy(mqc_solver_t* s, const double* theta, double* energy) {
     MQC_TRY
     require_gpu(s);
@@ -1356,15 +1440,8 @@ int mqc_energy(mqc_solver_t* s, const double* theta, double* energy) {
     connect_group(s, false);
     for (mqc_solver* m : s->members) ensure_layout_ready(m, 0);
     double val[2] = {0, 0};
+    run_evaluation(s, 0, theta);
     CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev[0], s->stream));
-    forward(s, 0, theta);
-    CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev[1], s->stream));
-    happly(s, 0, own_views(s, 0), false);
-    reduce_mail(s, 4);
-    CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev[2], s->stream));
     CK(cudaMemcpyAsync(val, reduced_scalars(s), 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     sync_all(s);
     finish_timing(s, false);
@@ -1375,20 +1452,10 @@ int mqc_energy(mqc_solver_t* s, const double* theta, double* energy) {
 static void run_energy_grad(mqc_solver* s, const double* theta, double* energy, double* grad) {
     reset_counters(s);
     connect_group(s, true);
-    for (mqc_solver* m : s->members) { ensure_layout_ready(m, 1); if (!m->lam.p) { if (m->n_ranks > 1) throw MqcError("sharded handle was exported without lambda"); alloc_state(m, true); } }
+    for (mqc_solver* m : s->members) { ensure_layout_ready(m, 1); if (!m->lam.p) { if (m->n_ranks > 1) throw MqcError("sharded handle was exported without lambda"); invalidate_graphs(m); alloc_state(m, true); } }
     double val[2] = {0, 0};
+    run_evaluation(s, 1, theta);
     CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev[0], s->stream));
-    forward(s, 1, theta);
-    CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev[1], s->stream));
-    happly(s, 1, own_views(s, 1), true);
-    CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev[2], s->stream));
-    reverse_sweep(s, 1);
-    reduce_mail(s, MQC_MAIL_GRAD + s->n_theta);
-    CK(cudaSetDevice(s->device));
-    CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaMemcpyAsync(val, reduced_scalars(s), 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (grad && s->n_theta)
         CK(cudaMemcpyAsync(grad, reduced_grad(s), sizeof(double) * s->n_theta, cudaMemcpyDeviceToHost, s->stream));

@@ -109,6 +109,66 @@ def s2_ladder_terms(n_orb):
             np.array(four_i), np.array(four_a), np.array(four_c, dtype=np.complex128))
 
 
+_STRUCT = {}
+
+
+def _structure(n):
+    """The term table is LINEAR in (h1, tei, s2_shift): the Pauli keys and the sparse map from the
+    n^2 + n^4 + 1 inputs to the key coefficients depend on n only.  Built once per n (this is the
+    cache SURVEY.md §8b suggests: successive mu steps and fragments differ in coefficients only)."""
+    if n in _STRUCT:
+        return _STRUCT[n]
+    from scipy.sparse import coo_matrix
+    nq = 2 * n
+    xs, zs, cs, js = [], [], [], []
+
+    def add(idx, act, coeff, inp):
+        x, z, c = _expand_products(idx, act, coeff)
+        rep = len(x) // max(1, len(inp))
+        xs.append(x); zs.append(z); cs.append(c); js.append(np.repeat(inp, rep))
+
+    p, q = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    p, q = p.reshape(-1), q.reshape(-1)
+    for s in (0, 1):
+        idx = np.stack([2 * p + s, 2 * q + s], axis=1)
+        act = np.tile(np.array([1, 0]), (len(p), 1))
+        add(idx, act, np.ones(len(p), dtype=np.complex128), p * n + q)
+    p, q, r, s_ = np.meshgrid(*(np.arange(n),) * 4, indexing="ij")
+    p, q, r, s_ = (v.reshape(-1) for v in (p, q, r, s_))
+    inp4 = n * n + ((p * n + s_) * n + q) * n + r                # tei[p, s, q, r]
+    for sg in (0, 1):
+        for tu in (0, 1):
+            P, Q, R, S = 2 * p + sg, 2 * q + tu, 2 * r + tu, 2 * s_ + sg
+            ok = (P != Q) & (R != S)
+            idx = np.stack([P[ok], Q[ok], R[ok], S[ok]], axis=1)
+            act = np.tile(np.array([1, 1, 0, 0]), (idx.shape[0], 1))
+            step = 1 << 18
+            for a0 in range(0, idx.shape[0], step):
+                add(idx[a0:a0 + step], act[a0:a0 + step], np.full(len(idx[a0:a0 + step]), 0.5, dtype=np.complex128),
+                    inp4[ok][a0:a0 + step])
+    ti, ta, tc, fi, fa, fc = s2_ladder_terms(n)
+    s2_inp = n * n + n ** 4
+    add(ti, ta, tc, np.full(len(tc), s2_inp))
+    add(fi, fa, fc, np.full(len(fc), s2_inp))
+    x = _reverse_bits(np.concatenate(xs), nq)
+    z = _reverse_bits(np.concatenate(zs), nq)
+    c = np.concatenate(cs)
+    j = np.concatenate(js)
+    key = (x.astype(object) << 64) | z.astype(object) if nq > 32 else (x << np.uint64(32)) | z
+    uniq, inv = np.unique(key, return_inverse=True)
+    if nq > 32:
+        ux = np.array([int(k) >> 64 for k in uniq], dtype=np.uint64)
+        uz = np.array([int(k) & ((1 << 64) - 1) for k in uniq], dtype=np.uint64)
+    else:
+        ux = uniq >> np.uint64(32)
+        uz = uniq & np.uint64(0xFFFFFFFF)
+    A = coo_matrix((c, (inv, j)), shape=(len(uniq), s2_inp + 1)).tocsr()
+    _STRUCT[n] = (ux, uz, A)
+    if len(_STRUCT) > 6:
+        _STRUCT.pop(next(iter(_STRUCT)))
+    return _STRUCT[n]
+
+
 def fragment_term_table(one_body_mo, two_body_mo, n_imp_orbs=0, chempot_imp=0.0, s2_shift=0.0,
                         tol=1e-14):
     """(xmask, zmask, coeff) sorted by (xmask, zmask) for
@@ -118,43 +178,15 @@ def fragment_term_table(one_body_mo, two_body_mo, n_imp_orbs=0, chempot_imp=0.0,
     fock = np.asarray(one_body_mo, dtype=np.float64)
     tei = np.asarray(two_body_mo, dtype=np.float64)
     n = fock.shape[0]
-    nq = 2 * n
     h = fock.copy()
     if chempot_imp != 0.0:
         d = np.arange(n_imp_orbs)
         h[d, d] -= chempot_imp
-    xs, zs, cs = [], [], []
-    # one-body: both spins
-    p, q = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
-    p, q = p.reshape(-1), q.reshape(-1)
-    for s in (0, 1):
-        idx = np.stack([2 * p + s, 2 * q + s], axis=1)
-        act = np.tile(np.array([1, 0]), (len(p), 1))
-        x, z, c = _expand_products(idx, act, h[p, q].astype(np.complex128))
-        xs.append(x); zs.append(z); cs.append(c)
-    # two-body: h2[P,Q,R,S] = tei[p,s,q,r] for spins (sP,sQ,sR,sS) = (s,t,t,s)
-    p, q, r, s_ = np.meshgrid(*(np.arange(n),) * 4, indexing="ij")
-    p, q, r, s_ = (v.reshape(-1) for v in (p, q, r, s_))
-    val = 0.5 * tei[p, s_, q, r]
-    for sg in (0, 1):
-        for tu in (0, 1):
-            P, Q, R, S = 2 * p + sg, 2 * q + tu, 2 * r + tu, 2 * s_ + sg
-            ok = (P != Q) & (R != S) & (val != 0.0)
-            idx = np.stack([P[ok], Q[ok], R[ok], S[ok]], axis=1)
-            act = np.tile(np.array([1, 1, 0, 0]), (idx.shape[0], 1))
-            # chunk to bound memory at large n
-            step = 1 << 18
-            for a0 in range(0, idx.shape[0], step):
-                x, z, c = _expand_products(idx[a0:a0 + step], act[a0:a0 + step],
-                                           val[ok][a0:a0 + step].astype(np.complex128))
-                xs.append(x); zs.append(z); cs.append(c)
-    if s2_shift != 0.0:
-        ti, ta, tc, fi, fa, fc = s2_ladder_terms(n)
-        x, z, c = _expand_products(ti, ta, tc * s2_shift)
-        xs.append(x); zs.append(z); cs.append(c)
-        x, z, c = _expand_products(fi, fa, fc * s2_shift)
-        xs.append(x); zs.append(z); cs.append(c)
-    return _combine(xs, zs, cs, nq, tol)
+    ux, uz, A = _structure(n)
+    v = np.concatenate([h.reshape(-1), tei.reshape(-1), [s2_shift]])
+    csum = A @ v
+    keep = np.abs(csum) > tol
+    return ux[keep], uz[keep], csum[keep]
 
 
 def s2_term_table(n_orb, tol=1e-14):
