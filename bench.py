@@ -167,6 +167,28 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def dmet_wall_time(device):
+    """H10 chain STO-3G, 2-atom fragments (BASELINE.json configs[0], test/dmet_hchain.py shape): wall
+    time of a whole DMET run (all chemical-potential steps, 5 fragments of 8 qubits each) with the
+    GPU UCCSD solver behind the reference's solve() signature."""
+    from multiscalequantumcomputing_b200.parallel import solve_fragments
+    from multiscalequantumcomputing_b200.solver import clear_warm_start
+    from multiscalequantumcomputing_b200.synth.hydrogen import hydrogen_chain, local_integrals
+    from multiscalequantumcomputing_b200.synth.dmet_loop import DMETRun, atom_clusters
+    ints = local_integrals(hydrogen_chain(10, 0.6))
+    cl = atom_clusters(10, 2)
+    best = None
+    for _ in range(3):
+        clear_warm_start()
+        run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[device], warm_start=False))
+        t = time.perf_counter(); e = run.run(); dt = time.perf_counter() - t
+        if best is None or dt < best["wall_s"]:
+            best = {"wall_s": dt, "solves": run.n_solves, "mu_steps": len(run.history), "energy": e}
+    best.update({"system": "H10 chain STO-3G 0.6 A, 5 fragments x 2 atoms, 8 qubits each, UCCSD", "unit": "s", "runs": 3,
+                 "reference": "745.97 s per DMET iteration with the reference's VQE solver (test/log_hchain_vqe:4039)"})
+    return best
+
+
 def run_ours(args):
     import torch
     from multiscalequantumcomputing_b200 import _lib
@@ -319,6 +341,13 @@ def run_ours(args):
                 cpu = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample}
             except Exception as exc:  # the checker could not be built on this box
                 cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % exc}
+        # second half of BASELINE.json's metric: wall time of one DMET run (configs[0] shape)
+        dmet = None
+        if world == 1:
+            try:
+                dmet = dmet_wall_time(local)
+            except Exception as exc:
+                dmet = {"unavailable": str(exc)}
         out = {"metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
@@ -329,6 +358,7 @@ def run_ours(args):
                        "d2h_bytes_per_step": int(grad_pin.numel() * 8 + 16), "ms_per_step": e2e_ms / args.steps},
                "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                "clocks": clocks, "roofline": roof, "roofline_streaming": streaming, "cpu_baseline": cpu,
+               "dmet_iteration": dmet,
                "energy": e_ref, "setup_s": setup_s}
         print(json.dumps(out))
     h.close()
