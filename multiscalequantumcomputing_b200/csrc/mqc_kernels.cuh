@@ -505,45 +505,64 @@ k_tile_sp2(const __grid_constant__ MqcPeers PR, const __grid_constant__ MqcPass 
             if (c0 == 0) cp_async_wait_all();
             team_sync<TW>(team);
             unsigned todo = s_todo[team];
+            // Factors are applied one after the other (barrier in between), but the warp
+            // reductions of their gradient partials are deferred: eight factors keep their
+            // per-lane partials in registers and are reduced together, as independent shuffle
+            // chains off the critical path (one reduction per factor cost ~200 cycles of pure
+            // latency between two barriers).
+            constexpr int GR = ADJ ? 8 : 1;
             while (todo) {
-                const int fc = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint4 A = hA[fc], B = hB[fc];
-                const int nLB = (int)B.y;
-                const int npairs = (int)A.y * nLB;
-                const double2 csv = hcs[fc];
-                const double c = csv.x, sn = csv.y;
-                const uint32_t sg = hsg[fc];
-                const float rcp = __uint_as_float(B.z);
-                const bool idA = (A.w >> 16) & 1u, idB = (B.w >> 16) & 1u;
-                double gacc = 0.0;
-                for (int u = tl; u < npairs; u += TT) {
-                    const int ua = (int)(((float)u + 0.5f) * rcp), ub = u - ua * nLB;
-                    const uint32_t la = idA ? ((uint32_t)ua * 129u | (((uint32_t)__popc(spat[ua] & A.w) & 1u) << 14)) : (uint32_t)slist[A.x + ua];
-                    const uint32_t lb = idB ? ((uint32_t)ub * 129u | (((uint32_t)__popc(spat[nAl + ub] & B.w) & 1u) << 14)) : (uint32_t)slist[B.x + ub];
-                    const int e0 = (int)(la & 0x7fu) * nBl + (int)(lb & 0x7fu);
-                    const int e1 = (int)((la >> 7) & 0x7fu) * nBl + (int)((lb >> 7) & 0x7fu);
-                    const bool neg = ((((la ^ lb) >> 14) ^ sg) & 1u) != 0u;
-                    const double ssn = neg ? -sn : sn;
-                    const double2 a = sp[e0], b = sp[e1];
-                    if (ADJ) {
-                        const double2 xa = sl[e0], xb = sl[e1];
-                        const double gv = xb.x * a.x + xb.y * a.y - xa.x * b.x - xa.y * b.y;
-                        gacc += neg ? -gv : gv;
-                        sl[e0] = make_double2(c * xa.x - ssn * xb.x, c * xa.y - ssn * xb.y);
-                        sl[e1] = make_double2(c * xb.x + ssn * xa.x, c * xb.y + ssn * xa.y);
-                    }
-                    sp[e0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
-                    sp[e1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
-                }
-                if (ADJ && npairs > wt * 32) {                    // uniform over the warp: this warp had pairs
-                    // lanes beyond the warp's share hold zero: only the butterfly stages below it matter
-                    const int mine = min(32, npairs - wt * 32);
+                double acc8[GR];
+                int fi8[GR];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) if (mine > o || TW > 1) gacc += __shfl_xor_sync(0xffffffffu, gacc, o);
-                    if (lane == 0) gw[hfi[fc]] += gacc;
+                for (int j = 0; j < GR; ++j) {
+                    acc8[j] = 0.0; fi8[j] = -1;
+                    if (todo) {                                   // uniform over the team
+                        const int fc = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const uint4 A = hA[fc], B = hB[fc];
+                        const int nLB = (int)B.y;
+                        const int npairs = (int)A.y * nLB;
+                        const double2 csv = hcs[fc];
+                        const double c = csv.x, sn = csv.y;
+                        const uint32_t sg = hsg[fc];
+                        const float rcp = __uint_as_float(B.z);
+                        const bool idA = (A.w >> 16) & 1u, idB = (B.w >> 16) & 1u;
+                        double gacc = 0.0;
+                        for (int u = tl; u < npairs; u += TT) {
+                            const int ua = (int)(((float)u + 0.5f) * rcp), ub = u - ua * nLB;
+                            const uint32_t la = idA ? ((uint32_t)ua * 129u | (((uint32_t)__popc(spat[ua] & A.w) & 1u) << 14)) : (uint32_t)slist[A.x + ua];
+                            const uint32_t lb = idB ? ((uint32_t)ub * 129u | (((uint32_t)__popc(spat[nAl + ub] & B.w) & 1u) << 14)) : (uint32_t)slist[B.x + ub];
+                            const int e0 = (int)(la & 0x7fu) * nBl + (int)(lb & 0x7fu);
+                            const int e1 = (int)((la >> 7) & 0x7fu) * nBl + (int)((lb >> 7) & 0x7fu);
+                            const bool neg = ((((la ^ lb) >> 14) ^ sg) & 1u) != 0u;
+                            const double ssn = neg ? -sn : sn;
+                            const double2 a = sp[e0], b = sp[e1];
+                            if (ADJ) {
+                                const double2 xa = sl[e0], xb = sl[e1];
+                                const double gv = xb.x * a.x + xb.y * a.y - xa.x * b.x - xa.y * b.y;
+                                gacc += neg ? -gv : gv;
+                                sl[e0] = make_double2(c * xa.x - ssn * xb.x, c * xa.y - ssn * xb.y);
+                                sl[e1] = make_double2(c * xb.x + ssn * xa.x, c * xb.y + ssn * xa.y);
+                            }
+                            sp[e0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
+                            sp[e1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
+                        }
+                        if (ADJ) { acc8[j] = gacc; fi8[j] = hfi[fc]; }
+                        team_sync<TW>(team);
+                    }
                 }
-                team_sync<TW>(team);
+                if (ADJ) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int j = 0; j < GR; ++j) acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], o);
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < GR; ++j) if (fi8[j] >= 0 && acc8[j] != 0.0) gw[fi8[j]] += acc8[j];
+                    }
+                }
             }
         }
         if (nf == 0) { cp_async_wait_all(); team_sync<TW>(team); }
