@@ -948,7 +948,7 @@ struct MqcFlags {
 };
 // All ranks launch this with the same epoch.  System-scope fence + release store publish
 // everything this GPU wrote (to its own and to peers' HBM) before the arrival flag; the
-// acquire spin returns once every peer has arrived.  Spins are bounded (~10 s) so that a dead
+// acquire spin returns once every peer has arrived.  Spins are bounded (~60 s) so that a dead
 // peer becomes an error flag, not a hung GPU.
 __global__ void k_rank_barrier(const __grid_constant__ MqcFlags F, const unsigned long long epoch,
                                int* __restrict__ err) {
@@ -963,7 +963,7 @@ __global__ void k_rank_barrier(const __grid_constant__ MqcFlags F, const unsigne
     while (true) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
         if (seen >= epoch) break;
-        if (clock64() - t0 > 20000000000ll) { *err = 1; break; }
+        if (clock64() - t0 > 120000000000ll) { *err = 1; break; }
         __nanosleep(200);
     }
     __threadfence_system();
