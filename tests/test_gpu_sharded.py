@@ -4,7 +4,7 @@ write the peers' shards directly, energy / gradient partial sums are reduced ove
 memory.  `ShardGroup` with a repeated device puts several ranks on ONE GPU, so the whole
 protocol (tile maps, peer addressing, ordering between ranks, reductions) runs on the
 single-GPU test tier; the one-process-per-GPU transport (CUDA IPC + flag barrier) is
-exercised by `scripts/shard_ipc_check.py` under torchrun when the box has >= 2 GPUs."""
+exercised by `tests/tools/shard_ipc_check.py` under torchrun when the box has >= 2 GPUs."""
 import os
 import subprocess
 import sys
@@ -115,7 +115,7 @@ def test_sharded_equals_unsharded_20_qubits():
 def test_ipc_ranks_under_torchrun():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29571",
-           os.path.join(ROOT, "scripts", "shard_ipc_check.py"), "--n-orb", "7"]
+           os.path.join(ROOT, "tests", "tools", "shard_ipc_check.py"), "--n-orb", "7"]
     for extra in ([], ["--blocked"]):
         res = subprocess.run(cmd + extra, capture_output=True, text=True, timeout=600, cwd=ROOT)
         assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]

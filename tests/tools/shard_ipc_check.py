@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """One process per GPU (torchrun): sharded UCCSD energy + gradient + RDMs through CUDA IPC peer
 memory, checked against the CPU oracle on rank 0.  Used by tests/test_gpu_sharded.py and as a
-stand-alone check:  torchrun --nproc-per-node 2 scripts/shard_ipc_check.py --n-orb 7"""
+stand-alone check:  torchrun --nproc-per-node 2 tests/tools/shard_ipc_check.py --n-orb 7"""
 import argparse
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 
