@@ -243,3 +243,60 @@ def test_properties_24_qubits_full_size():
     es, gs = hs.energy_grad(th)
     assert abs(es - e) < E_TOL and abs(gs - g).max() < G_TOL
     hs.close(); h.close()
+
+
+def test_empty_ansatz_is_the_reference_determinant():
+    """No factors at all: the state is the reference determinant, E = <ref|H|ref>, the gradient
+    is empty (the starting point of ADAPT-VQE; `test/testlog_vqe:25` logs this energy)."""
+    n, ne = 4, 4
+    h1, eri = random_fragment_integrals(n, 3)
+    tab = fragment_term_table(h1, eri, 0, 0.0, 0.25)
+    ref_index = (1 << 8) - (1 << 4)
+    h = _lib.Handle(2 * n)
+    h.set_hamiltonian(*tab)
+    h.set_ansatz(np.zeros(0, np.int32), np.zeros((0, 4), np.int32), np.zeros(0, np.int32), 0, ref_index)
+    psi = np.zeros(256, dtype=np.complex128); psi[ref_index] = 1.0
+    e_ref = np.vdot(psi, apply_terms(*tab, psi)).real
+    assert abs(h.energy(np.zeros(0)) - e_ref) < E_TOL
+    e, g = h.energy_grad(np.zeros(0))
+    assert abs(e - e_ref) < E_TOL and len(g) == 0
+    assert abs(h.state(np.zeros(0)) - psi).max() == 0.0
+    h.close()
+
+
+@pytest.mark.parametrize("n,occ", [(5, (0, 1, 2, 3, 4)), (6, (0, 2, 4, 6, 1))])
+def test_open_shell_sector_and_generalized_factors(n, occ):
+    """N_alpha != N_beta reference and generalized (not occupied->virtual) singles/doubles with a
+    shared parameter: the sector machinery (tiles, link tables, RDM strings) is not tied to the
+    closed-shell UCCSD list."""
+    from multiscalequantumcomputing_b200.adapt import generalized_pool
+    from multiscalequantumcomputing_b200.uccsd import FactorList
+    nq = 2 * n
+    h1, eri = random_fragment_integrals(n, 11)
+    tab = fragment_term_table(h1, eri, 0, 0.0, 0.25)
+    kind, idx = generalized_pool(n)
+    rng = np.random.default_rng(9)
+    pick = rng.choice(len(kind), size=60, replace=False)
+    ref_index = sum(1 << (nq - 1 - q) for q in occ)
+    theta_index = np.arange(60, dtype=np.int32)
+    theta_index[-1] = 0                                   # two factors share theta_0
+    F = FactorList(nq, kind[pick], idx[pick], theta_index, 59, ref_index)
+    na = sum(1 for q in occ if q % 2 == 0)
+    assert na != len(occ) - na
+    h = _lib.Handle(nq)
+    h.set_option("tile_bits", 8)
+    h.set_option("grad_tile_bits", 8)
+    h.set_hamiltonian(*tab)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    th = rng.normal(0, 0.3, F.n_theta)
+    orc = UCCSDOracle(nq, F.as_tuples(), F.theta_index, F.ref_index, tab)
+    assert abs(h.state(th) - orc.state(th)).max() < S_TOL
+    e_ref, g_ref = orc.energy_grad(th)
+    e, g = h.energy_grad(th)
+    assert abs(e - e_ref) < E_TOL and abs(g - g_ref).max() < G_TOL
+    r1, r2 = h.rdm12(n, na, len(occ) - na)
+    assert abs(np.trace(r1) - len(occ)) < 1e-10
+    assert abs(np.einsum("iijj->", r2) - len(occ) * (len(occ) - 1)) < 1e-9
+    e_bare = h.expectation(*fragment_term_table(h1, eri, 0, 0.0, 0.0)).real
+    assert abs(np.einsum("pq,pq->", h1, r1) + 0.5 * np.einsum("pqrs,pqrs->", eri, r2) - e_bare) < 1e-9
+    h.close()

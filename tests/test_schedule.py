@@ -122,3 +122,28 @@ def test_sparse_plan_reproduces_oracle_state(n, ne, kb, lb, order):
     for which in (0, 1):
         psi = h.sparse_plan_host_state(th, which)
         assert abs(psi - ref).max() < 1e-13
+
+
+def test_sparse_plan_open_shell_generalized_factors():
+    """N_alpha != N_beta reference, generalized singles/doubles: plan tables on the host = oracle."""
+    from multiscalequantumcomputing_b200.adapt import generalized_pool
+    from multiscalequantumcomputing_b200.uccsd import FactorList
+    n, occ = 5, (0, 1, 2, 3, 4)
+    nq = 2 * n
+    kind, idx = generalized_pool(n)
+    rng = np.random.default_rng(9)
+    pick = rng.choice(len(kind), size=50, replace=False)
+    ref_index = sum(1 << (nq - 1 - q) for q in occ)
+    F = FactorList(nq, kind[pick], idx[pick], np.arange(50, dtype=np.int32), 50, ref_index)
+    h = _lib.Handle(nq)
+    h.set_option("tile_bits", 7)
+    h.set_option("grad_tile_bits", 7)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    th = rng.normal(0, 0.3, F.n_theta)
+    ref = UCCSDOracle(nq, F.as_tuples(), F.theta_index, F.ref_index, EMPTY).state(th)
+    assert abs(h.sparse_plan_host_state(th, 0) - ref).max() < 1e-13
+    # and the generic schedule through the numpy interpreter
+    S = h.schedule(0)
+    cs = [(np.cos(th[t]), np.sin(th[t])) for t in F.theta_index]
+    psi = SI.to_logical(SI.run_forward(S, nq, F.ref_index, cs), S["final_layout"])
+    assert abs(psi - ref).max() < 1e-13
