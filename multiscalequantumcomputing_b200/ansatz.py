@@ -15,11 +15,15 @@ from .uccsd import FactorList
 
 
 class UCCSDAnsatz:
-    def __init__(self, n_qubits: int, term_table, factors: FactorList, device: int = 0, options=None):
+    def __init__(self, n_qubits: int, term_table, factors: FactorList, device: int = 0, options=None, devices=None):
+        """``devices``: list of 2, 4 or 8 GPU indices -> the state vector is sharded over them
+        (`mqc_shard_group_create`; fragments beyond one GPU's memory).  A repeated index puts
+        several shards on one GPU."""
         self.n_qubits = n_qubits
         self.factors = factors
         self.xmask, self.zmask, self.coeff = term_table
-        self.handle = _lib.Handle(n_qubits, device)
+        self.handle = _lib.ShardGroup(n_qubits, list(devices)) if devices is not None and len(devices) > 1 \
+            else _lib.Handle(n_qubits, device if devices is None else devices[0])
         for k, v in (options or {}).items():
             self.handle.set_option(k, v)
         self.handle.set_hamiltonian(self.xmask, self.zmask, self.coeff)
@@ -71,7 +75,10 @@ class UCCSDAnsatz:
     def state(self, theta):
         """(2^N, 1) complex128 column in OpenFermion index order (`wfn[idx, 0]`,
         dmet_solver_vqechem.py:114)."""
-        return self.handle.state(np.ascontiguousarray(theta, dtype=np.float64)).reshape(-1, 1)
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        if isinstance(self.handle, _lib.ShardGroup):
+            return self.handle.gather_state(th).reshape(-1, 1)
+        return self.handle.state(th).reshape(-1, 1)
 
     # -- extras -----------------------------------------------------------------------
     def prepare(self, theta):

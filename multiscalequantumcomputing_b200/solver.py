@@ -165,7 +165,9 @@ def solve(oei_mo, one_body_mo, two_body_mo, n_imp: int, n_imp_orbs: int, chempot
                              backend=_ansatz_factory)
         warm_start = False
     else:
-        make = _ansatz_factory or (lambda nq, tab, fac: UCCSDAnsatz(nq, tab, fac, device=device, options=(options or {}).get("gpu")))
+        # options["devices"] = [0, 1, ...]: shard the fragment's state vector over these GPUs
+        make = _ansatz_factory or (lambda nq, tab, fac: UCCSDAnsatz(nq, tab, fac, device=device, options=(options or {}).get("gpu"),
+                                                                    devices=(options or {}).get("devices")))
         ansatz = make(n_qubits, prob["table"], factors)
     key = (n_orb, n_elec, n_imp_orbs, device)
     if theta0 is None and warm_start and key in _WARM and len(_WARM[key]) == factors.n_theta:
