@@ -180,11 +180,12 @@ def dmet_wall_time(device):
     best = None
     for _ in range(3):
         clear_warm_start()
-        run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[device], warm_start=False))
+        # the five fragments of a mu step are independent: one worker (handle + stream) each on this GPU
+        run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[device] * len(cl), warm_start=False))
         t = time.perf_counter(); e = run.run(); dt = time.perf_counter() - t
         if best is None or dt < best["wall_s"]:
             best = {"wall_s": dt, "solves": run.n_solves, "mu_steps": len(run.history), "energy": e}
-    best.update({"system": "H10 chain STO-3G 0.6 A, 5 fragments x 2 atoms, 8 qubits each, UCCSD", "unit": "s", "runs": 3,
+    best.update({"system": "H10 chain STO-3G 0.6 A, 5 fragments x 2 atoms, 8 qubits each, UCCSD, fragments concurrent on one GPU", "unit": "s", "runs": 3,
                  "reference": "745.97 s per DMET iteration with the reference's VQE solver (test/log_hchain_vqe:4039)"})
     return best
 
