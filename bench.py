@@ -190,6 +190,40 @@ def dmet_wall_time(device):
     return best
 
 
+def reference_style_small(device):
+    """The reference's own kind of arithmetic - scipy.sparse csc Hamiltonian, sparse generators,
+    `expm_multiply` chain, reverse sweep (oracle.statevector.SparseReferenceStyle; what VQEChem /
+    OpenFermion / SciPy do behind mqc.solver) - is only feasible at small registers:
+    time one energy+gradient there, next to the CUDA path on the same inputs."""
+    from multiscalequantumcomputing_b200 import _lib
+    from multiscalequantumcomputing_b200.jw import fragment_term_table
+    from multiscalequantumcomputing_b200.synth.hydrogen import hydrogen_chain, mo_integrals
+    from multiscalequantumcomputing_b200.uccsd import uccsd_factors
+    from oracle.statevector import SparseReferenceStyle
+    rows = []
+    for n in (4, 6):
+        h_mo, eri_mo, e_nuc, e_rhf = mo_integrals(hydrogen_chain(n, 1.0), n)
+        tab = fragment_term_table(h_mo, eri_mo, 0, 0.0, 0.25)
+        F = uccsd_factors(n, n, "blocked")
+        th = np.random.default_rng(THETA_SEED).normal(0.0, THETA_SIGMA, F.n_theta)
+        S = SparseReferenceStyle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, tab)
+        t = time.perf_counter(); e_cpu, g_cpu = S.energy_grad(th); cpu_ms = (time.perf_counter() - t) * 1e3
+        h = _lib.Handle(2 * n, device)
+        h.set_hamiltonian(*tab)
+        h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+        for _ in range(3):
+            e_gpu, g_gpu = h.energy_grad(th)
+        reps = 50
+        t = time.perf_counter()
+        for _ in range(reps):
+            e_gpu, g_gpu = h.energy_grad(th)
+        gpu_ms = (time.perf_counter() - t) * 1e3 / reps
+        h.close()
+        rows.append({"n_qubits": 2 * n, "n_theta": F.n_theta, "cpu_scipy_sparse_ms": cpu_ms, "gpu_host_call_ms": gpu_ms,
+                     "dE": abs(e_gpu - e_cpu), "max_dg": float(np.abs(g_gpu - g_cpu).max())})
+    return rows
+
+
 def run_ours(args):
     import torch
     from multiscalequantumcomputing_b200 import _lib
@@ -349,6 +383,12 @@ def run_ours(args):
                 dmet = dmet_wall_time(local)
             except Exception as exc:
                 dmet = {"unavailable": str(exc)}
+        ref_small = None
+        if world == 1:
+            try:
+                ref_small = reference_style_small(local)
+            except Exception as exc:
+                ref_small = {"unavailable": str(exc)}
         out = {"metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
@@ -359,7 +399,7 @@ def run_ours(args):
                        "d2h_bytes_per_step": int(grad_pin.numel() * 8 + 16), "ms_per_step": e2e_ms / args.steps},
                "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                "clocks": clocks, "roofline": roof, "roofline_streaming": streaming, "cpu_baseline": cpu,
-               "dmet_iteration": dmet,
+               "dmet_iteration": dmet, "reference_style_scipy_sparse": ref_small,
                "energy": e_ref, "setup_s": setup_s}
         print(json.dumps(out))
     h.close()
