@@ -120,28 +120,47 @@ def dist_env():
 
 
 _CPU_REF = None
-_SEC = None
 
 
-def cpu_sample(table, factors, theta, n_fac=32, n_terms=1500):
-    global _CPU_REF, _SEC
-    from oracle.cref import CRefUCCSD, num_threads, use_all_cores
+def _cpu_ref(table, factors):
+    global _CPU_REF
+    from oracle.cref import CRefUCCSD, use_all_cores
     use_all_cores()
     if _CPU_REF is None:
         _CPU_REF = CRefUCCSD(factors.n_qubits, factors.kind, factors.idx, factors.theta_index, factors.n_theta,
                              factors.ref_index, table)
-    ref = _CPU_REF
-    if _SEC is None:
-        from oracle.fci import sector_indices
-        _SEC = sector_indices(N_ORB, N_ELEC)[1]
-    sec = _SEC
+    return _CPU_REF
+
+
+def cpu_full_evaluation(table, factors, theta):
+    """ONE full, un-extrapolated energy + adjoint-gradient evaluation of the bench workload with
+    the sector-aware C/OpenMP port (oracle/c: sweeps over the 853 776 determinants of the sector,
+    H applied X-group by X-group in (alpha string, beta string) coordinates) on all host cores.
+    Returns (seconds, cores, energy, gradient, phase seconds)."""
+    from oracle.cref import num_threads
+    ref = _cpu_ref(table, factors)
+    ref.sector_list()
+    t = time.perf_counter()
+    e, g, ph = ref.energy_grad_sector(theta)
+    dt = time.perf_counter() - t
+    return dt, num_threads(), e, g, ph
+
+
+def cpu_dense_sample(table, factors, theta, n_fac=16, n_terms=600):
+    """Context only: the dense-sweep variant of the port (every factor sweeps all 2^24 basis states,
+    as a generic state-vector simulator would) on a bounded sample, scaled linearly."""
+    from oracle.fci import sector_indices
+    ref = _cpu_ref(table, factors)
+    sec = sector_indices(N_ORB, N_ELEC)[1]
     tf, th, tr, nf, nt = ref.time_sample(theta, n_fac, n_terms, sector_index=sec)
     n_all, t_all = len(factors), len(table[0])
-    t_eval = tf / nf * n_all + th / nt * t_all + tr / nf * n_all
-    sample = ("forward over %d of %d factors (%.2fs), H apply over %d of %d Pauli terms (%.2fs), adjoint reverse "
-              "over %d factors (%.2fs); scaled linearly to one full evaluation = %.1fs" %
-              (nf, n_all, tf, nt, t_all, th, nf, tr, t_eval))
-    return 1.0 / t_eval, num_threads(), sample
+    return {"seconds_per_evaluation_extrapolated": tf / nf * n_all + th / nt * t_all + tr / nf * n_all,
+            "sample": "forward %d of %d factors %.2fs, H %d of %d terms %.2fs, reverse %d factors %.2fs" %
+                      (nf, n_all, tf, nt, t_all, th, nf, tr)}
+
+
+CPU_SAMPLE = ("one FULL evaluation per step (not extrapolated): sector-aware C/OpenMP port, forward sweep over all 1818 "
+              "factors, H|psi> over all 15169 Pauli terms, adjoint reverse sweep; determinants of the (6,6) sector only")
 
 
 def run_reference(args):
@@ -149,23 +168,28 @@ def run_reference(args):
     if rank != 0:
         return
     table, factors, theta, n_groups = workload()
-    vals = []
-    info = None
+    times, phases = [], []
+    cores = 0
+    e = None
     for it in range(args.warmup + args.steps):
-        v, cores, sample = cpu_sample(table, factors, theta, n_fac=16, n_terms=600)
+        dt, cores, e, g, ph = cpu_full_evaluation(table, factors, theta)
         if it >= args.warmup:
-            vals.append(v)
-            info = (cores, sample)
-    value = float(np.mean(vals))
+            times.append(dt)
+            phases.append(ph)
+    t_step = float(np.mean(times))
+    value = 1.0 / t_step
+    ph = np.mean(phases, axis=0)
     out = {"impl": "reference", "metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)",
            "data": "synthetic", "config": dict(CONFIG),
-           "cpu_baseline": {"value": value, "unit": "evals/s", "cores": info[0], "kind": "port", "sample": info[1]},
+           "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE,
+                            "phase_s": {"forward": ph[0], "hamiltonian": ph[1], "reverse": ph[2]}},
            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "energy": e,
            "note": "the reference's own path (OpenFermion/SciPy 2^N x 2^N sparse operators) cannot be built or run "
-                   "here and is infeasible at 24 qubits (SURVEY.md §5); this arm times oracle/c, a matrix-free "
-                   "C/OpenMP port of the same mathematics, on a bounded sample per step"}
+                   "here and is infeasible at 24 qubits (SURVEY.md §5); this arm times oracle/c, a matrix-free, "
+                   "sector-aware C/OpenMP port of the same mathematics: every step is one complete evaluation"}
     print(json.dumps(out))
 
 
@@ -203,26 +227,67 @@ def reference_style_small(device):
     from multiscalequantumcomputing_b200.uccsd import uccsd_factors
     from oracle.statevector import SparseReferenceStyle
     rows = []
-    for n in (4, 6):
+    for n in (4, 6, 8):
         h_mo, eri_mo, e_nuc, e_rhf = mo_integrals(hydrogen_chain(n, 1.0), n)
         tab = fragment_term_table(h_mo, eri_mo, 0, 0.0, 0.25)
         F = uccsd_factors(n, n, "blocked")
         th = np.random.default_rng(THETA_SEED).normal(0.0, THETA_SIGMA, F.n_theta)
+        t = time.perf_counter()
         S = SparseReferenceStyle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, tab)
+        build_s = time.perf_counter() - t
         t = time.perf_counter(); e_cpu, g_cpu = S.energy_grad(th); cpu_ms = (time.perf_counter() - t) * 1e3
         h = _lib.Handle(2 * n, device)
         h.set_hamiltonian(*tab)
         h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
         for _ in range(3):
             e_gpu, g_gpu = h.energy_grad(th)
-        reps = 50
+        reps = 50 if n < 8 else 20
         t = time.perf_counter()
         for _ in range(reps):
             e_gpu, g_gpu = h.energy_grad(th)
         gpu_ms = (time.perf_counter() - t) * 1e3 / reps
         h.close()
-        rows.append({"n_qubits": 2 * n, "n_theta": F.n_theta, "cpu_scipy_sparse_ms": cpu_ms, "gpu_host_call_ms": gpu_ms,
+        rows.append({"n_qubits": 2 * n, "n_theta": F.n_theta, "cpu_scipy_sparse_ms": cpu_ms,
+                     "cpu_operator_build_s": build_s, "gpu_host_call_ms": gpu_ms,
                      "dE": abs(e_gpu - e_cpu), "max_dg": float(np.abs(g_gpu - g_cpu).max())})
+    return rows
+
+
+def variant_legs(device, opts, steps=5):
+    """Same metric on the neighbouring workloads SURVEY.md §8d names: the seeded generic C3 instance
+    (29 737 Pauli terms / 5 479 X-groups: twice the K2 work of the H12 chain) and the plain
+    lexicographic UCCSD factor order (more passes than the blocked order the headline uses)."""
+    from multiscalequantumcomputing_b200 import _lib
+    from multiscalequantumcomputing_b200.jw import fragment_term_table, number_of_x_groups
+    from multiscalequantumcomputing_b200.synth.hydrogen import hydrogen_chain, mo_integrals, random_fragment_integrals
+    from multiscalequantumcomputing_b200.uccsd import uccsd_factors
+    h_mo, eri_mo, _, _ = mo_integrals(hydrogen_chain(N_ORB, BOND), N_ELEC)
+    tabs = {"H12_chain": fragment_term_table(h_mo, eri_mo, 0, 0.0, 0.25),
+            "generic_C3_seed1234": fragment_term_table(*random_fragment_integrals(N_ORB, 1234), 0, 0.0, 0.25)}
+    rows = []
+    for inst, order in (("H12_chain", "lex"), ("generic_C3_seed1234", "blocked"), ("generic_C3_seed1234", "lex")):
+        tab = tabs[inst]
+        F = uccsd_factors(N_ORB, N_ELEC, order, block_orbs=BLOCK_ORBS)
+        th = np.random.default_rng(THETA_SEED).normal(0.0, THETA_SIGMA, F.n_theta)
+        h = _lib.Handle(F.n_qubits, device)
+        for kv in opts:
+            k, v = kv.split("=")
+            h.set_option(k, int(v))
+        h.set_hamiltonian(*tab)
+        h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+        for _ in range(3):
+            e, g = h.energy_grad(th)
+        ph = np.zeros(4)
+        for _ in range(steps):
+            e = h.energy_grad_resident()
+            t = h.last_timing()
+            ph += (t["forward_ms"], t["hamiltonian_ms"], t["reverse_ms"], t["total_ms"])
+        ph /= steps
+        rows.append({"instance": inst, "factor_order": order, "n_pauli_terms": len(tab[0]),
+                     "n_x_groups": number_of_x_groups(tab[0]), "passes_per_sweep": t["forward_passes"],
+                     "evals_per_s": 1e3 / ph[3], "phase_ms": {"forward": ph[0], "hamiltonian": ph[1], "reverse": ph[2]},
+                     "energy": e})
+        h.close()
     return rows
 
 
@@ -374,8 +439,11 @@ def run_ours(args):
             cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "reported at N=1 only"}
         else:
             try:
-                v, cores, sample = cpu_sample(table, factors, theta)
-                cpu = {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample}
+                dt, cores, e_cpu, g_cpu, ph_cpu = cpu_full_evaluation(table, factors, theta)
+                cpu = {"value": 1.0 / dt, "unit": "evals/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE,
+                       "seconds": dt, "phase_s": {"forward": ph_cpu[0], "hamiltonian": ph_cpu[1], "reverse": ph_cpu[2]},
+                       "gpu_vs_cpu_dE": abs(e_cpu - e_ref), "gpu_vs_cpu_max_dg": float(np.abs(g_cpu - g_ref).max()),
+                       "dense_sweep_variant": cpu_dense_sample(table, factors, theta)}
             except Exception as exc:  # the checker could not be built on this box
                 cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % exc}
         # second half of BASELINE.json's metric: wall time of one DMET run (configs[0] shape)
@@ -391,6 +459,12 @@ def run_ours(args):
                 ref_small = reference_style_small(local)
             except Exception as exc:
                 ref_small = {"unavailable": str(exc)}
+        variants = None
+        if world == 1:
+            try:
+                variants = variant_legs(local, args.opt)
+            except Exception as exc:
+                variants = {"unavailable": str(exc)}
         out = {"metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
@@ -401,7 +475,9 @@ def run_ours(args):
                        "d2h_bytes_per_step": int(grad_pin.numel() * 8 + 16), "ms_per_step": e2e_ms / args.steps},
                "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                "clocks": clocks, "roofline": roof, "roofline_streaming": streaming, "cpu_baseline": cpu,
-               "dmet_iteration": dmet, "reference_style_scipy_sparse": ref_small,
+               "dmet_iteration": dmet, "reference_style_scipy_sparse": ref_small, "variants": variants,
+               "parity_note": "UCCSD energies / gradients are parity-unpinned by the reference (it runs ADAPT-VQE at 8 qubits "
+                              "only); they are pinned by the CPU oracle: cpu_baseline.gpu_vs_cpu_dE / _max_dg of THIS run",
                "energy": e_ref, "setup_s": setup_s}
         print(json.dumps(out))
     h.close()

@@ -151,6 +151,23 @@ int mqc_sigma_host_apply(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int6
 int mqc_sparse_plan_host_state(mqc_solver_t* s, int32_t which, const double* theta, double* re_im,
                                int64_t n_amplitudes);
 
+/* Host-only check of the COMPACT-sector plan (mqc_cplan.h: row / column layouts per pass, tile
+ * classes, pair-list blobs, row / column maps - the tables k_csweep walks): executes schedule
+ * `which` on one CPU thread and returns the state in OpenFermion order (<= 24 qubits).
+ * mqc_cplan_info: number of passes (-1: the handle does not use compact storage), the sector
+ * matrix shape and the shared memory one CTA needs (forward / adjoint). */
+int mqc_cplan_host_state(mqc_solver_t* s, int32_t which, const double* theta, double* re_im,
+                         int64_t n_amplitudes);
+int mqc_cplan_info(mqc_solver_t* s, int32_t which, int32_t* n_passes, int64_t* n_rows, int64_t* n_cols,
+                   int64_t* smem_forward, int64_t* smem_adjoint);
+
+/* Replaces: the `fcivec` argument of mqc/tools/rdm.py:131-138 (make_rdm1) and :157-172
+ * (make_rdm12): loads a caller-supplied wave function (OpenFermion order, 2^N amplitudes,
+ * interleaved re/im) as the prepared state, so that mqc_rdm12 / mqc_expectation evaluate it.
+ * Needs mqc_set_ansatz first (an empty factor list is fine: ref_index fixes the sector); with
+ * compact storage the vector must lie in that (N_alpha, N_beta) sector. */
+int mqc_load_state(mqc_solver_t* s, const double* re_im, int64_t n_amplitudes);
+
 /* Device-side timing of the last energy / energy_grad call (CUDA events on the solver's
  * stream): ms[0] forward sweep, ms[1] H apply, ms[2] reverse sweep, ms[3] total;
  * counters[0] kernel launches, counters[1] forward passes, counters[2] reverse passes. */

@@ -47,6 +47,9 @@ SIGNATURES = {
     "mqc_rdm12": [_H, C.c_int32, C.c_int32, C.c_int32, _f64p, _f64p],
     "mqc_last_timing": [_H, _f64p, _i64p],
     "mqc_sparse_plan_host_state": [_H, C.c_int32, _f64p, _f64p, C.c_int64],
+    "mqc_cplan_host_state": [_H, C.c_int32, _f64p, _f64p, C.c_int64],
+    "mqc_cplan_info": [_H, C.c_int32, _i32p, _i64p, _i64p, _i64p, _i64p],
+    "mqc_load_state": [_H, _f64p, C.c_int64],
     "mqc_sigma_host_apply": [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p,
                              _i64p, _i64p, _i64p],
     "mqc_schedule_info": [_H, C.c_int32, _i32p, _i32p, _i32p],
@@ -220,6 +223,24 @@ class Handle:
         t = self._theta(theta)
         check(self.lib.mqc_sparse_plan_host_state(self.h, which, ptr(t, _f64p), C.cast(out.ctypes.data, _f64p), out.shape[0]))
         return out
+
+    def cplan_host_state(self, theta, which=0) -> np.ndarray:
+        """CPU execution of the compact-sector plan (test of the tables k_csweep walks)."""
+        out = np.empty(1 << self.n_qubits, dtype=np.complex128)
+        t = self._theta(theta)
+        check(self.lib.mqc_cplan_host_state(self.h, which, ptr(t, _f64p), C.cast(out.ctypes.data, _f64p), out.shape[0]))
+        return out
+
+    def cplan_info(self, which=0):
+        npass = C.c_int32()
+        nr, nc, sf, sa = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(self.lib.mqc_cplan_info(self.h, which, C.byref(npass), C.byref(nr), C.byref(nc), C.byref(sf), C.byref(sa)))
+        return dict(n_passes=npass.value, n_rows=nr.value, n_cols=nc.value, smem_forward=sf.value, smem_adjoint=sa.value)
+
+    def load_state(self, psi):
+        """Make ``psi`` (OpenFermion order, 2^N complex amplitudes) the prepared state."""
+        v = np.ascontiguousarray(psi, dtype=np.complex128).reshape(-1)
+        check(self.lib.mqc_load_state(self.h, C.cast(v.ctypes.data, _f64p), v.shape[0]))
 
     def expectation(self, xmask, zmask, coeff) -> complex:
         x = np.ascontiguousarray(xmask, dtype=np.uint64)

@@ -16,6 +16,8 @@
 #include "mqc_kernels.cuh"
 #include "mqc_schedule.h"
 #include "mqc_sigma.h"
+#include "mqc_cplan.h"
+#include "mqc_csweep.cuh"
 
 static thread_local std::string g_err;
 
@@ -93,6 +95,17 @@ struct SigmaTables {                // link-table form of a sector Hamiltonian (
     size_t n_fallback = 0, n_fast = 0;
 };
 
+struct CPlanDev {                   // device copy of a compact-sector plan (mqc_cplan.h)
+    DevBuf<MqcCPassDev> pass;
+    DevBuf<MqcCClass> cls;
+    DevBuf<MqcCFactor> fac;
+    DevBuf<uint32_t> maps, tiles;
+    DevBuf<MqcCLive> live_tab;
+    DevBuf<MqcCProgHdr> prog_hdr;
+    DevBuf<uint32_t> prog;
+    void reset() { pass.release(); cls.release(); fac.release(); maps.release(); tiles.release(); live_tab.release(); prog_hdr.release(); prog.release(); }
+};
+
 struct LayoutTables {
     std::vector<int> phys;          // logical bit -> physical position
     HamTables ham;
@@ -159,6 +172,16 @@ struct mqc_solver {
     MqcTileLists tlist[2];          // host copy of the offsets; tiles live in pl_tiles
     DevBuf<u64> pl_tiles[2];
     int sp2 = 1, sp2_warps = 4, sp2_list = 1, sp2_smem_kb = 220, sp2_team = 0;
+    // compact sector storage (mqc_cplan.h): the state is the matrix C[alpha string][beta string];
+    // cpsi / clam ping-pong between the layouts of consecutive passes
+    int compact = 1, csweep_threads = 256, csweep_ctas = 0;
+    bool use_compact = false;
+    MqcCPlan cplan[2];
+    CPlanDev cdev[2];
+    DevBuf<double2> cpsi[2], clam[2];
+    int ccur = 0, clcur = 0;         // buffers that hold psi / lambda
+    bool cvalid = false;             // cpsi[ccur] holds the prepared state (canonical order) of schedule cwhich
+    int cwhich = 0;
     double* scalars_p() const { return mail.p; }
     double* grad_p() const { return mail.p + MQC_MAIL_GRAD; }
     unsigned long long* flags_p() const { return reinterpret_cast<unsigned long long*>(mail.p + MQC_MAIL_FLAGS); }
@@ -281,6 +304,16 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_tile_sp2<false, true, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000)); \
     CK(cudaFuncSetAttribute(k_tile_sp2<true, true, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     MQC_SP2_ATTR(1) MQC_SP2_ATTR(2) MQC_SP2_ATTR(4)
+    CK(cudaFuncSetAttribute(k_csweep<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     s->gpu_ready = true;
@@ -693,9 +726,61 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
     s->counters[0]++;
 }
 
+// ---- compact sector storage: one launch per pass over the matrix C[alpha][beta] ---------------
+static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
+    const MqcCPlan& PL = s->cplan[which];
+    const MqcCPassDev& P = PL.pass[pass];
+    const CPlanDev& D = s->cdev[which];
+    MqcCArgs A{};
+    A.pass = D.pass.p + pass; A.cls = D.cls.p; A.fac = D.fac.p; A.maps = D.maps.p; A.tiles = D.tiles.p;
+    A.live_tab = D.live_tab.p; A.prog_hdr = D.prog_hdr.p; A.prog = D.prog.p; A.cs = s->cs.p;
+    A.psi_in = s->cpsi[s->ccur].p; A.psi_out = s->cpsi[s->ccur ^ 1].p;
+    A.lam_in = adj ? s->clam[s->clcur].p : nullptr; A.lam_out = adj ? s->clam[s->clcur ^ 1].p : nullptr;
+    A.grad = adj ? s->grad_p() : nullptr;
+    A.nB = PL.nB;
+    int nt = s->csweep_threads;
+    // small tiles do not feed many threads: most factor visits of a tile couple <= capA * capB / 4 pairs
+    while (nt > 128 && P.capA * P.capB < 2 * nt) nt >>= 1;
+    const size_t smem = mqc_c_smem_bytes(P, adj, nt / 32);
+    if (smem > 232448) throw MqcError("compact tile does not fit shared memory");
+    int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / (smem + 1024));
+    per_sm = std::max(1, std::min(per_sm, std::min(32, 2048 / nt)));
+    unsigned grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->n_sm * per_sm);
+    if (s->csweep_ctas > 0) grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->csweep_ctas);
+    CK(cudaSetDevice(s->device));
+#define MQC_CS_LAUNCH(NT_) do { if (adj) k_csweep<true, NT_><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_><<<grid, NT_, smem, s->stream>>>(A); } while (0)
+    if (nt >= 512) MQC_CS_LAUNCH(512); else if (nt >= 256) MQC_CS_LAUNCH(256); else if (nt >= 128) MQC_CS_LAUNCH(128);
+    else if (nt >= 64) MQC_CS_LAUNCH(64); else MQC_CS_LAUNCH(32);
+    s->counters[0]++;
+    s->ccur ^= 1;
+    if (adj) s->clcur ^= 1;
+}
+
+static void forward_compact(mqc_solver* s, int which, const double* theta) {
+    const int nfac = (int)s->fac.size();
+    const MqcCPlan& PL = s->cplan[which];
+    CK(cudaSetDevice(s->device));
+    if (theta) {
+        s->theta_host.assign(theta, theta + s->n_theta);
+        CK(cudaMemcpyAsync(s->theta.p, s->theta_host.data(), sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
+    }
+    if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->cs.p, nfac); s->counters[0]++; }
+    s->ccur = 0;
+    const size_t cnt = (size_t)PL.nA * PL.nB;
+    CK(cudaMemsetAsync(s->cpsi[0].p, 0, sizeof(double2) * cnt, s->stream));
+    k_set_amplitude<<<1, 32, 0, s->stream>>>(s->cpsi[0].p, (u64)PL.ref_row * PL.nB + PL.ref_col, 1.0, 0.0);
+    s->counters[0]++;
+    const int np = (int)PL.pass.size();
+    for (int p = 0; p < np; ++p) launch_csweep(s, which, p, false);
+    s->counters[1] += np;
+    s->cvalid = true; s->cwhich = which;
+    s->state_layout = -1;
+}
+
 static void forward(mqc_solver* L, int which, const double* theta) {
     if (!L->have_ansatz) throw MqcError("mqc_set_ansatz has not been called");
     require_connected(L);
+    if (L->use_compact) { forward_compact(L, which, theta); return; }
     const int nfac = (int)L->fac.size();
     for (mqc_solver* s : L->members) {
         CK(cudaSetDevice(s->device));
@@ -771,7 +856,29 @@ static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Co
     s->counters[0]++;
 }
 
+// K2 directly on the compact matrix: C = cpsi[ccur] (canonical order), Lambda -> clam[0]
+static void happly_compact(mqc_solver* s, int which, const HamView& view, bool want_lam) {
+    LayoutTables& Lt = s->lay[which];
+    const unsigned nA = s->cplan[which].nA, nB = s->cplan[which].nB;
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemsetAsync(s->scalars_p(), 0, 4 * sizeof(double), s->stream));
+    const double2* C = s->cpsi[s->ccur].p;
+    s->clcur = 0;
+    double2* Lm = want_lam ? s->clam[0].p : nullptr;
+    const SigmaTables* SG = view.SG;
+    bool have = false;
+    if (SG && SG->ready) { launch_sigma(s, SG, C, C, Lm, nB, 0u, nA, 0u, nA, 0u, 0u, 0); have = true; }
+    if (!have || SG->n_fallback) {
+        unsigned bd = 256;
+        while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
+        dim3 grid(nA, (nB + bd * MQC_HS_R - 1) / (bd * MQC_HS_R));
+        k_happly_sector<<<grid, bd, 0, s->stream>>>(C, Lm, sec_ham_dev(Lt, *view.ST), s->scalars_p(), 0u, have ? 1 : 0);
+        s->counters[0]++;
+    }
+}
+
 static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, bool want_lam) {
+    if (L->use_compact && L->cvalid && L->state_layout < 0) { happly_compact(L, which, views[0], want_lam); return; }
     const bool sec = L->conserving && L->use_sector && views[0].ST;
     const bool blocked = sec && L->blocked;
     if (blocked) {
@@ -897,6 +1004,14 @@ static void reverse_sweep(mqc_solver* L, int which) {
         CK(cudaMemsetAsync(s->grad_p(), 0, sizeof(double) * std::max(1, s->n_theta), s->stream));
     }
     const int nfac = (int)L->fac.size();
+    if (L->use_compact) {
+        const int np = (int)L->cplan[which].pass.size();
+        for (int p = np - 1; p >= 0; --p) launch_csweep(L, which, p, true);
+        L->counters[2] += np;
+        L->cvalid = false;
+        L->state_layout = -1;
+        return;
+    }
     if (L->mode == 1) {
         const int np = (int)L->sched[which].passes.size();
         bool prev_g = false;
@@ -1110,6 +1225,9 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sigma_stage") s->sigma_stage = (int)value;
     else if (k == "graph") s->use_graph = (int)value;
     else if (k == "sigma_blocked") s->sigma_blocked = (int)value;
+    else if (k == "compact") s->compact = (int)value;
+    else if (k == "csweep_threads") { if (value != 32 && value != 64 && value != 128 && value != 256 && value != 512) throw MqcError("csweep_threads must be 32, 64, 128, 256 or 512"); s->csweep_threads = (int)value; }
+    else if (k == "csweep_ctas") s->csweep_ctas = (int)value;
     else if (k == "sp2") s->sp2 = (int)value;
     else if (k == "sp2_list") s->sp2_list = (int)value;
     else if (k == "sp2_team") { if (value != 0 && value != 1 && value != 2 && value != 4) throw MqcError("sp2_team must be 0 (auto), 1, 2 or 4"); s->sp2_team = (int)value; }
@@ -1215,6 +1333,16 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         else if (s->conserving && s->mode == 1) s->plan[w] = mqc_build_sparse_plan(s->sched[w], s->na, s->nb);
         else s->plan[w] = MqcSparsePlan();
     }
+    s->use_compact = false; s->cvalid = false;
+    for (int w = 0; w < 2; ++w) s->cplan[w] = MqcCPlan();
+    if (s->compact && s->conserving && s->use_sector && s->mode == 1 && s->n_ranks == 1) {
+        bool ok = true;
+        for (int w = 0; w < 2 && ok; ++w) {
+            s->cplan[w] = mqc_build_cplan(s->sched[w], s->fac, s->na, s->nb, ref_index);
+            ok = s->cplan[w].ok && s->cplan[w].max_smem[w] <= 232448;
+        }
+        s->use_compact = ok;
+    }
     for (int w = 0; w < 2; ++w) {
         s->lay[w].reset();
         s->lay[w].phys = s->sched[w].phys_final;
@@ -1263,7 +1391,25 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
             std::vector<int> ph = s->lay[w].phys;
             s->lay[w].phys_dev.upload(ph, s->stream);
         }
-        if (s->n_ranks == 1) alloc_state(s, false);
+        for (int w = 0; w < 2; ++w) {
+            CPlanDev& D = s->cdev[w];
+            D.reset();
+            if (!s->use_compact) continue;
+            const MqcCPlan& PL = s->cplan[w];
+            D.pass.upload(PL.pass.empty() ? std::vector<MqcCPassDev>(1) : PL.pass, s->stream);
+            D.cls.upload(PL.cls, s->stream); D.fac.upload(PL.fac, s->stream); D.maps.upload(PL.maps, s->stream);
+            D.tiles.upload(PL.tiles, s->stream); D.live_tab.upload(PL.live_tab, s->stream);
+            D.prog_hdr.upload(PL.prog_hdr, s->stream); D.prog.upload(PL.prog, s->stream);
+        }
+        if (s->use_compact) {
+            const size_t cnt = (size_t)s->cplan[0].nA * s->cplan[0].nB;
+            for (int b = 0; b < 2; ++b) if (s->cpsi[b].n != cnt) s->cpsi[b].alloc(cnt);
+            for (int b = 0; b < 2; ++b) s->clam[b].release();
+            s->psi.release(); s->lam.release();          // the dense register is only allocated on demand (bridge_to_dense)
+        } else {
+            for (int b = 0; b < 2; ++b) { s->cpsi[b].release(); s->clam[b].release(); }
+            if (s->n_ranks == 1) alloc_state(s, false);
+        }
         CK(cudaStreamSynchronize(s->stream));
     } else {
         cudaGetLastError();
@@ -1404,6 +1550,11 @@ static void run_evaluation(mqc_solver* s, int which, const double* theta) {
         CK(cudaGraphLaunch(s->gexec[which], s->stream));
         for (int i = 0; i < 3; ++i) s->counters[i] = s->gcounters[which][i];
         for (mqc_solver* m : s->members) m->state_layout = which == 1 ? -1 : which;
+        if (s->use_compact) {
+            s->state_layout = -1;
+            s->cvalid = (which == 0); s->cwhich = which;
+            s->ccur = (int)(s->cplan[which].pass.size() & 1);
+        }
         return;
     }
     if (!s->eager_done[which]) {                  // first call: allocates its work buffers
@@ -1452,7 +1603,16 @@ int mqc_energy(mqc_solver_t* s, const double* theta, double* energy) {
 static void run_energy_grad(mqc_solver* s, const double* theta, double* energy, double* grad) {
     reset_counters(s);
     connect_group(s, true);
-    for (mqc_solver* m : s->members) { ensure_layout_ready(m, 1); if (!m->lam.p) { if (m->n_ranks > 1) throw MqcError("sharded handle was exported without lambda"); invalidate_graphs(m); alloc_state(m, true); } }
+    for (mqc_solver* m : s->members) {
+        ensure_layout_ready(m, 1);
+        if (m->use_compact) {
+            const size_t cnt = (size_t)m->cplan[1].nA * m->cplan[1].nB;
+            for (int b = 0; b < 2; ++b) if (m->clam[b].n != cnt) { invalidate_graphs(m); m->clam[b].alloc(cnt); }
+        } else if (!m->lam.p) {
+            if (m->n_ranks > 1) throw MqcError("sharded handle was exported without lambda");
+            invalidate_graphs(m); alloc_state(m, true);
+        }
+    }
     double val[2] = {0, 0};
     run_evaluation(s, 1, theta);
     CK(cudaSetDevice(s->device));
@@ -1502,13 +1662,35 @@ int mqc_event_elapsed_ms(mqc_solver_t* s, double* ms) {
     MQC_CATCH
 }
 
-static void ensure_state(mqc_solver* s, const double* theta) {
+// the prepared state exists: dense psi in layout state_layout, or (compact storage) cpsi[ccur]
+static void ensure_prepared(mqc_solver* s, const double* theta) {
     if (theta) { connect_group(s, false); forward(s, 0, theta); return; }
-    if (s->state_layout >= 0) return;
+    if (s->state_layout >= 0 || (s->use_compact && s->cvalid)) return;
     if ((int)s->theta_host.size() != s->n_theta || !s->have_ansatz) throw MqcError("no prepared state: pass theta");
     std::vector<double> th = s->theta_host;
     connect_group(s, false);
     forward(s, 0, th.data());
+}
+// compact storage -> dense register in the physical layout of schedule cwhich (for the consumers
+// that still address 2^N amplitudes: mqc_state and RDM sectors other than the ansatz's)
+static void bridge_to_dense(mqc_solver* s) {
+    if (!(s->use_compact && s->cvalid) || s->state_layout >= 0) return;
+    const int w = s->cwhich;
+    CK(cudaSetDevice(s->device));
+    if (!s->psi.p) { invalidate_graphs(s); s->psi.alloc(s->dim); s->peer_psi[0] = s->psi.p; }
+    LayoutTables& Lt = s->lay[w];
+    build_sector_tables(s, Lt, s->na, s->nb);
+    CK(cudaMemsetAsync(s->psi.p, 0, sizeof(double2) * s->dim, s->stream));
+    const unsigned nA = s->cplan[w].nA, nB = s->cplan[w].nB;
+    const u64 cnt = (u64)nA * nB;
+    MqcPeers PR = peers_of(s);
+    PR.lam[0] = s->psi.p;               // k_sector_scatter writes through the lambda table: point it at psi
+    k_sector_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(PR, s->cpsi[s->ccur].p, Lt.astr.p, Lt.bstr.p, 0u, nA, nB, 0u);
+    s->state_layout = w;
+}
+static void ensure_state(mqc_solver* s, const double* theta) {
+    ensure_prepared(s, theta);
+    bridge_to_dense(s);
 }
 
 int mqc_state(mqc_solver_t* s, const double* theta, double* re_im, int64_t n_amplitudes) {
@@ -1548,8 +1730,8 @@ int mqc_expectation(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask, con
     MQC_TRY
     require_gpu(L);
     if (n_terms < 0 || (n_terms && (!xmask || !zmask || !coeff_re)) || !value_re) throw MqcError("bad arguments");
-    ensure_state(L, nullptr);
-    const int w = L->state_layout;
+    ensure_prepared(L, nullptr);
+    const int w = (L->use_compact && L->cvalid && L->state_layout < 0) ? L->cwhich : L->state_layout;
     HamHost H;
     H.x.assign(xmask, xmask + n_terms);
     H.z.assign(zmask, zmask + n_terms);
@@ -1741,6 +1923,90 @@ int mqc_sigma_host_apply(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int6
     if (n_fallback) *n_fallback = (int64_t)S.fallback_terms.size();
     if (c_re_im && l_re_im)
         mqc_sigma_apply_host(S, reinterpret_cast<const double2*>(c_re_im), reinterpret_cast<double2*>(l_re_im));
+    MQC_CATCH
+}
+
+// Host-only: run the compact-sector plan of schedule `which` on the CPU (one thread) and return the
+// state in OpenFermion order (tests of the plan tables that k_csweep walks; small registers only).
+int mqc_cplan_host_state(mqc_solver_t* s, int32_t which, const double* theta, double* re_im, int64_t n_amplitudes) {
+    MQC_TRY
+    if (!s || which < 0 || which > 1 || !s->have_ansatz || !theta || !re_im) throw MqcError("bad arguments");
+    if (s->n > 24) throw MqcError("host plan execution: up to 24 qubits");
+    if ((u64)n_amplitudes != (1ull << s->n)) throw MqcError("state buffer must hold 2^N amplitudes");
+    if (!s->use_compact || !s->cplan[which].ok) throw MqcError("no compact-sector plan (the ansatz must conserve N_alpha and N_beta; option compact=1)");
+    const MqcCPlan& PL = s->cplan[which];
+    std::vector<double> cv(s->fac.size()), sv(s->fac.size());
+    for (size_t k = 0; k < s->fac.size(); ++k) { cv[k] = std::cos(theta[s->fac[k].theta]); sv[k] = std::sin(theta[s->fac[k].theta]); }
+    const std::vector<double> C = mqc_cplan_forward_host(PL, cv, sv);
+    std::memset(re_im, 0, sizeof(double) * 2 * (size_t)n_amplitudes);
+    const int n = s->n;
+    for (uint32_t ia = 0; ia < PL.nA; ++ia) for (uint32_t ib = 0; ib < PL.nB; ++ib) {
+        u64 x = 0;
+        for (int p = 0; p < PL.n_orb; ++p) {
+            if ((PL.astr[ia] >> p) & 1u) x |= 1ull << (n - 1 - 2 * p);
+            if ((PL.bstr[ib] >> p) & 1u) x |= 1ull << (n - 2 - 2 * p);
+        }
+        re_im[2 * x] = C[2 * ((size_t)ia * PL.nB + ib)]; re_im[2 * x + 1] = C[2 * ((size_t)ia * PL.nB + ib) + 1];
+    }
+    MQC_CATCH
+}
+
+int mqc_cplan_info(mqc_solver_t* s, int32_t which, int32_t* n_passes, int64_t* n_rows, int64_t* n_cols, int64_t* smem_forward,
+                   int64_t* smem_adjoint) {
+    MQC_TRY
+    if (!s || which < 0 || which > 1 || !s->have_ansatz) throw MqcError("no schedule");
+    const MqcCPlan& PL = s->cplan[which];
+    if (n_passes) *n_passes = (s->use_compact && PL.ok) ? (int32_t)PL.pass.size() : -1;
+    if (n_rows) *n_rows = PL.nA;
+    if (n_cols) *n_cols = PL.nB;
+    if (smem_forward) *smem_forward = (int64_t)PL.max_smem[0];
+    if (smem_adjoint) *smem_adjoint = (int64_t)PL.max_smem[1];
+    MQC_CATCH
+}
+
+// Replaces: nothing in the reference computes on a caller-supplied wave function except the RDM
+// routines themselves (mqc/tools/rdm.py:131-172 take `fcivec`): this loads a state vector in
+// OpenFermion order so that mqc_rdm12 / mqc_expectation run on it (golden-vector tests).
+int mqc_load_state(mqc_solver_t* s, const double* re_im, int64_t n_amplitudes) {
+    MQC_TRY
+    require_gpu(s);
+    if (!re_im || (u64)n_amplitudes != (1ull << s->n)) throw MqcError("state buffer must hold 2^N amplitudes");
+    if (s->n_ranks > 1) throw MqcError("mqc_load_state needs an unsharded handle");
+    if (!s->have_ansatz) throw MqcError("call mqc_set_ansatz first (an empty factor list fixes the sector through ref_index)");
+    if (s->n > 30) throw MqcError("mqc_load_state: up to 30 qubits");
+    CK(cudaSetDevice(s->device));
+    const int n = s->n;
+    if (s->use_compact) {
+        const MqcCPlan& PL = s->cplan[0];
+        std::vector<double2> C((size_t)PL.nA * PL.nB);
+        double norm_in = 0.0, norm_sec = 0.0;
+        for (u64 i = 0; i < (u64)n_amplitudes; ++i) norm_in += re_im[2 * i] * re_im[2 * i] + re_im[2 * i + 1] * re_im[2 * i + 1];
+        for (uint32_t ia = 0; ia < PL.nA; ++ia) for (uint32_t ib = 0; ib < PL.nB; ++ib) {
+            u64 x = 0;
+            for (int p = 0; p < PL.n_orb; ++p) {
+                if ((PL.astr[ia] >> p) & 1u) x |= 1ull << (n - 1 - 2 * p);
+                if ((PL.bstr[ib] >> p) & 1u) x |= 1ull << (n - 2 - 2 * p);
+            }
+            const double2 v = make_double2(re_im[2 * x], re_im[2 * x + 1]);
+            C[(size_t)ia * PL.nB + ib] = v;
+            norm_sec += v.x * v.x + v.y * v.y;
+        }
+        if (norm_in - norm_sec > 1e-12 * std::max(1.0, norm_in))
+            throw MqcError("mqc_load_state: the vector has weight outside the (N_alpha, N_beta) sector of the handle's reference determinant");
+        s->ccur = 0;
+        CK(cudaMemcpyAsync(s->cpsi[0].p, C.data(), sizeof(double2) * C.size(), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        s->cvalid = true; s->cwhich = 0; s->state_layout = -1;
+    } else {
+        const std::vector<int>& ph = s->lay[0].phys;
+        std::vector<double2> P((size_t)n_amplitudes);
+        for (u64 i = 0; i < (u64)n_amplitudes; ++i) P[mqc_map_mask(i, ph)] = make_double2(re_im[2 * i], re_im[2 * i + 1]);
+        if (!s->psi.p) alloc_state(s, false);
+        CK(cudaMemcpyAsync(s->psi.p, P.data(), sizeof(double2) * P.size(), cudaMemcpyHostToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        s->state_layout = 0;
+    }
+    s->theta_host.clear();              // the loaded state is not a function of the parameters
     MQC_CATCH
 }
 

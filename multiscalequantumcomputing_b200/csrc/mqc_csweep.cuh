@@ -1,0 +1,313 @@
+// K1 / K3 on the COMPACT sector matrix C[alpha string][beta string] (plan: mqc_cplan.h).
+//
+//   k_csweep<false>  forward pass:  tile rows arrive by bulk (TMA) copies global -> shared,
+//                    completion on an mbarrier; factors; scatter through the row / column map
+//                    into the layout of the next pass.
+//   k_csweep<true>   adjoint pass (reverse order, -theta) on psi and lambda together with the
+//                    gradient partials: gather through the maps (cp.async), factors, rows
+//                    leave by bulk copies shared -> global.
+//
+// One CTA owns a tile (persistent over the pass's tile list, heaviest first).  The tile's class
+// program (mqc_cplan.h) tells every thread which pair of slots to rotate for each live factor:
+// the program headers arrive with the same mbarrier transaction as the rows, the 32-bit pair
+// words are fetched coalesced from L2 three factors ahead, so that between two barriers a
+// thread only reads its two amplitudes, rotates and writes them back.  Algorithmic bytes per launch: 2 * 16 * N_det (forward),
+// 4 * 16 * N_det (adjoint) - the state is read once and written once, nothing else is touched.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mqc_common.h"
+#include "mqc_cplan.h"
+
+struct MqcCArgs {
+    const MqcCPassDev* pass;
+    const MqcCClass* cls;
+    const MqcCFactor* fac;
+    const uint32_t* maps;
+    const uint32_t* tiles;
+    const MqcCLive* live_tab;
+    const MqcCProgHdr* prog_hdr;
+    const uint32_t* prog;
+    const double2* cs;
+    const double2* psi_in;
+    double2* psi_out;
+    const double2* lam_in;
+    double2* lam_out;
+    double* grad;
+    uint32_t nB;
+};
+
+__device__ __forceinline__ uint32_t mqc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mqc_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mqc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mqc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mqc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mqc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = mqc_smem_u32(bar);
+    uint32_t done = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+// bulk copy global -> shared (TMA engine, SASS UBLKCP), bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void mqc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(mqc_smem_u32(dst)), "l"(src), "r"(bytes), "r"(mqc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mqc_bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(mqc_smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mqc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void mqc_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void mqc_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mqc_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mqc_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void mqc_cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// one pair rotation on psi (and lambda, with the gradient partial): w = slot0 | slot1 << 14 | parity << 28
+template <bool ADJ>
+__device__ __forceinline__ double mqc_rotate_pair(double2* __restrict__ sp, double2* __restrict__ sl, const uint32_t w,
+                                                  const double c, const double s) {
+    const int e0 = (int)(w & 0x3fffu), e1 = (int)((w >> 14) & 0x3fffu);
+    const bool neg = ((w >> 28) & 1u) != 0u;
+    const double ssn = neg ? -s : s;
+    const double2 a = sp[e0], b = sp[e1];
+    double g = 0.0;
+    if (ADJ) {
+        const double2 xa = sl[e0], xb = sl[e1];
+        const double gv = xb.x * a.x + xb.y * a.y - xa.x * b.x - xa.y * b.y;
+        g = neg ? -gv : gv;                      // pair parity alone (the tile sign is applied at the flush)
+        sl[e0] = make_double2(c * xa.x - ssn * xb.x, c * xa.y - ssn * xb.y);
+        sl[e1] = make_double2(c * xb.x + ssn * xa.x, c * xb.y + ssn * xa.y);
+    }
+    sp[e0] = make_double2(c * a.x - ssn * b.x, c * a.y - ssn * b.y);
+    sp[e1] = make_double2(c * b.x + ssn * a.x, c * b.y + ssn * a.y);
+    return g;
+}
+
+template <bool ADJ, int NT>
+__global__ void __launch_bounds__(NT, (1024 / NT) > 16 ? 16 : (1024 / NT))
+k_csweep(const __grid_constant__ MqcCArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const MqcCPassDev* __restrict__ P = A.pass;
+    const int nf = P->nf, strideB = P->strideB, capA = P->capA, capB = P->capB;
+    const uint32_t nB = A.nB;
+    // ---- shared memory carve-up (mqc_c_smem_bytes) -------------------------------------------
+    unsigned char* q = smem_raw;
+    double2* sp = reinterpret_cast<double2*>(q);              q += (size_t)capA * strideB * 16;
+    double2* sl = reinterpret_cast<double2*>(q);              if (ADJ) q += (size_t)capA * strideB * 16;
+    uint2* shdr = reinterpret_cast<uint2*>(q);                q += ((size_t)P->max_live * 8 + 15) & ~(size_t)15;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(q);          q += (size_t)MQC_C_RING_SLOTS * MQC_C_CHUNK * 4;
+    double2* hcs = reinterpret_cast<double2*>(q);             q += (size_t)nf * 16;
+    unsigned char* hsg = q;                                   q += ((size_t)nf + 15) & ~(size_t)15;
+    uint32_t* smap = reinterpret_cast<uint32_t*>(q);          q += ((size_t)(capA + capB) * 4 + 15) & ~(size_t)15;
+    const size_t gw_stride = (((size_t)nf * 8 + 15) & ~(size_t)15) / 8;
+    double* gw = reinterpret_cast<double*>(q);                if (ADJ) q += (size_t)NW * gw_stride * 8;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(q);           // [0] tile rows + headers, [1 ..] ring slots
+    uint64_t* rbar = bar + 1;
+    constexpr uint32_t RMASK = MQC_C_RING_SLOTS * MQC_C_CHUNK - 1;
+
+    if (tid == 0) {
+        for (int i = 0; i <= MQC_C_RING_SLOTS; ++i) mqc_mbar_init(bar + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (ADJ) for (int i = tid; i < (int)(NW * gw_stride); i += NT) gw[i] = 0.0;
+    __syncthreads();
+    uint32_t phase = 0, phbits = 0;
+
+    const uint32_t n_tiles = P->n_tiles;
+    for (uint32_t it = blockIdx.x; it < n_tiles; it += gridDim.x) {
+        uint32_t ia, ib;
+        if (P->tiles_explicit) { const uint32_t t = __ldg(A.tiles + P->tile_off + it); ia = t & 0xffffu; ib = t >> 16; }
+        else { ia = it / (uint32_t)P->n_clsB; ib = it - ia * (uint32_t)P->n_clsB; }
+        const uint4 ca4 = __ldg(reinterpret_cast<const uint4*>(A.cls + P->clsA_off + ia));
+        const uint4 cb4 = __ldg(reinterpret_cast<const uint4*>(A.cls + P->clsB_off + ib));
+        const uint32_t row0 = ca4.x, umask = ca4.y, col0 = cb4.x, vmask = cb4.y;
+        const int ka = (int)(ca4.z & 0xffffu), nAl = (int)(ca4.z >> 16), kb = (int)(cb4.z & 0xffffu), nBl = (int)(cb4.z >> 16);
+        const uint4 lt4 = __ldg(reinterpret_cast<const uint4*>(A.live_tab + P->live_tab_off + (size_t)ka * MQC_C_KMAX + kb));
+        const int n_live = (int)lt4.y;
+        const uint32_t* __restrict__ prog = A.prog + lt4.z;          // this class's pair words
+        const int NC = (int)((lt4.w + MQC_C_CHUNK - 1) / MQC_C_CHUNK);   // chunks of the program
+        int issued = 0, have = 0;                                    // chunks (processing order) issued / arrived
+        auto issue_chunk = [&](int k) {
+            const int c = ADJ ? NC - 1 - k : k;
+            const int slot = c & (MQC_C_RING_SLOTS - 1);
+            const uint32_t words = min((uint32_t)MQC_C_CHUNK, lt4.w - (uint32_t)c * MQC_C_CHUNK);
+            mqc_mbar_expect_tx(rbar + slot, words * 4u);
+            mqc_bulk_g2s(ring + slot * MQC_C_CHUNK, prog + (size_t)c * MQC_C_CHUNK, words * 4u, rbar + slot);
+        };
+        // last chunk (processing order) a step needs
+        auto k_hi = [&](const uint2 h) -> int {
+            const int c_lo = (int)(h.x / MQC_C_CHUNK), c_hi = (int)((h.x + (h.y & 0xffffu) - 1u) / MQC_C_CHUNK);
+            return ADJ ? NC - 1 - c_lo : c_hi;
+        };
+        auto k_lo = [&](const uint2 h) -> int {
+            const int c_lo = (int)(h.x / MQC_C_CHUNK), c_hi = (int)((h.x + (h.y & 0xffffu) - 1u) / MQC_C_CHUNK);
+            return ADJ ? NC - 1 - c_hi : c_lo;
+        };
+        auto wait_chunks = [&](int k_need) {
+            while (have <= k_need) {
+                const int c = ADJ ? NC - 1 - have : have;
+                const int slot = c & (MQC_C_RING_SLOTS - 1);
+                mqc_mbar_wait(rbar + slot, (phbits >> slot) & 1u);
+                phbits ^= 1u << slot;
+                ++have;
+            }
+        };
+        const uint32_t magicB = mqc_c_magic((uint32_t)nBl);
+        const int cnt = nAl * nBl;
+
+        // ---- asynchronous fetch: program headers (and the rows, forward) -> one mbarrier phase ------
+        if (warp == 0) {
+            const uint32_t bH = ((uint32_t)n_live * 8u + 15u) & ~15u;
+            if (lane == 0) {
+                mqc_fence_async();              // generic-proxy accesses of the previous tile before async-proxy writes
+                mqc_mbar_expect_tx(bar, bH + (ADJ ? 0u : (uint32_t)cnt * 16u));
+            }
+            __syncwarp();
+            if (lane == 31 && bH) mqc_bulk_g2s(shdr, A.prog_hdr + lt4.x, bH, bar);
+            if (lane == 0) { for (; issued < NC && issued < MQC_C_RING_SLOTS; ++issued) issue_chunk(issued); }
+            if (!ADJ)
+                for (int ja = lane; ja < nAl; ja += 32)
+                    mqc_bulk_g2s(sp + (size_t)ja * strideB, A.psi_in + (size_t)(row0 + ja) * nB + col0, (uint32_t)nBl * 16u, bar);
+        }
+        // ---- per-tile factor constants and the tile's row / column map ------------------------------
+        for (int f = tid; f < nf; f += NT) {
+            const uint4 F = __ldg(reinterpret_cast<const uint4*>(A.fac + P->fac_off + f));
+            const uint32_t sg = ((uint32_t)__popc(umask & F.x) + (uint32_t)__popc(vmask & F.y) + (F.w >> 31)) & 1u;
+            const double2 v = A.cs[(int)F.z];
+            const double sn = ADJ ? -v.y : v.y;
+            hcs[f] = make_double2(v.x, sg ? -sn : sn);
+            hsg[f] = (unsigned char)sg;
+        }
+        for (int i = tid; i < nAl + nBl; i += NT)
+            smap[i] = i < nAl ? (P->row_identity ? row0 + i : __ldg(A.maps + P->map_row_off + row0 + i))
+                              : (P->col_identity ? col0 + (i - nAl) : __ldg(A.maps + P->map_col_off + col0 + (i - nAl)));
+        if (ADJ) {
+            __syncthreads();
+            for (int e = tid; e < cnt; e += NT) {
+                const int ja = (nBl == 1) ? e : (int)__umulhi((uint32_t)e, magicB), jb = e - ja * nBl;
+                const size_t g = (size_t)smap[ja] * nB + smap[nAl + jb];
+                mqc_cp_async16(sp + ja * strideB + jb, A.psi_in + g);
+                mqc_cp_async16(sl + ja * strideB + jb, A.lam_in + g);
+            }
+            mqc_cp_async_wait_all();
+        }
+        mqc_mbar_wait(bar, phase);
+        phase ^= 1u;
+        __syncthreads();
+
+        // ---- factors: step i of the class program = header (first word, pairs | factor << 16) + its
+        //      pair words in the ring; the thread's first word of step i + 1 is read before the barrier
+        //      that ends step i, so between two barriers a thread only rotates ----------------------------
+        if (n_live > 0) {
+            auto step = [&](int i) -> int { return ADJ ? n_live - 1 - i : i; };
+            uint2 hc = shdr[step(0)];
+            wait_chunks(k_hi(hc));
+            uint32_t wc = ring[(hc.x + (uint32_t)tid) & RMASK];
+            for (int i0 = 0; i0 < n_live; i0 += 8) {
+                double acc8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc8[j] = 0.0;
+                    const int i = i0 + j;
+                    if (i < n_live) {                                   // uniform over the CTA
+                        const uint32_t npairs = hc.y & 0xffffu;
+                        const double2 csv = hcs[hc.y >> 16];
+                        uint2 hn = hc;
+                        uint32_t wn = 0u;
+                        if (i + 1 < n_live) {
+                            hn = shdr[step(i + 1)];
+                            wait_chunks(k_hi(hn));
+                            wn = ring[(hn.x + (uint32_t)tid) & RMASK];
+                        }
+                        double gacc = 0.0;
+                        if ((uint32_t)tid < npairs) gacc = mqc_rotate_pair<ADJ>(sp, sl, wc, csv.x, csv.y);
+                        for (uint32_t u = (uint32_t)tid + NT; u < npairs; u += NT)
+                            gacc += mqc_rotate_pair<ADJ>(sp, sl, ring[(hc.x + u) & RMASK], csv.x, csv.y);
+                        if (ADJ) acc8[j] = gacc;
+                        __syncthreads();
+                        if (tid == 0 && issued < NC) {                  // chunks before the next step's first are free
+                            const int kfree = k_lo(hn);
+                            if (issued - MQC_C_RING_SLOTS < kfree) {
+                                mqc_fence_async();
+                                for (; issued < NC && issued - MQC_C_RING_SLOTS < kfree; ++issued) issue_chunk(issued);
+                            }
+                        }
+                        hc = hn; wc = wn;
+                    }
+                }
+                if (ADJ) {
+                    // transposed butterfly: eight per-lane partials -> one total per lane group
+                    // (9 double shuffles instead of 40); lane L with (L & 3) == 0 ends up with
+                    // the total of factor j = 4 * bit4(L) + 2 * bit3(L) + bit2(L)
+                    double w4[4], w2r[2], w1r;
+                    {
+                        const bool hi = (lane & 16) != 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double send = hi ? acc8[j] : acc8[j + 4], keep = hi ? acc8[j + 4] : acc8[j];
+                            w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+                    }
+                    {
+                        const bool hi = (lane & 8) != 0;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const double send = hi ? w4[j] : w4[j + 2], keep = hi ? w4[j + 2] : w4[j];
+                            w2r[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+                    }
+                    {
+                        const bool hi = (lane & 4) != 0;
+                        const double send = hi ? w2r[0] : w2r[1], keep = hi ? w2r[1] : w2r[0];
+                        w1r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    w1r += __shfl_xor_sync(0xffffffffu, w1r, 2);
+                    w1r += __shfl_xor_sync(0xffffffffu, w1r, 1);
+                    const int j = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                    if ((lane & 3) == 0 && i0 + j < n_live && w1r != 0.0) {
+                        const int f = (int)(shdr[step(i0 + j)].y >> 16);
+                        gw[(size_t)warp * gw_stride + f] += hsg[f] ? -w1r : w1r;
+                    }
+                }
+            }
+        }
+
+        // ---- store ------------------------------------------------------------------------------------
+        if (!ADJ) {
+            for (int e = tid; e < cnt; e += NT) {
+                const int ja = (nBl == 1) ? e : (int)__umulhi((uint32_t)e, magicB), jb = e - ja * nBl;
+                A.psi_out[(size_t)smap[ja] * nB + smap[nAl + jb]] = sp[ja * strideB + jb];
+            }
+        } else {
+            // rows leave by bulk copies (generic-proxy writes made visible to the async proxy first)
+            mqc_fence_async();
+            __syncthreads();
+            if (warp == 0) {
+                for (int ja = lane; ja < nAl; ja += 32) {
+                    mqc_bulk_s2g(A.psi_out + (size_t)(row0 + ja) * nB + col0, sp + (size_t)ja * strideB, (uint32_t)nBl * 16u);
+                    mqc_bulk_s2g(A.lam_out + (size_t)(row0 + ja) * nB + col0, sl + (size_t)ja * strideB, (uint32_t)nBl * 16u);
+                }
+                mqc_bulk_commit();
+                mqc_bulk_wait_read();
+            }
+        }
+        __syncthreads();            // the tile buffers, headers and maps are free for the next tile
+    }
+    if (ADJ) {
+        // one global atomic per (CTA, factor)
+        for (int f = tid; f < nf; f += NT) {
+            double g = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) g += gw[(size_t)w * gw_stride + f];
+            if (g != 0.0) atomicAdd(A.grad + (A.fac[P->fac_off + f].theta_sign & 0x7fffffff), 2.0 * g);
+        }
+    }
+}
