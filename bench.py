@@ -408,6 +408,7 @@ def run_ours(args):
             if world > 1:
                 raise RuntimeError("reported at N=1 only")
             hd = _lib.Handle(factors.n_qubits, local)
+            hd.set_option("compact", 0)
             hd.set_option("sparse_tiles", 0)
             hd.set_hamiltonian(*table)
             hd.set_ansatz(factors.kind, factors.idx, factors.theta_index, factors.n_theta, factors.ref_index)

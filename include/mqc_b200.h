@@ -91,6 +91,14 @@ int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value);
 int mqc_set_hamiltonian(mqc_solver_t* s, int64_t n_terms, const uint64_t* xmask,
                         const uint64_t* zmask, const double* coeff_re, const double* coeff_im);
 
+/* Replaces: the re-construction of `DMET(...)` for the SAME fragment at the next chemical
+ * potential / DMET iteration (mqc/third_party/qcdmet.py:244-260 calls the solver again and the
+ * reference rebuilds everything, mqc/solver/dmet_interface.py:45-128).  Same Pauli strings, in
+ * the same order, as the last mqc_set_hamiltonian; only the coefficients change.  The handle
+ * keeps its ansatz, sweep schedules, plans and device buffers. */
+int mqc_update_hamiltonian_coeffs(mqc_solver_t* s, int64_t n_terms, const double* coeff_re,
+                                  const double* coeff_im);
+
 /* Replaces: `reference(imp, options)` + `ADAPT(options['ansatz'], imp, pool, ref)`,
  * mqc/solver/dmet_solver_vqechem.py:63-65, for a fixed factor list. */
 int mqc_set_ansatz(mqc_solver_t* s, int32_t n_factors, const int32_t* kind, const int32_t* idx4,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "mqc_set_option": [_H, C.c_char_p, C.c_int64],
     "mqc_set_hamiltonian": [_H, C.c_int64, _u64p, _u64p, _f64p, _f64p],
     "mqc_set_ansatz": [_H, C.c_int32, _i32p, _i32p, _i32p, C.c_int32, C.c_uint64],
+    "mqc_update_hamiltonian_coeffs": [_H, C.c_int64, _f64p, _f64p],
     "mqc_energy": [_H, _f64p, _f64p],
     "mqc_energy_grad": [_H, _f64p, _f64p, _f64p],
     "mqc_energy_grad_resident": [_H, _f64p],
@@ -161,6 +162,13 @@ class Handle:
         cr = np.ascontiguousarray(c.real)
         ci = np.ascontiguousarray(c.imag)
         check(self.lib.mqc_set_hamiltonian(self.h, len(x), ptr(x, _u64p), ptr(z, _u64p), ptr(cr, _f64p), ptr(ci, _f64p)))
+
+    def update_hamiltonian_coeffs(self, coeff):
+        """New coefficients for the Pauli strings of the last set_hamiltonian (same order)."""
+        c = np.asarray(coeff, dtype=np.complex128)
+        cr = np.ascontiguousarray(c.real)
+        ci = np.ascontiguousarray(c.imag)
+        check(self.lib.mqc_update_hamiltonian_coeffs(self.h, len(c), ptr(cr, _f64p), ptr(ci, _f64p)))
 
     def set_ansatz(self, kind, idx, theta_index, n_theta, ref_index):
         k = np.ascontiguousarray(kind, dtype=np.int32)

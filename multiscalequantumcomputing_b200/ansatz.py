@@ -36,6 +36,23 @@ class UCCSDAnsatz:
         self._cache = None
         self.n_evals = 0
 
+    def set_hamiltonian(self, term_table):
+        """Next chemical-potential step / DMET iteration of the same fragment shape: keep the handle
+        (ansatz, schedules, plans, buffers) and replace the Hamiltonian.  When the Pauli strings are
+        unchanged only the coefficients travel (`mqc_update_hamiltonian_coeffs`)."""
+        x, z, c = term_table
+        same = len(x) == len(self.xmask) and np.array_equal(x, self.xmask) and np.array_equal(z, self.zmask)
+        self.xmask, self.zmask, self.coeff = x, z, c
+        if same:
+            self.handle.update_hamiltonian_coeffs(c)
+        else:
+            self.handle.set_hamiltonian(x, z, c)
+        self._cache_theta = None
+        self._cache = None
+        self._niter = 0
+        self.n_evals = 0
+        self.n_handle_reuses = getattr(self, "n_handle_reuses", 0) + 1
+
     # -- reference surface ------------------------------------------------------------
     def get_nparams_opt(self):
         return self.factors.n_theta

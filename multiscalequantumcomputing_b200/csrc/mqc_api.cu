@@ -174,7 +174,7 @@ struct mqc_solver {
     int sp2 = 1, sp2_warps = 4, sp2_list = 1, sp2_smem_kb = 220, sp2_team = 0;
     // compact sector storage (mqc_cplan.h): the state is the matrix C[alpha string][beta string];
     // cpsi / clam ping-pong between the layouts of consecutive passes
-    int compact = 1, csweep_threads = 256, csweep_ctas = 0;
+    int compact = 1, csweep_threads = 128, csweep_ctas = 0;
     bool use_compact = false;
     MqcCPlan cplan[2];
     CPlanDev cdev[2];
@@ -1263,6 +1263,24 @@ int mqc_set_hamiltonian(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask,
         s->ham.c.resize(n_terms);
         for (int64_t t = 0; t < n_terms; ++t) s->ham.c[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
         s->have_ham = true;
+        s->lay[0].ham_ready = s->lay[1].ham_ready = false;
+        s->lay[0].sham_ready = s->lay[1].sham_ready = false;
+        s->sig.ready = false;
+        invalidate_graphs(s);
+    }
+    MQC_CATCH
+}
+
+// Same Pauli strings as the last mqc_set_hamiltonian, new coefficients (a chemical-potential step
+// or the next DMET iteration of the same fragment): the handle, its ansatz, sweep schedules,
+// plans and state buffers stay; only the Hamiltonian tables are rebuilt.
+int mqc_update_hamiltonian_coeffs(mqc_solver_t* L, int64_t n_terms, const double* coeff_re, const double* coeff_im) {
+    MQC_TRY
+    if (!L || !coeff_re) throw MqcError("bad arguments");
+    if (!L->have_ham) throw MqcError("mqc_set_hamiltonian has not been called");
+    if ((size_t)n_terms != L->ham.x.size()) throw MqcError("mqc_update_hamiltonian_coeffs: term count differs from the stored Pauli strings");
+    for (mqc_solver* s : L->members) {
+        for (int64_t t = 0; t < n_terms; ++t) s->ham.c[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
         s->lay[0].ham_ready = s->lay[1].ham_ready = false;
         s->lay[0].sham_ready = s->lay[1].sham_ready = false;
         s->sig.ready = false;

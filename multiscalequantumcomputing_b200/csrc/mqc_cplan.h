@@ -28,6 +28,8 @@
 // has nothing to decode.  ~8 MB for the whole 24-qubit UCCSD sweep (L2 resident).
 #pragma once
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <vector>
@@ -60,7 +62,7 @@ struct MqcCLive {              // class (ka, kb) -> its program
 // The pair words of a class program are contiguous in step order: the kernel streams them through
 // a shared-memory ring of MQC_C_RING_SLOTS chunks of MQC_C_CHUNK words (bulk copies, one mbarrier
 // per slot); a step may straddle at most MQC_C_RING_SLOTS - 1 chunks.
-#define MQC_C_CHUNK 1024
+#define MQC_C_CHUNK 256
 #define MQC_C_RING_SLOTS 4
 #define MQC_C_MAX_STEP_PAIRS (((MQC_C_RING_SLOTS - 1) * MQC_C_CHUNK) / 2)     // two consecutive steps fit the ring
 struct MqcCPassDev {
@@ -100,6 +102,36 @@ static inline void mqc_c_strings(int n_orb, int k, std::vector<uint32_t>& out) {
         const u64 c = v & (~v + 1ull), r = v + c;
         v = (((r ^ v) >> 2) / c) | r;
     }
+}
+
+// The pairs of a step are independent, so their order is free: arrange them so that the eight
+// threads of a quarter-warp (one 128-byte shared-memory wavefront of 16-byte amplitudes) hit eight
+// different bank groups, for the lower AND the upper partner (greedy, bounded look-ahead).
+static inline void mqc_c_bank_order(std::vector<uint32_t>& w) {
+    const size_t n = w.size();
+    if (n < 3) return;
+    std::vector<char> used(n, 0);
+    std::vector<uint32_t> out;
+    out.reserve(n);
+    size_t first = 0;
+    while (out.size() < n) {
+        unsigned m0 = 0, m1 = 0;
+        for (int slot = 0; slot < 8 && out.size() < n; ++slot) {
+            while (first < n && used[first]) ++first;
+            size_t pick = n, seen = 0;
+            for (size_t c = first; c < n && seen < 96; ++c) {
+                if (used[c]) continue;
+                ++seen;
+                const unsigned b0 = 1u << (w[c] & 7u), b1 = 1u << ((w[c] >> 14) & 7u);
+                if (!(m0 & b0) && !(m1 & b1)) { pick = c; break; }
+            }
+            if (pick == n) pick = first;
+            used[pick] = 1;
+            m0 |= 1u << (w[pick] & 7u); m1 |= 1u << ((w[pick] >> 14) & 7u);
+            out.push_back(w[pick]);
+        }
+    }
+    w.swap(out);
 }
 
 // shared memory of one CTA (bytes) for a pass; must match the carve-up in k_csweep
@@ -284,11 +316,15 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
                 H.np_f = (uint32_t)(LA.size() * LB.size()) | ((uint32_t)f << 16);
                 if (LA.size() * LB.size() > (size_t)MQC_C_MAX_STEP_PAIRS) return PL;
                 PL.prog_hdr.push_back(H);
+                std::vector<uint32_t> words;
+                words.reserve(LA.size() * LB.size());
                 for (uint32_t la : LA) for (uint32_t lb : LB) {
                     const uint32_t e0 = (la & 0x7fu) * (uint32_t)D.strideB + (lb & 0x7fu);
                     const uint32_t e1 = ((la >> 7) & 0x7fu) * (uint32_t)D.strideB + ((lb >> 7) & 0x7fu);
-                    PL.prog.push_back(e0 | (e1 << 14) | ((((la ^ lb) >> 14) & 1u) << 28));
+                    words.push_back(e0 | (e1 << 14) | ((((la ^ lb) >> 14) & 1u) << 28));
                 }
+                mqc_c_bank_order(words);
+                PL.prog.insert(PL.prog.end(), words.begin(), words.end());
                 Lv.cnt++;
             }
             while (PL.prog.size() & 3) PL.prog.push_back(0);

@@ -219,18 +219,20 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
                     const int i = i0 + j;
                     if (i < n_live) {                                   // uniform over the CTA
                         const uint32_t npairs = hc.y & 0xffffu;
-                        const double2 csv = hcs[hc.y >> 16];
                         uint2 hn = hc;
                         uint32_t wn = 0u;
                         if (i + 1 < n_live) {
                             hn = shdr[step(i + 1)];
                             wait_chunks(k_hi(hn));
-                            wn = ring[(hn.x + (uint32_t)tid) & RMASK];
                         }
                         double gacc = 0.0;
-                        if ((uint32_t)tid < npairs) gacc = mqc_rotate_pair<ADJ>(sp, sl, wc, csv.x, csv.y);
-                        for (uint32_t u = (uint32_t)tid + NT; u < npairs; u += NT)
-                            gacc += mqc_rotate_pair<ADJ>(sp, sl, ring[(hc.x + u) & RMASK], csv.x, csv.y);
+                        if ((uint32_t)(warp * 32) < npairs) {           // warps without a pair in this step only keep step
+                            const double2 csv = hcs[hc.y >> 16];
+                            if ((uint32_t)tid < npairs) gacc = mqc_rotate_pair<ADJ>(sp, sl, wc, csv.x, csv.y);
+                            for (uint32_t u = (uint32_t)tid + NT; u < npairs; u += NT)
+                                gacc += mqc_rotate_pair<ADJ>(sp, sl, ring[(hc.x + u) & RMASK], csv.x, csv.y);
+                        }
+                        if ((uint32_t)(warp * 32) < (hn.y & 0xffffu)) wn = ring[(hn.x + (uint32_t)tid) & RMASK];
                         if (ADJ) acc8[j] = gacc;
                         __syncthreads();
                         if (tid == 0 && issued < NC) {                  // chunks before the next step's first are free

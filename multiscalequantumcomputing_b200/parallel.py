@@ -34,10 +34,16 @@ def assign_round_robin(n_items: int, n_workers: int):
     return [list(range(w, n_items, n_workers)) for w in range(n_workers)]
 
 
-def solve_fragments(problems: Sequence, devices: Sequence[int] = None, solver: Callable = None, **kw):
+def solve_fragments(problems: Sequence, devices: Sequence[int] = None, solver: Callable = None, fragment_ids=None, **kw):
     """Solve every fragment problem, one per GPU at a time.  Returns [(E_imp, rdm1), ...] in input
-    order.  ``solver(*args, device=d, **kw)`` defaults to the CUDA `solve`."""
+    order.  ``solver(*args, device=d, **kw)`` defaults to the CUDA `solve`.
+
+    ``fragment_ids``: ``True`` (problem i is fragment i) or a list of hashable ids: the solver keeps one
+    GPU handle and one warm-start vector per fragment across calls (successive chemical-potential
+    steps and DMET iterations re-use them, `solver.solve(fragment_id=...)`)."""
     solver = solver or solve
+    if fragment_ids is True:
+        fragment_ids = list(range(len(problems)))
     if devices is None:
         n = _lib.device_count()
         if n == 0:
@@ -49,7 +55,8 @@ def solve_fragments(problems: Sequence, devices: Sequence[int] = None, solver: C
 
     def work(w):
         for i in plan[w]:
-            out[i] = solver(*_as_args(problems[i]), device=devices[w], **kw)
+            extra = {} if fragment_ids is None else {"fragment_id": ("frag", fragment_ids[i])}
+            out[i] = solver(*_as_args(problems[i]), device=devices[w], **extra, **kw)
 
     if len(devices) == 1:
         work(0)

@@ -21,7 +21,9 @@ consumed internally (`:75-81`).  Differences, all deliberate (SURVEY.md §0, §7
 """
 from __future__ import annotations
 
+import threading
 import time
+import warnings
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -70,6 +72,9 @@ class imp_optimizer:
                 result = minimize(ansatz.energy, params, method=self._method, jac=ansatz.gradient,
                                   options=options, callback=ansatz.callback)
                 params = result["x"]
+                if not result.get("success", True) and float(np.abs(result["jac"]).max()) > 100 * self._cgtol:
+                    warnings.warn("VQE parameter optimisation stopped without converging: %s (max |g| = %.2e)"
+                                  % (result.get("message", ""), float(np.abs(result["jac"]).max())))
             converged = self.check_converged(ansatz, result)
             if converged:
                 self.print_info(ansatz, result)
@@ -99,6 +104,8 @@ def embedding_mos(fock_mu, tei, n_elec):
     """RHF in the embedding space (pattern of dmet_solver_fci.py:28-42): gives the
     occupied/virtual split UCCSD needs."""
     e_el, mo_e, C, dm, ok = rhf(fock_mu, tei, n_elec, conv=1e-12)
+    if not ok:
+        warnings.warn("embedding RHF did not converge: the UCCSD reference determinant is built on unconverged orbitals")
     # fix the gauge so that CPU-oracle and GPU runs see identical orbitals
     for k in range(C.shape[1]):
         j = np.argmax(np.abs(C[:, k]))
@@ -140,22 +147,49 @@ def finish_solve(rdm1_mo, rdm2_mo, C, oei_mo, one_body_mo, two_body_mo, n_imp_or
     return float(e), rdm1, rdm2
 
 
+# Per-fragment persistent state: QC-DMET calls the solver again for the same
+# fragment at every chemical-potential step and DMET iteration (`mqc/third_party/qcdmet.py:244-260`)
+# and the reference rebuilds everything each time (`mqc/solver/dmet_interface.py:45-128`).  A caller
+# that passes ``fragment_id`` gets (a) its GPU handle back - ansatz, sweep schedules, plans, buffers
+# stay, only the Hamiltonian coefficients travel (`mqc_update_hamiltonian_coeffs`) - and (b) its own
+# warm-start parameters.  Handles are not thread safe: one fragment id must not be solved from two
+# threads at the same time (`parallel.solve_fragments` keeps fragment i on worker i mod W).
+_LOCK = threading.Lock()
 _WARM = {}
+_HANDLES = {}
+STATS = {"handle_creates": 0, "handle_reuses": 0}
+
+
+def _cache_key(fragment_id, n_orb, n_elec, device, options):
+    gpu = tuple(sorted(((options or {}).get("gpu") or {}).items()))
+    devs = tuple((options or {}).get("devices") or ())
+    return (fragment_id, n_orb, n_elec, device, gpu, devs)
 
 
 def solve(oei_mo, one_body_mo, two_body_mo, n_imp: int, n_imp_orbs: int, chempot_imp=0.0,
-          skip_vqe: bool = True, *, device: int = 0, options=None, theta0=None, warm_start=True,
-          return_details=False, verbose=False, _ansatz_factory=None):
+          skip_vqe: bool = True, *, device: int = 0, options=None, theta0=None, warm_start=None,
+          fragment_id=None, return_details=False, verbose=False, _ansatz_factory=None):
+    """``fragment_id`` (any hashable) switches on the per-fragment cache: the GPU handle is re-used
+    across calls and, unless ``warm_start=False``, the optimisation starts from this fragment's last
+    parameters.  Without it every call is independent of every other (the reference's behaviour);
+    ``warm_start=True`` without a fragment id is refused because fragments of equal shape would seed
+    each other."""
     t0 = time.perf_counter()
     n_elec = int(n_imp)                      # the reference's n_imp IS the electron count (:21)
     if chempot_imp is None:
         chempot_imp = 0.0
+    if warm_start is None:
+        warm_start = fragment_id is not None
+    if warm_start and fragment_id is None:
+        raise ValueError("warm_start=True needs fragment_id: the warm-start store is per fragment")
     prob = prepare_problem(one_body_mo, two_body_mo, n_elec, n_imp_orbs, chempot_imp)
     n_orb, factors = prob["n_orb"], prob["factors"]
     n_qubits = 2 * n_orb
     if verbose:
         print("running %d qubit uccsd calculation" % n_qubits)
     kind = (options or {}).get("ansatz", "uccsd")
+    key = _cache_key(fragment_id, n_orb, n_elec, device, options)
+    cached = False
     if kind == "adapt":
         # the reference's default: ADAPT-VQE, Nu operators per macro iteration (dmet_solver_vqechem.py:35-41)
         from .adapt import ADAPTAnsatz
@@ -165,13 +199,31 @@ def solve(oei_mo, one_body_mo, two_body_mo, n_imp: int, n_imp_orbs: int, chempot
                              backend=_ansatz_factory)
         warm_start = False
     else:
-        # options["devices"] = [0, 1, ...]: shard the fragment's state vector over these GPUs
-        make = _ansatz_factory or (lambda nq, tab, fac: UCCSDAnsatz(nq, tab, fac, device=device, options=(options or {}).get("gpu"),
-                                                                    devices=(options or {}).get("devices")))
-        ansatz = make(n_qubits, prob["table"], factors)
-    key = (n_orb, n_elec, n_imp_orbs, device)
-    if theta0 is None and warm_start and key in _WARM and len(_WARM[key]) == factors.n_theta:
-        theta0 = _WARM[key]
+        ansatz = None
+        if fragment_id is not None and _ansatz_factory is None:
+            with _LOCK:
+                ansatz = _HANDLES.get(key)
+        if ansatz is not None:
+            ansatz.set_hamiltonian(prob["table"])
+            ansatz._params = np.zeros(factors.n_theta)
+            cached = True
+            with _LOCK:
+                STATS["handle_reuses"] += 1
+        else:
+            # options["devices"] = [0, 1, ...]: shard the fragment's state vector over these GPUs
+            make = _ansatz_factory or (lambda nq, tab, fac: UCCSDAnsatz(nq, tab, fac, device=device, options=(options or {}).get("gpu"),
+                                                                        devices=(options or {}).get("devices")))
+            ansatz = make(n_qubits, prob["table"], factors)
+            with _LOCK:
+                STATS["handle_creates"] += 1
+                if fragment_id is not None and _ansatz_factory is None:
+                    _HANDLES[key] = ansatz
+                    cached = True
+    if theta0 is None and warm_start:
+        with _LOCK:
+            w = _WARM.get(key)
+        if w is not None and len(w) == factors.n_theta:
+            theta0 = w
     if theta0 is not None:
         ansatz._params = np.array(theta0, dtype=np.float64)
     t1 = time.perf_counter()
@@ -179,7 +231,8 @@ def solve(oei_mo, one_body_mo, two_body_mo, n_imp: int, n_imp_orbs: int, chempot
     ansatz, params = opt.run(ansatz)
     t2 = time.perf_counter()
     if warm_start:
-        _WARM[key] = np.array(params)
+        with _LOCK:
+            _WARM[key] = np.array(params)
     ansatz.prepare(params)
     n_alpha = n_elec // 2                      # noa / nob split of dmet_interface.py:84-85
     rdm1_mo, rdm2_mo = ansatz.rdm12(n_orb, n_alpha, n_elec - n_alpha)
@@ -195,13 +248,26 @@ def solve(oei_mo, one_body_mo, two_body_mo, n_imp: int, n_imp_orbs: int, chempot
                            n_evals=getattr(ansatz, "n_evals", 0), n_theta=ansatz.get_nparams_opt(),
                            n_terms=len(prob["table"][0]), mo_coeff=prob["C"],
                            t_setup=t1 - t0, t_opt=t2 - t1, t_rdm=t3 - t2)
-        if hasattr(ansatz, "close"):
+        if hasattr(ansatz, "close") and not cached:
             ansatz.close()
         return e_imp, rdm1, det
-    if hasattr(ansatz, "close"):
+    if hasattr(ansatz, "close") and not cached:
         ansatz.close()
     return e_imp, rdm1
 
 
 def clear_warm_start():
-    _WARM.clear()
+    with _LOCK:
+        _WARM.clear()
+
+
+def clear_handle_cache():
+    """Destroy the cached per-fragment GPU handles (end of a DMET run)."""
+    with _LOCK:
+        hs = list(_HANDLES.values())
+        _HANDLES.clear()
+    for a in hs:
+        try:
+            a.close()
+        except Exception:
+            pass

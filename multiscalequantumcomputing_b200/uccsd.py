@@ -45,17 +45,30 @@ class FactorList:
         return out
 
 
+def electron_split(n_elec: int):
+    """noa = N // 2, nob = N - noa (`mqc/solver/dmet_interface.py:84-85`): an odd electron count
+    puts the extra electron into the beta string."""
+    noa = n_elec // 2
+    return noa, n_elec - noa
+
+
+def occupied_qubits(n_elec: int):
+    noa, nob = electron_split(n_elec)
+    return sorted([2 * p for p in range(noa)] + [2 * p + 1 for p in range(nob)])
+
+
 def reference_index(n_qubits: int, n_elec: int) -> int:
-    """Qubits 0..n_elec-1 occupied; qubit 0 is the most significant index bit
-    (`test/testlog_vqe:25`: index 240 for N=8, N_e=4)."""
-    return (1 << n_qubits) - (1 << (n_qubits - n_elec))
+    """Lowest noa alpha and nob beta spin orbitals occupied; qubit 0 is the most significant index
+    bit.  Even N: qubits 0..N-1 (`test/testlog_vqe:25`: index 240 for N=8, N_e=4)."""
+    return sum(1 << (n_qubits - 1 - q) for q in occupied_qubits(n_elec))
 
 
 def _all_excitations(n_orb: int, n_elec: int):
-    assert n_elec % 2 == 0, "closed-shell reference expected (noa = nob, dmet_interface.py:84-85)"
     nq = 2 * n_orb
-    occ = list(range(n_elec))
-    vir = list(range(n_elec, nq))
+    if n_elec < 0 or n_elec > nq or electron_split(n_elec)[1] > n_orb:
+        raise ValueError("cannot place %d electrons in %d spatial orbitals" % (n_elec, n_orb))
+    occ = occupied_qubits(n_elec)
+    vir = [q for q in range(nq) if q not in set(occ)]
     singles = [(i, a) for i in occ for a in vir if i % 2 == a % 2]
     doubles = []
     for i, j in combinations(occ, 2):
@@ -93,12 +106,15 @@ def uccsd_factors(n_orb: int, n_elec: int, order: str = "blocked", block_orbs: i
     if order == "lex":
         seq = [(1, s + (-1, -1)) for s in singles] + [(2, d) for d in doubles]
     elif order == "blocked":
-        nocc, nvir = n_elec // 2, n_orb - n_elec // 2
+        # spatial orbitals that hold an occupied / an empty spin orbital (they overlap in the singly
+        # occupied orbital of an odd-electron reference)
+        noa, nob = electron_split(n_elec)
+        nocc, nvir = nob, n_orb - noa
         so = min(nocc, block_orbs // 2)
         sv = min(nvir, block_orbs - so)
         so = min(nocc, block_orbs - sv)
-        occ_blocks = _pair_cover(range(nocc), so)
-        vir_blocks = _pair_cover(range(nocc, n_orb), sv)
+        occ_blocks = _pair_cover(range(nocc), max(so, 1)) if nocc else [()]
+        vir_blocks = _pair_cover(range(noa, n_orb), max(sv, 1)) if nvir else [()]
         seq = []
         done = set()
         flip = False

@@ -57,7 +57,8 @@ class OracleAnsatz:
         self._psi = self.orc.state(np.asarray(theta))
 
     def rdm12(self, n_orb, n_alpha, n_beta, want_rdm2=True):
-        assert n_alpha == n_beta
+        if n_alpha != n_beta:           # rdm.py's string tables are closed-shell (Sz = 0): literal ladder operators instead
+            return ordm.rdm12_bruteforce(self._psi, n_orb)
         return ordm.get_rdm12(self._psi, n_alpha + n_beta, n_orb)
 
     def expectation(self, table):

@@ -91,3 +91,31 @@ def test_24_qubit_plan_shape():
     assert i0["n_passes"] == len(h.schedule(0)["passes"]) and i1["n_passes"] == len(h.schedule(1)["passes"])
     assert i0["smem_forward"] < 64 * 1024 and i1["smem_adjoint"] < 100 * 1024       # several CTAs per SM
     h.close()
+
+
+@pytest.mark.parametrize("n,ne", [(4, 3), (5, 5), (6, 3)])
+def test_odd_electron_reference(n, ne):
+    """noa = N // 2, nob = N - noa (`mqc/solver/dmet_interface.py:84-85`): open-shell reference
+    determinant, UCCSD singles / doubles from it, compact plan against the oracle state."""
+    from multiscalequantumcomputing_b200.uccsd import electron_split, occupied_qubits
+    F = uccsd_factors(n, ne, "blocked")
+    noa, nob = electron_split(ne)
+    assert (noa, nob) == (ne // 2, ne - ne // 2) and nob == noa + 1
+    occ = occupied_qubits(ne)
+    assert sum(1 for q in occ if q % 2 == 0) == noa and sum(1 for q in occ if q % 2 == 1) == nob
+    assert F.ref_index == sum(1 << (2 * n - 1 - q) for q in occ)
+    for k, ix in zip(F.kind, F.idx):                 # every factor excites occupied -> virtual, spin conserved
+        qs = [int(v) for v in (ix[:2] if k == 1 else ix)]
+        src, dst = (qs[:1], qs[1:]) if k == 1 else (qs[:2], qs[2:])
+        assert all(q in occ for q in src) and all(q not in occ for q in dst)
+        assert sorted(q % 2 for q in src) == sorted(q % 2 for q in dst)
+    h = _lib.Handle(2 * n)
+    h.set_option("tile_bits", 6)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    from math import comb
+    info = h.cplan_info(0)
+    assert (info["n_rows"], info["n_cols"]) == (comb(n, noa), comb(n, nob))
+    th = np.random.default_rng(3).normal(0, 0.2, F.n_theta)
+    ref = UCCSDOracle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, EMPTY).state(th)
+    assert abs(h.cplan_host_state(th, 0) - ref).max() < 1e-14
+    h.close()

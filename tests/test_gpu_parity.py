@@ -35,23 +35,35 @@ def _setup(n, ne, order="blocked", opts=None, seed=1234, s2=0.25):
     return h, orc, F, tab, th
 
 
+# options without "compact": 0 run the compact-sector path (k_csweep) whenever the ansatz conserves
+# (N_alpha, N_beta); "compact": 0 keeps the dense-register kernels (sharded states, non-conserving
+# ansaetze) under the same checks
 CASES = [
     (4, 4, "blocked", {}),                                       # 8 qubits: whole register in one tile
+    (4, 2, "lex", {"tile_bits": 6, "grad_tile_bits": 6}),         # compact, several passes of small tiles
+    (5, 4, "blocked", {"tile_bits": 7, "grad_tile_bits": 6, "csweep_threads": 32}),
+    (6, 6, "lex", {"tile_bits": 9, "grad_tile_bits": 8, "csweep_threads": 64}),
+    (6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "csweep_ctas": 3}),    # persistent CTAs loop over many tiles
+    (7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 9, "csweep_threads": 256}),
+    (8, 8, "lex", {"tile_bits": 12, "grad_tile_bits": 10}),
+    (6, 2, "blocked", {"tile_bits": 8, "grad_tile_bits": 8}),                     # dilute sector
+    (8, 8, "blocked", {"sigma": 0}),                                               # compact state + X-group H kernel
+    (4, 4, "blocked", {"compact": 0}),
     (4, 4, "lex", {"mode": 0}),                                  # one factor per pass
-    (4, 2, "lex", {"tile_bits": 6, "grad_tile_bits": 6, "low_bits": 2}),
-    (5, 4, "blocked", {"tile_bits": 7, "grad_tile_bits": 7, "low_bits": 3}),
-    (6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "low_bits": 2}),
-    (6, 6, "lex", {"tile_bits": 9, "grad_tile_bits": 8, "low_bits": 3}),
+    (4, 2, "lex", {"tile_bits": 6, "grad_tile_bits": 6, "low_bits": 2, "compact": 0}),
+    (5, 4, "blocked", {"tile_bits": 7, "grad_tile_bits": 7, "low_bits": 3, "compact": 0}),
+    (6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "low_bits": 2, "compact": 0}),
+    (6, 6, "lex", {"tile_bits": 9, "grad_tile_bits": 8, "low_bits": 3, "compact": 0}),
     (6, 6, "lex", {"mode": 0}),
     (6, 6, "blocked", {"sector": 0}),                            # dense H|psi> path
-    (7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 9}),
-    (8, 8, "blocked", {}),                                       # 16 qubits, default 12/11-bit tiles
-    (8, 8, "blocked", {"grad_tile_bits": 12, "tile_threads": 512}),
-    (6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "sp2": 0}),           # first-generation sector tiles
-    (8, 8, "blocked", {"sp2": 0, "sigma": 0}),                                     # ... and X-group H kernel
-    (7, 6, "lex", {"tile_bits": 10, "grad_tile_bits": 9, "sp2_warps": 2}),
-    (6, 2, "blocked", {"tile_bits": 8, "grad_tile_bits": 8}),                     # dilute sector
-    (7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 10, "sp2_list": 0, "sigma_stage": 0}),   # large-register paths
+    (7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 9, "compact": 0}),
+    (8, 8, "blocked", {"compact": 0}),                            # 16 qubits, dense register, sector tiles
+    (8, 8, "blocked", {"grad_tile_bits": 12, "tile_threads": 512, "compact": 0}),
+    (6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 7, "sp2": 0, "compact": 0}),           # first-generation sector tiles
+    (8, 8, "blocked", {"sp2": 0, "sigma": 0, "compact": 0}),                                     # ... and X-group H kernel
+    (7, 6, "lex", {"tile_bits": 10, "grad_tile_bits": 9, "sp2_warps": 2, "compact": 0}),
+    (6, 2, "blocked", {"tile_bits": 8, "grad_tile_bits": 8, "compact": 0}),                     # dilute sector
+    (7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 10, "sp2_list": 0, "sigma_stage": 0, "compact": 0}),   # large-register paths
 ]
 
 
@@ -97,20 +109,81 @@ def test_rdm12(n, ne):
 
 
 def test_rdm_golden_vector(golden):
-    """The logged VQE wave function (test/testlog_vqe:56-91) through the GPU RDM kernels
-    reproduces the logged rdm1 / rdm2 (test/testlog_vqe:99-185) to the printed digits."""
-    # prepare that state exactly: put it in as the "reference" is impossible (36 amplitudes),
-    # so compare through the oracle on a UCCSD state instead and check the golden separately
+    """The logged VQE wave function (test/testlog_vqe:56-94) loaded into the GPU (mqc_load_state)
+    and pushed through the GPU RDM kernels reproduces the reference's logged rdm1 / rdm2
+    (test/testlog_vqe:98-185) to the printed digits, and the oracle's float64 RDMs to 1e-12;
+    both storage forms of the state (compact sector matrix, dense register)."""
     strs = np.array(golden["ring_strings"]["values"])
     fc = np.array(golden["ring_fcivec"]["values"])
     o1, o2 = ordm.make_rdm12(fc, 4, strs)
-    assert abs(o1 - np.array(golden["ring_vqe_rdm1"]["values"])).max() < 6e-4
-    ints = local_integrals(hydrogen_ring(10, 1.0))
-    p = fragment_problems(ints, atom_clusters(10, 2), 0.0, True)[0]
-    e_imp, rdm1, det = solve(p.oei, p.fock, p.tei, p.nelec, p.n_imp_orbs, 0.0, return_details=True, warm_start=False)
-    # UCCSD is within 2e-6 Ha of the logged ADAPT/FCI state, so its RDMs match the dump too
-    assert abs(np.sort(np.linalg.eigvalsh(rdm1)) - np.sort(np.linalg.eigvalsh(o1))).max() < 2e-3
-    assert abs(e_imp - golden["ring_fci"]["e_imp"][0]) < 1e-4
+    psi = np.zeros(256, dtype=np.complex128)
+    for st, c in zip(strs, fc):
+        psi[ordm.qubit_inverse(4, int(st))] = c
+    g1 = np.array(golden["ring_vqe_rdm1"]["values"])
+    g2 = np.array(golden["ring_vqe_rdm2"]["values"])
+    for compact in (1, 0):
+        h = _lib.Handle(8)
+        h.set_option("compact", compact)
+        h.set_ansatz(np.zeros(0, np.int32), np.zeros((0, 4), np.int32), np.zeros(0, np.int32), 0, 240)
+        h.load_state(psi)
+        assert abs(h.state() - psi).max() == 0.0
+        r1, r2 = h.rdm12(4, 2, 2)
+        assert abs(r1 - g1).max() < 6e-4 and abs(r2 - g2).max() < 6e-4          # the reference's own dump
+        assert abs(r1 - o1).max() < 1e-12 and abs(r2 - o2).max() < 1e-12        # float64 restatement of rdm.py
+        # <H> of the loaded state through K2
+        ints = local_integrals(hydrogen_ring(10, 1.0))
+        p = fragment_problems(ints, atom_clusters(10, 2), 0.0, True)[0]
+        tab = fragment_term_table(p.fock, p.tei, 0, 0.0, 0.0)
+        e_k2 = h.expectation(*tab).real
+        assert abs(e_k2 - np.vdot(psi, apply_terms(*tab, psi)).real) < 1e-12
+        h.close()
+    # a vector outside the handle's sector is refused by the compact storage
+    h = _lib.Handle(8)
+    h.set_ansatz(np.zeros(0, np.int32), np.zeros((0, 4), np.int32), np.zeros(0, np.int32), 0, 240)
+    bad = np.zeros(256, dtype=np.complex128); bad[255] = 1.0
+    with pytest.raises(_lib.MqcError):
+        h.load_state(bad)
+    h.close()
+
+
+def _c_oracle_check(tab, F, th, e, g):
+    from oracle.cref import CRefUCCSD, use_all_cores
+    use_all_cores()
+    ref = CRefUCCSD(F.n_qubits, F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index, tab)
+    e_ref, g_ref, _ = ref.energy_grad_sector(th)
+    assert abs(e - e_ref) < E_TOL, (e, e_ref)
+    assert np.abs(g - g_ref).max() < G_TOL
+
+
+def test_24_qubits_against_c_oracle():
+    """BASELINE.json configs[2] at FULL size - the workload bench.py quotes (H12 chain, 24 qubits,
+    1 818 parameters): energy 1e-10 and gradient 1e-9 against one complete evaluation of the CPU
+    oracle (oracle/c, sector-aware variant, validated against the numpy oracle in test_oracle_c.py)."""
+    import bench
+    tab, F, th, _ = bench.workload()
+    h = _lib.Handle(F.n_qubits)
+    h.set_hamiltonian(*tab)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    assert h.cplan_info(1)["n_passes"] > 0                      # the compact-sector path is the one under test
+    e, g = h.energy_grad(th)
+    _c_oracle_check(tab, F, th, e, g)
+    h.close()
+
+
+def test_24_qubits_generic_instance_against_c_oracle():
+    """The seeded generic C3 instance of SURVEY.md §8d (rng 1234: 29 737 Pauli terms in 5 479
+    X-groups, twice the K2 work of the H12 chain), lexicographic factor order."""
+    n = 12
+    tab = fragment_term_table(*random_fragment_integrals(n, 1234), 0, 0.0, 0.25)
+    assert len(tab[0]) > 29000
+    F = uccsd_factors(n, n, "lex")
+    th = np.random.default_rng(4321).normal(0, 0.05, F.n_theta)
+    h = _lib.Handle(2 * n)
+    h.set_hamiltonian(*tab)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    e, g = h.energy_grad(th)
+    _c_oracle_check(tab, F, th, e, g)
+    h.close()
 
 
 def test_expectation_s2_and_linearity():
@@ -148,7 +221,7 @@ def test_properties_20_qubits():
         assert abs(fd - g[k]) < 1e-6
     # fused tile sweep == one-factor-per-pass sweep
     h0 = _lib.Handle(2 * n)
-    h0.set_option("mode", 0)
+    h0.set_option("mode", 0)                                # also leaves the compact storage: dense register
     h0.set_hamiltonian(*tab)
     h0.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
     e0, g0 = h0.energy_grad(th)
@@ -231,6 +304,7 @@ def test_properties_24_qubits_full_size():
     assert abs(e_rdm - e_bare) < 1e-9
     # other execution paths of the same evaluation
     hd = _lib.Handle(2 * n)
+    hd.set_option("compact", 0)
     hd.set_option("sparse_tiles", 0)
     hd.set_hamiltonian(*tab)
     hd.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
@@ -300,3 +374,64 @@ def test_open_shell_sector_and_generalized_factors(n, occ):
     e_bare = h.expectation(*fragment_term_table(h1, eri, 0, 0.0, 0.0)).real
     assert abs(np.einsum("pq,pq->", h1, r1) + 0.5 * np.einsum("pqrs,pqrs->", eri, r2) - e_bare) < 1e-9
     h.close()
+
+
+@pytest.mark.parametrize("n,ne", [(4, 3), (5, 5), (6, 3)])
+def test_odd_electron_fragment(n, ne):
+    """Open-shell fragment (noa = N // 2, nob = N - noa, `mqc/solver/dmet_interface.py:84-85`):
+    state, energy, gradient and RDMs against the oracle; then the drop-in solve() on it."""
+    h, orc, F, tab, th = _setup(n, ne, "blocked", {"tile_bits": 7, "grad_tile_bits": 6})
+    assert abs(h.state(th) - orc.state(th)).max() < S_TOL
+    e_ref, g_ref = orc.energy_grad(th)
+    e, g = h.energy_grad(th)
+    assert abs(e - e_ref) < E_TOL and abs(g - g_ref).max() < G_TOL
+    h.prepare(th)
+    r1, r2 = h.rdm12(n, ne // 2, ne - ne // 2)
+    b1, b2 = ordm.rdm12_bruteforce(orc.state(th), n)
+    assert abs(r1 - b1).max() < R_TOL and abs(r2 - b2).max() < R_TOL
+    assert abs(np.trace(r1) - ne) < 1e-10
+    h.close()
+    h1, eri = random_fragment_integrals(n, 21)
+    e1, d1 = solve(h1, h1, eri, ne, 2, 0.01)
+    e2, d2 = solve(h1, h1, eri, ne, 2, 0.01, _ansatz_factory=lambda nq, t, f: OracleAnsatz(nq, t, f))
+    assert abs(e1 - e2) < 1e-8 and abs(d1 - d2).max() < 1e-6
+    assert abs(np.trace(d1) - ne) < 1e-8
+
+
+def test_update_hamiltonian_coeffs_and_handle_cache():
+    """Per-fragment persistent state: a second Hamiltonian with the same Pauli
+    strings only sends coefficients (mqc_update_hamiltonian_coeffs) and gives the same numbers as
+    a fresh handle; solve(fragment_id=...) creates ONE handle per fragment over a whole DMET run."""
+    from multiscalequantumcomputing_b200 import solver as S
+    n, ne = 6, 6
+    h, orc, F, tab, th = _setup(n, ne, "blocked", {"tile_bits": 8, "grad_tile_bits": 8})
+    e0, g0 = h.energy_grad(th)
+    h1, eri = random_fragment_integrals(n, 77)
+    tab2 = fragment_term_table(h1, eri, 0, 0.0, 0.25)
+    assert np.array_equal(tab2[0], tab[0]) and np.array_equal(tab2[1], tab[1])
+    h.update_hamiltonian_coeffs(tab2[2])
+    e1, g1 = h.energy_grad(th)
+    orc2 = UCCSDOracle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, tab2)
+    e_ref, g_ref = orc2.energy_grad(th)
+    assert abs(e1 - e_ref) < E_TOL and abs(g1 - g_ref).max() < G_TOL and abs(e1 - e0) > 1e-3
+    h.update_hamiltonian_coeffs(tab[2])
+    e2, g2 = h.energy_grad(th)
+    assert abs(e2 - e0) < 1e-13 and abs(g2 - g0).max() < 1e-13
+    with pytest.raises(_lib.MqcError):
+        h.update_hamiltonian_coeffs(tab[2][:-1])
+    h.close()
+    # whole DMET loop: handles are created once per fragment, every later mu step re-uses them
+    ints = local_integrals(hydrogen_chain(10, 0.9))
+    cl = atom_clusters(10, 2)
+    S.clear_handle_cache(); S.clear_warm_start()
+    S.STATS["handle_creates"] = S.STATS["handle_reuses"] = 0
+    from multiscalequantumcomputing_b200.parallel import solve_fragments
+    run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[0], fragment_ids=True))
+    e_cached = run.run()
+    assert S.STATS["handle_creates"] == len(cl)
+    assert S.STATS["handle_reuses"] == run.n_solves - len(cl) and S.STATS["handle_reuses"] > 0
+    S.clear_handle_cache(); S.clear_warm_start()
+    ref = DMETRun(ints, cl, solver=lambda *a: solve(*a))
+    assert abs(e_cached - ref.run()) < 1e-8
+    with pytest.raises(ValueError):
+        solve(ints.h_loc[:4, :4], ints.h_loc[:4, :4], ints.eri_loc[:4, :4, :4, :4], 4, 2, 0.0, warm_start=True)

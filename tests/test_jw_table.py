@@ -8,7 +8,7 @@ from oracle.fermion import to_label_form, jordan_wigner, FermionOperator
 from oracle.hamiltonian import qubit_hamiltonian, qubit_s2, term_table
 
 
-@pytest.mark.parametrize("n,mu,s2", [(2, 0.0, 0.0), (4, 0.0, 0.0), (4, 0.013, 0.25), (5, -0.2, 0.25)])
+@pytest.mark.parametrize("n,mu,s2", [(2, 0.0, 0.0), (4, 0.0, 0.0), (4, 0.013, 0.25), (5, -0.2, 0.25), (6, 0.01, 0.25)])
 def test_table_matches_oracle(n, mu, s2):
     h1, eri = random_fragment_integrals(n, 99 + n)
     xm, zm, cf = term_table(qubit_hamiltonian(h1, eri, n // 2, mu, s2), 2 * n, 1e-14)
