@@ -291,6 +291,41 @@ def variant_legs(device, opts, steps=5):
     return rows
 
 
+def sharded_legs(rank, world, local):
+    """Collective.  The state vector of ONE fragment split over the N ranks (CUDA IPC peer mapping,
+    flag barrier, rank-bit passes over NVLink): 30 qubits energy + adjoint gradient with an in-run
+    parity check against the unsharded evaluation on rank 0; on 8 ranks also 34 qubits (energy +
+    gradient) and 36 qubits (energy, 1.1 TB dense register, row-distributed sector matrix for K2)."""
+    from multiscalequantumcomputing_b200 import _lib
+    from multiscalequantumcomputing_b200.shardbench import problem, sharded_point
+    out = {"points": [], "note": "strong scaling: one fragment, fixed size, N ranks; times are CUDA-event maxima over ranks"}
+    try:
+        p = sharded_point(15, "grad", rank, world, local, steps=2, warmup=1, keep_gradient=True)
+        g_sh = p.pop("_gradient")
+        if rank == 0:
+            ne, F, th, tab = problem(15)
+            h1 = _lib.Handle(30, local)
+            h1.set_hamiltonian(*tab)
+            h1.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+            e1, g1 = h1.energy_grad(th)
+            e1, g1 = h1.energy_grad(th)
+            t1 = h1.last_timing()
+            h1.close()
+            p["parity_vs_one_rank"] = {"dE": abs(p["value"] - e1), "max_dg": float(np.abs(g_sh - g1).max()),
+                                       "one_rank_ms": t1["total_ms"], "one_rank_storage": "compact sector matrix"}
+            assert p["parity_vs_one_rank"]["dE"] < 1e-10 and p["parity_vs_one_rank"]["max_dg"] < 1e-9, p["parity_vs_one_rank"]
+            p["speedup_vs_one_rank"] = t1["total_ms"] / p["ms"]["total"]
+        out["points"].append(p)
+        if world == 8:
+            out["points"].append(sharded_point(17, "grad", rank, world, local, steps=1, warmup=1))
+            out["points"].append(sharded_point(18, "energy", rank, world, local, steps=1, warmup=1))
+    except AssertionError:
+        raise
+    except Exception as exc:
+        out["error"] = "%s: %s" % (type(exc).__name__, exc)
+    return out
+
+
 def run_ours(args):
     import torch
     from multiscalequantumcomputing_b200 import _lib
@@ -361,6 +396,10 @@ def run_ours(args):
         tt = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms, wall_ms = (float(v) for v in tt.cpu())
+    # ---- sharded state (BASELINE.json configs[4]): strong scaling of ONE evaluation over the N ranks -------
+    sharded = None
+    if use_dist and not args.no_sharded:
+        sharded = sharded_legs(rank, world, local)
     ms_step = dev_ms / args.steps
     value = world * 1e3 / ms_step
     e2e_val = world * 1e3 / (e2e_ms / args.steps)
@@ -476,7 +515,7 @@ def run_ours(args):
                        "d2h_bytes_per_step": int(grad_pin.numel() * 8 + 16), "ms_per_step": e2e_ms / args.steps},
                "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                "clocks": clocks, "roofline": roof, "roofline_streaming": streaming, "cpu_baseline": cpu,
-               "dmet_iteration": dmet, "reference_style_scipy_sparse": ref_small, "variants": variants,
+               "dmet_iteration": dmet, "reference_style_scipy_sparse": ref_small, "variants": variants, "sharded": sharded,
                "parity_note": "UCCSD energies / gradients are parity-unpinned by the reference (it runs ADAPT-VQE at 8 qubits "
                               "only); they are pinned by the CPU oracle: cpu_baseline.gpu_vs_cpu_dE / _max_dg of THIS run",
                "energy": e_ref, "setup_s": setup_s}
@@ -493,6 +532,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. sparse_tiles=0)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded-state legs of an N > 1 run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

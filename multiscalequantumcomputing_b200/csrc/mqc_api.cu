@@ -18,6 +18,7 @@
 #include "mqc_sigma.h"
 #include "mqc_cplan.h"
 #include "mqc_csweep.cuh"
+#include "mqc_rdm.cuh"
 
 static thread_local std::string g_err;
 
@@ -160,7 +161,8 @@ struct mqc_solver {
     double2* peer_cown[MQC_MAX_RANKS] = {};
     int sigma_blocked = -1;          // -1 auto, 0 replicate C on every rank, 1 distribute its rows
     bool blocked = false, connected_cown = false;
-    DevBuf<double> theta, mail, red, rdm_acc;
+    DevBuf<double> theta, mail, red, rdm_acc, rdm_gpart, rdm_g1part, rdm_out;
+    int rdm_gram = 1;                // K4 on the compact matrix as a Gram update (mqc_rdm.cuh); 0: literal loops with atomics
     DevBuf<int> theta_index, err;
     DevBuf<MqcTileFactor> tf[2];
     DevBuf<uint16_t> dlut[2];       // pair-address tables of the dense tile kernel
@@ -304,16 +306,13 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_tile_sp2<false, true, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000)); \
     CK(cudaFuncSetAttribute(k_tile_sp2<true, true, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     MQC_SP2_ATTR(1) MQC_SP2_ATTR(2) MQC_SP2_ATTR(4)
-    CK(cudaFuncSetAttribute(k_csweep<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    CK(cudaFuncSetAttribute(k_csweep<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+#define MQC_CS_ATTR(NT_, CH_) \
+    CK(cudaFuncSetAttribute(k_csweep<false, NT_, CH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); \
+    CK(cudaFuncSetAttribute(k_csweep<true, NT_, CH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    MQC_CS_ATTR(32, 256) MQC_CS_ATTR(64, 256) MQC_CS_ATTR(128, 256) MQC_CS_ATTR(256, 256) MQC_CS_ATTR(512, 256)
+    MQC_CS_ATTR(32, 1024) MQC_CS_ATTR(64, 1024) MQC_CS_ATTR(128, 1024) MQC_CS_ATTR(256, 1024) MQC_CS_ATTR(512, 1024)
+    CK(cudaFuncSetAttribute(k_rdm_gram<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_rdm_gram<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     s->gpu_ready = true;
@@ -741,14 +740,16 @@ static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     int nt = s->csweep_threads;
     // small tiles do not feed many threads: most factor visits of a tile couple <= capA * capB / 4 pairs
     while (nt > 128 && P.capA * P.capB < 2 * nt) nt >>= 1;
-    const size_t smem = mqc_c_smem_bytes(P, adj, nt / 32);
+    const size_t smem = mqc_c_smem_bytes(P, adj, nt / 32, PL.chunk);
     if (smem > 232448) throw MqcError("compact tile does not fit shared memory");
     int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / (smem + 1024));
     per_sm = std::max(1, std::min(per_sm, std::min(32, 2048 / nt)));
     unsigned grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->n_sm * per_sm);
     if (s->csweep_ctas > 0) grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->csweep_ctas);
     CK(cudaSetDevice(s->device));
-#define MQC_CS_LAUNCH(NT_) do { if (adj) k_csweep<true, NT_><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_><<<grid, NT_, smem, s->stream>>>(A); } while (0)
+#define MQC_CS_LAUNCH(NT_) do { \
+        if (PL.chunk == 256) { if (adj) k_csweep<true, NT_, 256><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_, 256><<<grid, NT_, smem, s->stream>>>(A); } \
+        else { if (adj) k_csweep<true, NT_, 1024><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_, 1024><<<grid, NT_, smem, s->stream>>>(A); } } while (0)
     if (nt >= 512) MQC_CS_LAUNCH(512); else if (nt >= 256) MQC_CS_LAUNCH(256); else if (nt >= 128) MQC_CS_LAUNCH(128);
     else if (nt >= 64) MQC_CS_LAUNCH(64); else MQC_CS_LAUNCH(32);
     s->counters[0]++;
@@ -1226,6 +1227,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "graph") s->use_graph = (int)value;
     else if (k == "sigma_blocked") s->sigma_blocked = (int)value;
     else if (k == "compact") s->compact = (int)value;
+    else if (k == "rdm_gram") s->rdm_gram = (int)value;
     else if (k == "csweep_threads") { if (value != 32 && value != 64 && value != 128 && value != 256 && value != 512) throw MqcError("csweep_threads must be 32, 64, 128, 256 or 512"); s->csweep_threads = (int)value; }
     else if (k == "csweep_ctas") s->csweep_ctas = (int)value;
     else if (k == "sp2") s->sp2 = (int)value;
@@ -1358,6 +1360,7 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         for (int w = 0; w < 2 && ok; ++w) {
             s->cplan[w] = mqc_build_cplan(s->sched[w], s->fac, s->na, s->nb, ref_index);
             ok = s->cplan[w].ok && s->cplan[w].max_smem[w] <= 232448;
+            if (!ok && getenv("MQC_DEBUG")) fprintf(stderr, "[mqc] compact plan %d not used: %s (smem %zu)\n", w, s->cplan[w].why, s->cplan[w].max_smem[w]);
         }
         s->use_compact = ok;
     }
@@ -1791,7 +1794,42 @@ int mqc_rdm12(mqc_solver_t* L, int32_t n_orb, int32_t n_alpha, int32_t n_beta, d
     require_gpu(L);
     if (!rdm1) throw MqcError("null rdm1");
     if (2 * n_orb != L->n) throw MqcError("n_orb must be n_qubits / 2");
-    ensure_state(L, nullptr);
+    ensure_prepared(L, nullptr);
+    if (L->use_compact && L->cvalid && L->state_layout < 0 && L->rdm_gram && n_alpha == L->na && n_beta == L->nb && n_orb <= 31) {
+        // compact storage: Gram-matrix form, no atomics (mqc_rdm.cuh)
+        mqc_solver* s = L;
+        CK(cudaSetDevice(s->device));
+        LayoutTables& Lt = s->lay[s->cwhich];
+        build_sector_tables(s, Lt, n_alpha, n_beta);
+        const int n2i = n_orb * n_orb;
+        const int T = n2i <= 144 ? 9 : 8, BS = 16 * T;
+        const int nblk = (n2i + BS - 1) / BS;
+        MqcRdmC R{};
+        R.C = s->cpsi[s->ccur].p; R.aorb = Lt.aorb.p; R.borb = Lt.borb.p; R.rank_a = Lt.rank_a.p; R.rank_b = Lt.rank_b.p;
+        R.nA = s->cplan[s->cwhich].nA; R.nB = s->cplan[s->cwhich].nB; R.n = n_orb; R.n2 = n2i; R.nblk = nblk;
+        const u64 n_blocks = (u64)R.nA * ((R.nB + MQC_RDM_KB - 1) / MQC_RDM_KB);
+        const int groups = (int)std::min<u64>(n_blocks, (u64)std::max(1, s->n_sm / (nblk * nblk)));
+        const size_t gsz = (size_t)groups * nblk * nblk * BS * BS, g1sz = (size_t)groups * n2i;
+        if (s->rdm_gpart.n < gsz) s->rdm_gpart.alloc(gsz);
+        if (s->rdm_g1part.n < g1sz) s->rdm_g1part.alloc(g1sz);
+        const size_t n2s = (size_t)n2i, n4s = n2s * n2s;
+        if (s->rdm_out.n < n2s + n4s) s->rdm_out.alloc(n2s + n4s);
+        R.gpart = s->rdm_gpart.p; R.g1part = s->rdm_g1part.p;
+        CK(cudaMemsetAsync(s->rdm_g1part.p, 0, sizeof(double) * g1sz, s->stream));
+        const size_t smem = (size_t)(nblk > 1 ? 2 : 1) * MQC_RDM_KB * BS * sizeof(double2);
+        dim3 grid(groups, nblk * nblk);
+        if (T == 9) k_rdm_gram<9><<<grid, MQC_RDM_THREADS, smem, s->stream>>>(R);
+        else k_rdm_gram<8><<<grid, MQC_RDM_THREADS, smem, s->stream>>>(R);
+        const size_t work = rdm2 ? n4s : n2s;
+        k_rdm_finish<<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->rdm_gpart.p, s->rdm_g1part.p, groups, n_orb, nblk, BS,
+                                                                          s->rdm_out.p, rdm2 ? s->rdm_out.p + n2s : nullptr);
+        CK(cudaMemcpyAsync(rdm1, s->rdm_out.p, sizeof(double) * n2s, cudaMemcpyDeviceToHost, s->stream));
+        if (rdm2) CK(cudaMemcpyAsync(rdm2, s->rdm_out.p + n2s, sizeof(double) * n4s, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        s->counters[0] += 2;
+        return 0;
+    }
+    bridge_to_dense(L);
     sync_all(L);
     const int w = L->state_layout;
     const size_t n2 = (size_t)n_orb * n_orb, n4 = n2 * n2;

@@ -62,9 +62,9 @@ struct MqcCLive {              // class (ka, kb) -> its program
 // The pair words of a class program are contiguous in step order: the kernel streams them through
 // a shared-memory ring of MQC_C_RING_SLOTS chunks of MQC_C_CHUNK words (bulk copies, one mbarrier
 // per slot); a step may straddle at most MQC_C_RING_SLOTS - 1 chunks.
-#define MQC_C_CHUNK 256
+// The chunk is 256 words when every step has <= 384 pairs (7 + 7 active orbitals), else 1024.
 #define MQC_C_RING_SLOTS 4
-#define MQC_C_MAX_STEP_PAIRS (((MQC_C_RING_SLOTS - 1) * MQC_C_CHUNK) / 2)     // two consecutive steps fit the ring
+#define MQC_C_MAX_STEP_PAIRS(chunk) (((MQC_C_RING_SLOTS - 1) * (chunk)) / 2)     // two consecutive steps fit the ring
 struct MqcCPassDev {
     int32_t nf, n_clsA, n_clsB, strideB;
     int32_t capA, capB, row_identity, col_identity;
@@ -86,7 +86,10 @@ struct MqcCPlan {
     std::vector<MqcCProgHdr> prog_hdr;       // per class: headers of its live factors, sequence order (even count: 16-byte units)
     std::vector<uint32_t> prog;              // pair words
     std::vector<uint32_t> astr, bstr;        // canonical (ascending) strings, orbital space
+    int chunk = 256;                         // pair words per ring slot (256 or 1024)
+    uint32_t max_step_pairs = 0;
     size_t max_smem[2] = {0, 0};             // shared memory a CTA needs: forward, adjoint (any pass)
+    const char* why = "";                    // why ok == false
 };
 
 MQC_HD uint32_t mqc_c_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)(0xFFFFFFFFu / d) + 1u; }
@@ -135,12 +138,12 @@ static inline void mqc_c_bank_order(std::vector<uint32_t>& w) {
 }
 
 // shared memory of one CTA (bytes) for a pass; must match the carve-up in k_csweep
-static inline size_t mqc_c_smem_bytes(const MqcCPassDev& P, bool adj, int n_warps) {
+static inline size_t mqc_c_smem_bytes(const MqcCPassDev& P, bool adj, int n_warps, int chunk) {
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
     size_t b = 0;
     b += (size_t)(adj ? 2 : 1) * P.capA * P.strideB * 16;
     b += al((size_t)P.max_live * 8);              // class program headers
-    b += (size_t)MQC_C_RING_SLOTS * MQC_C_CHUNK * 4;   // pair-word ring
+    b += (size_t)MQC_C_RING_SLOTS * chunk * 4;    // pair-word ring
     b += (size_t)P.nf * 16;                       // cos / sin
     b += al((size_t)P.nf);                        // per-tile factor signs
     b += al((size_t)(P.capA + P.capB) * 4);       // row / column maps of the tile
@@ -219,9 +222,9 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
         MqcCPassDev D{};
         D.nf = P.f1 - P.f0;
         D.f0 = P.f0;
-        if (D.nf > 4095) return PL;
+        if (D.nf > 4095) { PL.why = "more than 4095 factors in a pass"; return PL; }
         const int a_act = __builtin_popcount(SA[p]), b_act = __builtin_popcount(SB[p]);
-        if (a_act >= MQC_C_KMAX || b_act >= MQC_C_KMAX) return PL;
+        if (a_act >= MQC_C_KMAX || b_act >= MQC_C_KMAX) { PL.why = "too many active orbitals of one spin"; return PL; }
         D.n_clsA = (int32_t)clsA[p].size(); D.n_clsB = (int32_t)clsB[p].size();
         D.clsA_off = PL.cls.size(); PL.cls.insert(PL.cls.end(), clsA[p].begin(), clsA[p].end());
         D.clsB_off = PL.cls.size(); PL.cls.insert(PL.cls.end(), clsB[p].begin(), clsB[p].end());
@@ -229,10 +232,10 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
         bool kA[MQC_C_KMAX] = {}, kB[MQC_C_KMAX] = {};
         for (const MqcCClass& c : clsA[p]) { capA = std::max(capA, (int)c.cnt); kA[c.k] = true; }
         for (const MqcCClass& c : clsB[p]) { capB = std::max(capB, (int)c.cnt); kB[c.k] = true; }
-        if (capA > 127 || capB > 127) return PL;              // pair entries hold 7-bit pattern ranks
+        if (capA > 127 || capB > 127) { PL.why = "more than 127 patterns per class"; return PL; }   // 7-bit pattern ranks
         D.capA = capA; D.capB = capB;
         D.strideB = capB | 1;                                 // odd row stride: bank-conflict-free row pairs
-        if (capA * D.strideB > 16383) return PL;              // 14-bit row offsets in the alpha entries
+        if (capA * D.strideB > 16383) { PL.why = "tile larger than 16383 slots"; return PL; }      // 14-bit slots in the pair words
         // maps: layout p position -> layout p + 1 position
         D.map_row_off = PL.maps.size();
         { std::vector<uint32_t> m(PL.nA); bool id = true; for (uint32_t i = 0; i < PL.nA; ++i) { m[posA[p][i]] = posA[p + 1][i]; id = id && posA[p][i] == posA[p + 1][i]; }
@@ -261,7 +264,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
             const MqcFactor& F = fac[S.tf[P.f0 + f].slot];
             uint32_t za, zb;
             split(F.m, mA[f], mB[f]); split(F.v, vA[f], vB[f]); split(F.z, za, zb);
-            if ((mA[f] & ~SA[p]) || (mB[f] & ~SB[p])) return PL;      // the schedule guarantees this
+            if ((mA[f] & ~SA[p]) || (mB[f] & ~SB[p])) { PL.why = "factor moves an inactive orbital"; return PL; }      // the schedule guarantees this
             zAi[f] = za & SA[p]; zBi[f] = zb & SB[p];
             MqcCFactor C{};
             C.zA_out = za & ~SA[p]; C.zB_out = zb & ~SB[p];
@@ -310,11 +313,12 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
                 const std::vector<uint32_t>& LA = lists[0][(size_t)f * MQC_C_KMAX + ka];
                 const std::vector<uint32_t>& LB = lists[1][(size_t)f * MQC_C_KMAX + kb];
                 if (LA.empty() || LB.empty()) continue;
-                if (PL.prog.size() + LA.size() * LB.size() > 0xFFFFFFF0ull) return PL;
+                if (PL.prog.size() + LA.size() * LB.size() > 0xFFFFFFF0ull) { PL.why = "program pool too large"; return PL; }
                 MqcCProgHdr H;
                 H.off = (uint32_t)PL.prog.size() - Lv.word_base;
                 H.np_f = (uint32_t)(LA.size() * LB.size()) | ((uint32_t)f << 16);
-                if (LA.size() * LB.size() > (size_t)MQC_C_MAX_STEP_PAIRS) return PL;
+                if (LA.size() * LB.size() > (size_t)MQC_C_MAX_STEP_PAIRS(1024)) { PL.why = "a step has more pairs than the ring holds"; return PL; }
+                PL.max_step_pairs = std::max(PL.max_step_pairs, (uint32_t)(LA.size() * LB.size()));
                 PL.prog_hdr.push_back(H);
                 std::vector<uint32_t> words;
                 words.reserve(LA.size() * LB.size());
@@ -333,8 +337,10 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
         }
         if (PL.prog_hdr.size() & 1) PL.prog_hdr.push_back(MqcCProgHdr{0, 0});
         PL.pass.push_back(D);
-        for (int adj = 0; adj < 2; ++adj) PL.max_smem[adj] = std::max(PL.max_smem[adj], mqc_c_smem_bytes(D, adj != 0, 8));
     }
+    PL.chunk = PL.max_step_pairs <= (uint32_t)MQC_C_MAX_STEP_PAIRS(256) ? 256 : 1024;
+    for (const MqcCPassDev& D : PL.pass)
+        for (int adj = 0; adj < 2; ++adj) PL.max_smem[adj] = std::max(PL.max_smem[adj], mqc_c_smem_bytes(D, adj != 0, 4, PL.chunk));
     if (PL.cls.empty()) PL.cls.push_back(MqcCClass{});
     if (PL.fac.empty()) PL.fac.push_back(MqcCFactor{});
     if (PL.maps.empty()) PL.maps.push_back(0);

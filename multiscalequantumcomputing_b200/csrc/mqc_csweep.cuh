@@ -89,7 +89,7 @@ __device__ __forceinline__ double mqc_rotate_pair(double2* __restrict__ sp, doub
     return g;
 }
 
-template <bool ADJ, int NT>
+template <bool ADJ, int NT, int CH>
 __global__ void __launch_bounds__(NT, (1024 / NT) > 16 ? 16 : (1024 / NT))
 k_csweep(const __grid_constant__ MqcCArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -103,7 +103,7 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
     double2* sp = reinterpret_cast<double2*>(q);              q += (size_t)capA * strideB * 16;
     double2* sl = reinterpret_cast<double2*>(q);              if (ADJ) q += (size_t)capA * strideB * 16;
     uint2* shdr = reinterpret_cast<uint2*>(q);                q += ((size_t)P->max_live * 8 + 15) & ~(size_t)15;
-    uint32_t* ring = reinterpret_cast<uint32_t*>(q);          q += (size_t)MQC_C_RING_SLOTS * MQC_C_CHUNK * 4;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(q);          q += (size_t)MQC_C_RING_SLOTS * CH * 4;
     double2* hcs = reinterpret_cast<double2*>(q);             q += (size_t)nf * 16;
     unsigned char* hsg = q;                                   q += ((size_t)nf + 15) & ~(size_t)15;
     uint32_t* smap = reinterpret_cast<uint32_t*>(q);          q += ((size_t)(capA + capB) * 4 + 15) & ~(size_t)15;
@@ -111,7 +111,7 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
     double* gw = reinterpret_cast<double*>(q);                if (ADJ) q += (size_t)NW * gw_stride * 8;
     uint64_t* bar = reinterpret_cast<uint64_t*>(q);           // [0] tile rows + headers, [1 ..] ring slots
     uint64_t* rbar = bar + 1;
-    constexpr uint32_t RMASK = MQC_C_RING_SLOTS * MQC_C_CHUNK - 1;
+    constexpr uint32_t RMASK = MQC_C_RING_SLOTS * CH - 1;
 
     if (tid == 0) {
         for (int i = 0; i <= MQC_C_RING_SLOTS; ++i) mqc_mbar_init(bar + i, 1);
@@ -133,22 +133,22 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
         const uint4 lt4 = __ldg(reinterpret_cast<const uint4*>(A.live_tab + P->live_tab_off + (size_t)ka * MQC_C_KMAX + kb));
         const int n_live = (int)lt4.y;
         const uint32_t* __restrict__ prog = A.prog + lt4.z;          // this class's pair words
-        const int NC = (int)((lt4.w + MQC_C_CHUNK - 1) / MQC_C_CHUNK);   // chunks of the program
+        const int NC = (int)((lt4.w + CH - 1) / CH);   // chunks of the program
         int issued = 0, have = 0;                                    // chunks (processing order) issued / arrived
         auto issue_chunk = [&](int k) {
             const int c = ADJ ? NC - 1 - k : k;
             const int slot = c & (MQC_C_RING_SLOTS - 1);
-            const uint32_t words = min((uint32_t)MQC_C_CHUNK, lt4.w - (uint32_t)c * MQC_C_CHUNK);
+            const uint32_t words = min((uint32_t)CH, lt4.w - (uint32_t)c * CH);
             mqc_mbar_expect_tx(rbar + slot, words * 4u);
-            mqc_bulk_g2s(ring + slot * MQC_C_CHUNK, prog + (size_t)c * MQC_C_CHUNK, words * 4u, rbar + slot);
+            mqc_bulk_g2s(ring + slot * CH, prog + (size_t)c * CH, words * 4u, rbar + slot);
         };
         // last chunk (processing order) a step needs
         auto k_hi = [&](const uint2 h) -> int {
-            const int c_lo = (int)(h.x / MQC_C_CHUNK), c_hi = (int)((h.x + (h.y & 0xffffu) - 1u) / MQC_C_CHUNK);
+            const int c_lo = (int)(h.x / CH), c_hi = (int)((h.x + (h.y & 0xffffu) - 1u) / CH);
             return ADJ ? NC - 1 - c_lo : c_hi;
         };
         auto k_lo = [&](const uint2 h) -> int {
-            const int c_lo = (int)(h.x / MQC_C_CHUNK), c_hi = (int)((h.x + (h.y & 0xffffu) - 1u) / MQC_C_CHUNK);
+            const int c_lo = (int)(h.x / CH), c_hi = (int)((h.x + (h.y & 0xffffu) - 1u) / CH);
             return ADJ ? NC - 1 - c_hi : c_lo;
         };
         auto wait_chunks = [&](int k_need) {

@@ -1,6 +1,6 @@
 # 32-qubit energy + gradient on 1 / 2 / 4 ranks (strong scaling of the sharded state), one box
 mkdir -p gpurun_out
-OUT=gpurun_out/r01_shard_4gpu.jsonl
+OUT=gpurun_out/r02_shard_4gpu.jsonl
 : > $OUT
 run() { R=$1; shift; echo "== $R ranks: $*"
   timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $R --master-addr 127.0.0.1 --master-port 29583 scripts/shard_bench.py "$@" 2>&1 | tail -1 | tee -a $OUT; }

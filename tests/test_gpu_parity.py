@@ -96,9 +96,11 @@ def test_gradient_at_zero_angles():
     h.close()
 
 
-@pytest.mark.parametrize("n,ne", [(4, 4), (5, 4), (6, 6)])
-def test_rdm12(n, ne):
-    h, orc, F, tab, th = _setup(n, ne, "blocked", {"tile_bits": 9, "grad_tile_bits": 8})
+@pytest.mark.parametrize("n,ne,extra", [(4, 4, {}), (5, 4, {}), (6, 6, {}), (7, 6, {}),
+                                        (6, 6, {"rdm_gram": 0}),          # compact state, literal K4 loops (atomics)
+                                        (5, 4, {"compact": 0})])          # dense register
+def test_rdm12(n, ne, extra):
+    h, orc, F, tab, th = _setup(n, ne, "blocked", dict({"tile_bits": 9, "grad_tile_bits": 8}, **extra))
     h.prepare(th)
     r1, r2 = h.rdm12(n, ne // 2, ne - ne // 2)
     o1, o2 = ordm.get_rdm12(orc.state(th), ne, n)
@@ -227,6 +229,27 @@ def test_properties_20_qubits():
     e0, g0 = h0.energy_grad(th)
     assert abs(e - e0) < E_TOL and abs(g - g0).max() < G_TOL
     h.close(); h0.close()
+
+
+def test_properties_26_qubits_rdm_blocks():
+    """13 orbitals: n^2 = 169 > 144, so the Gram-form K4 (mqc_rdm.cuh) runs its blocked variant
+    (2 x 2 blocks of 128 rows).  No CPU oracle at this size: traces, symmetry and the energy
+    contracted from the RDMs against <H> of K2."""
+    n, ne = 13, 12
+    h1, eri = random_fragment_integrals(n, 5)
+    bare = fragment_term_table(h1, eri, 0, 0.0, 0.0)
+    F = uccsd_factors(n, ne, "blocked")
+    h = _lib.Handle(2 * n)
+    h.set_hamiltonian(*bare)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    th = np.random.default_rng(11).normal(0, 0.05, F.n_theta)
+    h.prepare(th)
+    e_bare = h.expectation(*bare).real
+    r1, r2 = h.rdm12(n, ne // 2, ne // 2)
+    assert abs(np.trace(r1) - ne) < 1e-10 and abs(np.einsum("iijj->", r2) - ne * (ne - 1)) < 1e-8
+    assert abs(r1 - r1.T).max() < 1e-12 and abs(r2 - r2.transpose(2, 3, 0, 1)).max() < 1e-12
+    assert abs(np.einsum("pq,pq->", h1, r1) + 0.5 * np.einsum("pqrs,pqrs->", eri, r2) - e_bare) < 1e-9
+    h.close()
 
 
 def test_solve_matches_oracle_backed_solve():
@@ -426,12 +449,16 @@ def test_update_hamiltonian_coeffs_and_handle_cache():
     S.clear_handle_cache(); S.clear_warm_start()
     S.STATS["handle_creates"] = S.STATS["handle_reuses"] = 0
     from multiscalequantumcomputing_b200.parallel import solve_fragments
-    run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[0], fragment_ids=True))
+    run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[0], fragment_ids=True, warm_start=False))
     e_cached = run.run()
     assert S.STATS["handle_creates"] == len(cl)
     assert S.STATS["handle_reuses"] == run.n_solves - len(cl) and S.STATS["handle_reuses"] > 0
-    S.clear_handle_cache(); S.clear_warm_start()
     ref = DMETRun(ints, cl, solver=lambda *a: solve(*a))
-    assert abs(e_cached - ref.run()) < 1e-8
+    e_ref = ref.run()
+    assert abs(e_cached - e_ref) < 1e-9                       # re-used handles: same arithmetic as fresh ones
+    # with the per-fragment warm start the optimiser stops at a (gtol-)different point of the same minimum
+    warm = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[0], fragment_ids=True))
+    assert abs(warm.run() - e_ref) < 1e-6
+    S.clear_handle_cache(); S.clear_warm_start()
     with pytest.raises(ValueError):
         solve(ints.h_loc[:4, :4], ints.h_loc[:4, :4], ints.eri_loc[:4, :4, :4, :4], 4, 2, 0.0, warm_start=True)
