@@ -53,9 +53,9 @@ def workload():
 CONFIG = {"workload": "uccsd_statevector_24q_H12chain_sto3g_energy+adjoint_gradient",
           "n_qubits": 2 * N_ORB, "n_orb": N_ORB, "n_elec": N_ELEC, "bond_angstrom": BOND,
           "ansatz": "JW-UCCSD, blocked order", "fragments_per_gpu": 1,
-          "l2_policy": "every step re-initialises the 268 MB state and its 268 MB adjoint (memsets of 4x the 126 MB L2 "
-                       "stream through L2 and flush it between steps); within a step the sector working set (~60 MB) "
-                       "is L2 resident by design"}
+          "l2_policy": "explicit flush: a 256 MB device buffer (2x the 126 MB L2) is overwritten between timed steps, outside "
+                       "the timed region (per-step CUDA events / per-call clocks are summed); within a step the compact "
+                       "sector working set (psi + lambda ping-pong, 55 MB) is L2 resident by design"}
 
 
 class ClockSampler:
@@ -198,19 +198,23 @@ def dmet_wall_time(device):
     time of a whole DMET run (all chemical-potential steps, 5 fragments of 8 qubits each) with the
     GPU UCCSD solver behind the reference's solve() signature."""
     from multiscalequantumcomputing_b200.parallel import solve_fragments
-    from multiscalequantumcomputing_b200.solver import clear_warm_start
+    from multiscalequantumcomputing_b200 import solver as S
     from multiscalequantumcomputing_b200.synth.hydrogen import hydrogen_chain, local_integrals
     from multiscalequantumcomputing_b200.synth.dmet_loop import DMETRun, atom_clusters
     ints = local_integrals(hydrogen_chain(10, 0.6))
     cl = atom_clusters(10, 2)
     best = None
     for _ in range(3):
-        clear_warm_start()
-        # the five fragments of a mu step are independent: one worker (handle + stream) each on this GPU
-        run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[device] * len(cl), warm_start=False))
+        S.clear_warm_start(); S.clear_handle_cache()
+        S.STATS["handle_creates"] = S.STATS["handle_reuses"] = 0
+        # the five fragments of a mu step are independent: one worker (handle + stream) each on this GPU; every
+        # fragment keeps its handle (and its last parameters) over the chemical-potential steps
+        run = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[device] * len(cl), fragment_ids=True))
         t = time.perf_counter(); e = run.run(); dt = time.perf_counter() - t
         if best is None or dt < best["wall_s"]:
-            best = {"wall_s": dt, "solves": run.n_solves, "mu_steps": len(run.history), "energy": e}
+            best = {"wall_s": dt, "solves": run.n_solves, "mu_steps": len(run.history), "energy": e,
+                    "handle_creates": S.STATS["handle_creates"], "handle_reuses": S.STATS["handle_reuses"]}
+    S.clear_warm_start(); S.clear_handle_cache()
     best.update({"system": "H10 chain STO-3G 0.6 A, 5 fragments x 2 atoms, 8 qubits each, UCCSD, fragments concurrent on one GPU", "unit": "s", "runs": 3,
                  "reference": "745.97 s per DMET iteration with the reference's VQE solver (test/log_hchain_vqe:4039)"})
     return best
@@ -362,21 +366,27 @@ def run_ours(args):
     e_ref, g_ref = e, g_np.copy()
 
     # ---- value: inputs resident, CUDA events on the solver's stream ---------------------
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.add_(1)
+        torch.cuda.synchronize()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
     phase = np.zeros(3)
     launches = 0
-    h.event_record(0)
+    dev_ms = 0.0
     w0 = time.perf_counter()
     for _ in range(args.steps):
-        e = h.energy_grad_resident()
+        flush_l2()
+        e = h.energy_grad_resident()            # synchronous; its own CUDA events bracket the evaluation
         t = h.last_timing()
         phase += (t["forward_ms"], t["hamiltonian_ms"], t["reverse_ms"])
+        dev_ms += t["total_ms"]
         launches += t["launches"]
-    h.event_record(1)
-    dev_ms = h.event_elapsed_ms()
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
@@ -385,11 +395,13 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the public call --------------------------------------
     barrier()
-    w0 = time.perf_counter()
+    e2e_ms = 0.0
     for _ in range(args.steps):
-        e2 = h.energy_grad_into(th_np, g_np)
+        flush_l2()
+        w1 = time.perf_counter()
+        e2 = h.energy_grad_into(th_np, g_np)    # returns after (energy, gradient) are in host memory
+        e2e_ms += (time.perf_counter() - w1) * 1e3
     barrier()
-    e2e_ms = (time.perf_counter() - w0) * 1e3
     assert abs(e2 - e_ref) < 1e-9 and np.abs(g_np - g_ref).max() < 1e-9
 
     if use_dist:
@@ -413,6 +425,9 @@ def run_ours(args):
         phase /= args.steps
         names = ("k_tile_sp2<false> (forward sweep)", "k_sigma (H|psi>)", "k_tile_sp2<true> (adjoint reverse sweep)")
         sparse = tim["forward_passes"] > 0 and "sparse_tiles=0" not in args.opt and "sector=0" not in args.opt
+        if h.cplan_info(1)["n_passes"] > 0:
+            names = ("k_csweep<false> (forward sweep, compact sector matrix)", "k_sigma (H|psi>)",
+                     "k_csweep<true> (adjoint reverse sweep, compact sector matrix)")
         if not sparse:
             names = ("k_tile_sweep<false> (forward sweep)", "k_happly (H|psi>)", "k_tile_sweep<true> (adjoint reverse sweep)")
         # algorithmic bytes per LAUNCH of each kernel
@@ -444,8 +459,8 @@ def run_ours(args):
         # sweeps) measured live on the same workload: 2 S bytes per launch.
         streaming = None
         try:
-            if world > 1:
-                raise RuntimeError("reported at N=1 only")
+            if world > 1 or args.quick:
+                raise RuntimeError("reported at N=1 only" if world > 1 else "skipped (--quick)")
             hd = _lib.Handle(factors.n_qubits, local)
             hd.set_option("compact", 0)
             hd.set_option("sparse_tiles", 0)
@@ -475,8 +490,8 @@ def run_ours(args):
         except Exception as exc:
             streaming = {"unavailable": str(exc)}
         cpu = None
-        if world > 1:
-            cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "reported at N=1 only"}
+        if world > 1 or args.quick:
+            cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "reported at N=1 only" if world > 1 else "skipped (--quick)"}
         else:
             try:
                 dt, cores, e_cpu, g_cpu, ph_cpu = cpu_full_evaluation(table, factors, theta)
@@ -488,19 +503,19 @@ def run_ours(args):
                 cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "unavailable: %s" % exc}
         # second half of BASELINE.json's metric: wall time of one DMET run (configs[0] shape)
         dmet = None
-        if world == 1:
+        if world == 1 and not args.quick:
             try:
                 dmet = dmet_wall_time(local)
             except Exception as exc:
                 dmet = {"unavailable": str(exc)}
         ref_small = None
-        if world == 1:
+        if world == 1 and not args.quick:
             try:
                 ref_small = reference_style_small(local)
             except Exception as exc:
                 ref_small = {"unavailable": str(exc)}
         variants = None
-        if world == 1:
+        if world == 1 and not args.quick:
             try:
                 variants = variant_legs(local, args.opt)
             except Exception as exc:
@@ -533,6 +548,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (e.g. sparse_tiles=0)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded-state legs of an N > 1 run")
+    ap.add_argument("--quick", action="store_true", help="only the timed evaluation legs (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -52,8 +52,12 @@ struct MqcCFactor {
 };
 struct MqcCProgHdr {           // one live factor (step) of a class program
     uint32_t off;              // first pair word, relative to the program's first word
-    uint32_t np_f;             // number of pairs | pass-local factor index << 16
+    uint32_t np_f;             // pairs (11 bits) | pass-local factor index << 11 (12 bits) | ring bookkeeping << 23:
+                               //   2 bits each: chunks to wait for before this step (forward order / adjoint order),
+                               //   chunks to issue after this step (forward / adjoint); see mqc_c_ring_flags
 };
+#define MQC_C_NP(y) ((y) & 0x7ffu)
+#define MQC_C_F(y) (((y) >> 11) & 0xfffu)
 struct MqcCLive {              // class (ka, kb) -> its program
     uint32_t off, cnt;         // headers in the header pool
     uint32_t word_base;        // first pair word in the program pool (multiple of 4: 16-byte aligned)
@@ -135,6 +139,36 @@ static inline void mqc_c_bank_order(std::vector<uint32_t>& w) {
         }
     }
     w.swap(out);
+}
+
+// Ring bookkeeping of a class program, precomputed so that the kernel neither divides nor compares:
+// the chunks arrive in processing order (forward: c = 0, 1, ..; adjoint: c = NC - 1, NC - 2, ..); a step
+// waits for the chunks it is the first to need and, once it is done, the chunks that the NEXT step
+// no longer needs make room for as many new ones.
+static inline void mqc_c_ring_flags(MqcCProgHdr* H, int n, uint32_t n_words, int chunk) {
+    const int NC = (int)((n_words + chunk - 1) / chunk);
+    auto c_lo = [&](int i) { return (int)(H[i].off / chunk); };
+    auto c_hi = [&](int i) { return (int)((H[i].off + MQC_C_NP(H[i].np_f) - 1u) / chunk); };
+    int have = 0, issued = std::min(NC, MQC_C_RING_SLOTS);
+    for (int i = 0; i < n; ++i) {                              // forward order
+        const int need = c_hi(i) + 1;
+        const int w = std::max(0, need - have);
+        have = std::max(have, need);
+        int is = 0;
+        if (i + 1 < n) { const int target = std::min(NC, c_lo(i + 1) + MQC_C_RING_SLOTS); is = std::max(0, target - issued); issued += is; }
+        if (w > 3 || is > 3) throw std::runtime_error("program ring bookkeeping overflow");
+        H[i].np_f |= ((uint32_t)w << 23) | ((uint32_t)is << 27);
+    }
+    have = 0; issued = std::min(NC, MQC_C_RING_SLOTS);
+    for (int i = n - 1; i >= 0; --i) {                         // adjoint order, k = NC - 1 - c
+        const int need = NC - 1 - c_lo(i) + 1;
+        const int w = std::max(0, need - have);
+        have = std::max(have, need);
+        int is = 0;
+        if (i > 0) { const int target = std::min(NC, NC - 1 - c_hi(i - 1) + MQC_C_RING_SLOTS); is = std::max(0, target - issued); issued += is; }
+        if (w > 3 || is > 3) throw std::runtime_error("program ring bookkeeping overflow");
+        H[i].np_f |= ((uint32_t)w << 25) | ((uint32_t)is << 29);
+    }
 }
 
 // shared memory of one CTA (bytes) for a pass; must match the carve-up in k_csweep
@@ -316,7 +350,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
                 if (PL.prog.size() + LA.size() * LB.size() > 0xFFFFFFF0ull) { PL.why = "program pool too large"; return PL; }
                 MqcCProgHdr H;
                 H.off = (uint32_t)PL.prog.size() - Lv.word_base;
-                H.np_f = (uint32_t)(LA.size() * LB.size()) | ((uint32_t)f << 16);
+                H.np_f = (uint32_t)(LA.size() * LB.size()) | ((uint32_t)f << 11);
                 if (LA.size() * LB.size() > (size_t)MQC_C_MAX_STEP_PAIRS(1024)) { PL.why = "a step has more pairs than the ring holds"; return PL; }
                 PL.max_step_pairs = std::max(PL.max_step_pairs, (uint32_t)(LA.size() * LB.size()));
                 PL.prog_hdr.push_back(H);
@@ -339,6 +373,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
         PL.pass.push_back(D);
     }
     PL.chunk = PL.max_step_pairs <= (uint32_t)MQC_C_MAX_STEP_PAIRS(256) ? 256 : 1024;
+    for (const MqcCLive& Lv : PL.live_tab) if (Lv.cnt) mqc_c_ring_flags(&PL.prog_hdr[Lv.off], (int)Lv.cnt, Lv.n_words, PL.chunk);
     for (const MqcCPassDev& D : PL.pass)
         for (int adj = 0; adj < 2; ++adj) PL.max_smem[adj] = std::max(PL.max_smem[adj], mqc_c_smem_bytes(D, adj != 0, 4, PL.chunk));
     if (PL.cls.empty()) PL.cls.push_back(MqcCClass{});
@@ -376,8 +411,8 @@ static inline std::vector<double> mqc_cplan_forward_host(const MqcCPlan& PL, con
             const MqcCLive& L = PL.live_tab[D.live_tab_off + (size_t)cA.k * MQC_C_KMAX + cB.k];
             for (uint32_t i = 0; i < L.cnt; ++i) {
                 const MqcCProgHdr& H = PL.prog_hdr[L.off + i];
-                const int f = (int)(H.np_f >> 16);
-                const uint32_t npairs = H.np_f & 0xffffu;
+                const int f = (int)MQC_C_F(H.np_f);
+                const uint32_t npairs = MQC_C_NP(H.np_f);
                 const MqcCFactor& F = PL.fac[D.fac_off + f];
                 const unsigned sg = ((unsigned)__builtin_popcount(cA.mask & F.zA_out) + (unsigned)__builtin_popcount(cB.mask & F.zB_out) + ((uint32_t)F.theta_sign >> 31)) & 1u;
                 const double c = cosv[F.slot], sn = sg ? -sinv[F.slot] : sinv[F.slot];

@@ -73,14 +73,14 @@ template <bool ADJ>
 __device__ __forceinline__ double mqc_rotate_pair(double2* __restrict__ sp, double2* __restrict__ sl, const uint32_t w,
                                                   const double c, const double s) {
     const int e0 = (int)(w & 0x3fffu), e1 = (int)((w >> 14) & 0x3fffu);
-    const bool neg = ((w >> 28) & 1u) != 0u;
-    const double ssn = neg ? -s : s;
+    const int sgn = (int)((w << 3) & 0x80000000u);                            // pair parity -> sign bit of a double
+    const double ssn = __hiloint2double(__double2hiint(s) ^ sgn, __double2loint(s));
     const double2 a = sp[e0], b = sp[e1];
     double g = 0.0;
     if (ADJ) {
         const double2 xa = sl[e0], xb = sl[e1];
         const double gv = xb.x * a.x + xb.y * a.y - xa.x * b.x - xa.y * b.y;
-        g = neg ? -gv : gv;                      // pair parity alone (the tile sign is applied at the flush)
+        g = __hiloint2double(__double2hiint(gv) ^ sgn, __double2loint(gv));    // pair parity alone (the tile sign is applied at the flush)
         sl[e0] = make_double2(c * xa.x - ssn * xb.x, c * xa.y - ssn * xb.y);
         sl[e1] = make_double2(c * xb.x + ssn * xa.x, c * xb.y + ssn * xa.y);
     }
@@ -142,17 +142,9 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
             mqc_mbar_expect_tx(rbar + slot, words * 4u);
             mqc_bulk_g2s(ring + slot * CH, prog + (size_t)c * CH, words * 4u, rbar + slot);
         };
-        // last chunk (processing order) a step needs
-        auto k_hi = [&](const uint2 h) -> int {
-            const int c_lo = (int)(h.x / CH), c_hi = (int)((h.x + (h.y & 0xffffu) - 1u) / CH);
-            return ADJ ? NC - 1 - c_lo : c_hi;
-        };
-        auto k_lo = [&](const uint2 h) -> int {
-            const int c_lo = (int)(h.x / CH), c_hi = (int)((h.x + (h.y & 0xffffu) - 1u) / CH);
-            return ADJ ? NC - 1 - c_hi : c_lo;
-        };
-        auto wait_chunks = [&](int k_need) {
-            while (have <= k_need) {
+        // wait for the next `count` chunks in processing order (header flags, mqc_c_ring_flags)
+        auto wait_chunks = [&](uint32_t count) {
+            for (; count; --count) {
                 const int c = ADJ ? NC - 1 - have : have;
                 const int slot = c & (MQC_C_RING_SLOTS - 1);
                 mqc_mbar_wait(rbar + slot, (phbits >> slot) & 1u);
@@ -208,8 +200,9 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
         //      that ends step i, so between two barriers a thread only rotates ----------------------------
         if (n_live > 0) {
             auto step = [&](int i) -> int { return ADJ ? n_live - 1 - i : i; };
+            constexpr int WSH = ADJ ? 25 : 23, ISH = ADJ ? 29 : 27;
             uint2 hc = shdr[step(0)];
-            wait_chunks(k_hi(hc));
+            wait_chunks((hc.y >> WSH) & 3u);
             uint32_t wc = ring[(hc.x + (uint32_t)tid) & RMASK];
             for (int i0 = 0; i0 < n_live; i0 += 8) {
                 double acc8[8];
@@ -218,28 +211,28 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
                     acc8[j] = 0.0;
                     const int i = i0 + j;
                     if (i < n_live) {                                   // uniform over the CTA
-                        const uint32_t npairs = hc.y & 0xffffu;
-                        uint2 hn = hc;
+                        const uint32_t npairs = MQC_C_NP(hc.y);
+                        uint2 hn = make_uint2(0u, 0u);
                         uint32_t wn = 0u;
                         if (i + 1 < n_live) {
                             hn = shdr[step(i + 1)];
-                            wait_chunks(k_hi(hn));
+                            wait_chunks((hn.y >> WSH) & 3u);
                         }
                         double gacc = 0.0;
                         if ((uint32_t)(warp * 32) < npairs) {           // warps without a pair in this step only keep step
-                            const double2 csv = hcs[hc.y >> 16];
+                            const double2 csv = hcs[MQC_C_F(hc.y)];
                             if ((uint32_t)tid < npairs) gacc = mqc_rotate_pair<ADJ>(sp, sl, wc, csv.x, csv.y);
                             for (uint32_t u = (uint32_t)tid + NT; u < npairs; u += NT)
                                 gacc += mqc_rotate_pair<ADJ>(sp, sl, ring[(hc.x + u) & RMASK], csv.x, csv.y);
                         }
-                        if ((uint32_t)(warp * 32) < (hn.y & 0xffffu)) wn = ring[(hn.x + (uint32_t)tid) & RMASK];
+                        if ((uint32_t)(warp * 32) < MQC_C_NP(hn.y)) wn = ring[(hn.x + (uint32_t)tid) & RMASK];
                         if (ADJ) acc8[j] = gacc;
                         __syncthreads();
-                        if (tid == 0 && issued < NC) {                  // chunks before the next step's first are free
-                            const int kfree = k_lo(hn);
-                            if (issued - MQC_C_RING_SLOTS < kfree) {
+                        if (tid == 0) {                                 // slots the next step no longer needs get new chunks
+                            uint32_t cnt_is = (hc.y >> ISH) & 3u;
+                            if (cnt_is) {
                                 mqc_fence_async();
-                                for (; issued < NC && issued - MQC_C_RING_SLOTS < kfree; ++issued) issue_chunk(issued);
+                                for (; cnt_is; --cnt_is) issue_chunk(issued++);
                             }
                         }
                         hc = hn; wc = wn;
@@ -275,7 +268,7 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
                     w1r += __shfl_xor_sync(0xffffffffu, w1r, 1);
                     const int j = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
                     if ((lane & 3) == 0 && i0 + j < n_live && w1r != 0.0) {
-                        const int f = (int)(shdr[step(i0 + j)].y >> 16);
+                        const int f = (int)MQC_C_F(shdr[step(i0 + j)].y);
                         gw[(size_t)warp * gw_stride + f] += hsg[f] ? -w1r : w1r;
                     }
                 }

@@ -14,7 +14,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]
 lines = ["# ncu summaries, round %s" % R, "",
-         "Command profiled: `python bench.py --steps 2 --warmup 3` (24-qubit H12-chain UCCSD energy+gradient), one B200,",
+         "Command profiled: `python bench.py --steps 2 --warmup 3 --quick` (24-qubit H12-chain UCCSD energy+gradient), one B200,",
          "`ncu --set full --clock-control none --import-source on`; numbers under ncu are cold-cache and serialised:",
          "use them for traffic, occupancy, stall reasons and SHARES of the step, never as bench values.", ""]
 def raw(rep):
@@ -22,7 +22,7 @@ def raw(rep):
     rows = list(csv.reader(io.StringIO(txt)))
     return rows[0], rows[1], rows[2:]
 traffic = {}
-for name in ("tile_fwd", "tile_adj", "happly", "dense_fwd", "sp2f", "sp2a", "sp2", "sigma"):
+for name in ("tile_fwd", "tile_adj", "happly", "dense_fwd", "sp2f", "sp2a", "sp2", "csweep_fwd", "csweep_adj", "sigma", "rdm_gram"):
     rep = "gpurun_out/%s_%s.ncu-rep" % (R, name)
     if not os.path.exists(rep):
         continue
