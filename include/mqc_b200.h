@@ -153,6 +153,14 @@ int mqc_sigma_host_apply(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int6
                          const double* coeff_im, const double* c_re_im, double* l_re_im,
                          int64_t* n_rows, int64_t* n_cols, int64_t* n_fallback);
 
+/* Host-only: the opposite-spin double excitations a^+_{i alpha} a_{j alpha} a^+_{k beta} a_{l beta} are applied by
+ * their own kernel in a sign-adjusted string basis (csrc/mqc_sigma_ab.h); their weights W[ij][kl] are read off
+ * the Pauli-term table and verified term group by term group.  Reports how many Pauli terms that kernel
+ * takes over and how many non-zero weights it holds; mqc_sigma_host_apply evaluates both parts. */
+int mqc_sigma_ab_info(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int64_t n_terms, const uint64_t* xmask,
+                      const uint64_t* zmask, const double* coeff_re, const double* coeff_im, int64_t* n_ab_terms,
+                      int64_t* n_weights);
+
 /* Host-only check of the compressed-sector tile plan (pattern tables and per-factor pair lists
  * that k_tile_sp2 walks): executes schedule `which` on one CPU thread and returns the state in
  * OpenFermion order.  Unsharded handles up to 22 qubits. */

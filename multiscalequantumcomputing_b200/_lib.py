@@ -53,6 +53,7 @@ SIGNATURES = {
     "mqc_load_state": [_H, _f64p, C.c_int64],
     "mqc_sigma_host_apply": [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p,
                              _i64p, _i64p, _i64p],
+    "mqc_sigma_ab_info": [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _u64p, _u64p, _f64p, _f64p, _i64p, _i64p],
     "mqc_schedule_info": [_H, C.c_int32, _i32p, _i32p, _i32p],
     "mqc_schedule_pass": [_H, C.c_int32, C.c_int32, _i32p, _i32p, _u64p, _i32p, _i32p, _i32p],
     "mqc_schedule_factor": [_H, C.c_int32, C.c_int32, _u32p, _u32p, _u32p, _u64p, _i32p, _i32p],
@@ -127,6 +128,19 @@ def sigma_host_apply(n_qubits, n_alpha, n_beta, table, c_sector=None):
                                        ptr(ci, _f64p), C.cast(cs.ctypes.data, _f64p), C.cast(out.ctypes.data, _f64p),
                                        C.byref(nr), C.byref(nc), C.byref(nf)))
     return out, (nr.value, nc.value), nf.value
+
+
+def sigma_ab_info(n_qubits, n_alpha, n_beta, table):
+    """(Pauli terms taken over by the opposite-spin doubles kernel, non-zero weights W[ij][kl])."""
+    lib = load()
+    x = np.ascontiguousarray(table[0], dtype=np.uint64)
+    z = np.ascontiguousarray(table[1], dtype=np.uint64)
+    c = np.asarray(table[2], dtype=np.complex128)
+    cr, ci = np.ascontiguousarray(c.real), np.ascontiguousarray(c.imag)
+    nt, nw = C.c_int64(), C.c_int64()
+    check(lib.mqc_sigma_ab_info(n_qubits, n_alpha, n_beta, len(x), ptr(x, _u64p), ptr(z, _u64p), ptr(cr, _f64p), ptr(ci, _f64p),
+                                C.byref(nt), C.byref(nw)))
+    return nt.value, nw.value
 
 
 class Handle:

@@ -16,6 +16,7 @@
 #include "mqc_kernels.cuh"
 #include "mqc_schedule.h"
 #include "mqc_sigma.h"
+#include "mqc_sigma_ab.h"
 #include "mqc_cplan.h"
 #include "mqc_csweep.cuh"
 #include "mqc_rdm.cuh"
@@ -91,6 +92,12 @@ struct SigmaTables {                // link-table form of a sector Hamiltonian (
     DevBuf<double> w22, w4a, w4b, ta1, tb1, tab, tbb, hdiag, diag_c;
     DevBuf<u64> aq, bq, diag_z;
     MqcSigmaDev dev{};
+    // alpha-beta doubles in the sign-adjusted basis (mqc_sigma_ab.h); their Pauli terms are NOT in the tables above
+    DevBuf<double> ab_w;
+    DevBuf<unsigned> ab_lnk, ab_ell, ab_g;
+    MqcSigmaABDev ab{};
+    bool ab_ready = false;
+    size_t n_ab_terms = 0;
     bool ready = false;
     unsigned row0 = 0, row1 = 0;
     size_t n_fallback = 0, n_fast = 0;
@@ -190,7 +197,7 @@ struct mqc_solver {
 
     HamHost ham, ham_fb;            // all terms / the terms the link-table kernel leaves to k_happly_sector
     SigmaTables sig;
-    int use_sigma = 1, sigma_stage = 1;
+    int use_sigma = 1, sigma_stage = 1, sigma_ab = 0;     // sigma_ab: opposite-spin doubles through k_sigma_ab (measured: no faster, both are shared-memory-gather bound)
     // The launch sequence of an evaluation depends on theta only through device buffers, so a
     // single-rank handle replays it as a CUDA graph from the third call on (first call: eager,
     // allocates; second: captured).  Any change of tables or options drops the graphs.
@@ -311,6 +318,8 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_csweep<true, NT_, CH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     MQC_CS_ATTR(32, 256) MQC_CS_ATTR(64, 256) MQC_CS_ATTR(128, 256) MQC_CS_ATTR(256, 256) MQC_CS_ATTR(512, 256)
     MQC_CS_ATTR(32, 1024) MQC_CS_ATTR(64, 1024) MQC_CS_ATTR(128, 1024) MQC_CS_ATTR(256, 1024) MQC_CS_ATTR(512, 1024)
+    CK(cudaFuncSetAttribute(k_sigma_ab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma_ab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_rdm_gram<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_rdm_gram<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
@@ -528,13 +537,38 @@ static void row_slice(const mqc_solver* s, unsigned n_rows, unsigned& r0, unsign
 }
 
 // link tables of operator H for the (na, nb) sector; the terms they do not cover go to `fb`
-static void build_sigma(mqc_solver* s, const HamHost& H, int na, int nb, SigmaTables& T, HamHost& fb) {
+static void build_sigma(mqc_solver* s, const HamHost& H, int na, int nb, SigmaTables& T, HamHost& fb, bool split_ab = false) {
     const int n = s->n, n_orb = n / 2;
     std::vector<u64> xq(H.x.size()), zq(H.x.size());
     for (size_t t = 0; t < H.x.size(); ++t) { xq[t] = logical_to_qubit(H.x[t], n); zq[t] = logical_to_qubit(H.z[t], n); }
-    MqcSigmaHost S = mqc_sigma_build(n_orb, na, nb, xq, zq, H.c);
+    // opposite-spin double excitations go to k_sigma_ab; the link tables get the rest
+    std::vector<size_t> keep(H.x.size());
+    std::iota(keep.begin(), keep.end(), 0);
+    std::vector<double2> cq = H.c;
+    T.ab_ready = false; T.n_ab_terms = 0;
+    if (split_ab) {
+        std::vector<unsigned> astr, bstr;
+        std::vector<int> ra, rb;
+        mqc_sg_strings(n_orb, na, astr, ra);
+        mqc_sg_strings(n_orb, nb, bstr, rb);
+        MqcSigmaAB AB = mqc_sigma_ab_build(n_orb, na, nb, xq, zq, H.c, astr, bstr);
+        if (AB.ok) {
+            std::vector<char> used(H.x.size(), 0);
+            for (size_t t : AB.used_terms) used[t] = 1;
+            keep.clear();
+            for (size_t t = 0; t < H.x.size(); ++t) if (!used[t]) keep.push_back(t);
+            std::vector<u64> x2, z2; std::vector<double2> c2;
+            for (size_t t : keep) { x2.push_back(xq[t]); z2.push_back(zq[t]); c2.push_back(H.c[t]); }
+            xq.swap(x2); zq.swap(z2); cq.swap(c2);
+            T.ab_w.upload(AB.W, s->stream); T.ab_lnk.upload(AB.lnk_a, s->stream); T.ab_ell.upload(AB.ell_b, s->stream);
+            T.ab_g.upload(AB.gB, s->stream);
+            T.ab = MqcSigmaABDev{T.ab_w.p, T.ab_lnk.p, T.ab_ell.p, T.ab_g.p, nullptr, AB.n_a, AB.n_b, AB.e_a, AB.e_b, AB.n_pair};
+            T.ab_ready = true; T.n_ab_terms = AB.used_terms.size();
+        }
+    }
+    MqcSigmaHost S = mqc_sigma_build(n_orb, na, nb, xq, zq, cq);
     fb.x.clear(); fb.z.clear(); fb.c.clear();
-    for (size_t t : S.fallback_terms) { fb.x.push_back(H.x[t]); fb.z.push_back(H.z[t]); fb.c.push_back(H.c[t]); }
+    for (size_t t : S.fallback_terms) { fb.x.push_back(H.x[keep[t]]); fb.z.push_back(H.z[keep[t]]); fb.c.push_back(H.c[keep[t]]); }
     T.n_fallback = S.fallback_terms.size(); T.n_fast = S.n_fast_terms;
     cudaStream_t st = s->stream;
     T.lnk_a1.upload(S.lnk_a1, st); T.lnk_a2.upload(S.lnk_a2, st); T.ell_b1.upload(S.ell_b1, st); T.ell_b2.upload(S.ell_b2, st);
@@ -560,6 +594,7 @@ static void build_sigma(mqc_solver* s, const HamHost& H, int na, int nb, SigmaTa
     D.m2_mask = T.m2_mask.p; D.sa_b2 = T.sa_b2.p; D.sb_a2 = T.sb_a2.p; D.sa_b4 = T.sa_b4.p; D.sb_a4 = T.sb_a4.p;
     D.aorb = T.aorb.p; D.borb = T.borb.p; D.hdiag = T.hdiag.p; D.row0 = T.row0;
     T.dev = D;
+    T.ab.aorb = T.aorb.p;
     CK(cudaStreamSynchronize(st));
     T.ready = true;
 }
@@ -575,7 +610,7 @@ static void ensure_layout_ready(mqc_solver* s, int which) {
     if (s->conserving && s->use_sector) {
         build_sector_tables(s, L, s->na, s->nb);
         const bool sigma = s->use_sigma && s->n / 2 <= 18;
-        if (sigma && !s->sig.ready) { invalidate_graphs(s); build_sigma(s, s->ham, s->na, s->nb, s->sig, s->ham_fb); }
+        if (sigma && !s->sig.ready) { invalidate_graphs(s); build_sigma(s, s->ham, s->na, s->nb, s->sig, s->ham_fb, s->use_compact && s->sigma_ab); }
         if (!L.sham_ready) { invalidate_graphs(s); build_sec_ham(s, sigma ? s->ham_fb : s->ham, L.phys, L.sham); L.sham_ready = true; }
     }
 }
@@ -874,6 +909,14 @@ static void happly_compact(mqc_solver* s, int which, const HamView& view, bool w
         while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
         dim3 grid(nA, (nB + bd * MQC_HS_R - 1) / (bd * MQC_HS_R));
         k_happly_sector<<<grid, bd, 0, s->stream>>>(C, Lm, sec_ham_dev(Lt, *view.ST), s->scalars_p(), 0u, have ? 1 : 0);
+        s->counters[0]++;
+    }
+    if (SG && SG->ready && SG->ab_ready) {                // opposite-spin doubles: L += H_ab C (mqc_sigma_ab.h)
+        const bool stage = s->sigma_stage && mqc_sigma_ab_smem_bytes(nB, true) <= 113 * 1024;
+        const size_t smem = mqc_sigma_ab_smem_bytes(nB, stage);
+        dim3 grid(nA, (nB + MQC_AB_THREADS * MQC_AB_R - 1) / (MQC_AB_THREADS * MQC_AB_R));
+        if (stage) k_sigma_ab<true><<<grid, MQC_AB_THREADS, smem, s->stream>>>(C, Lm, SG->ab, s->scalars_p());
+        else k_sigma_ab<false><<<grid, MQC_AB_THREADS, smem, s->stream>>>(C, Lm, SG->ab, s->scalars_p());
         s->counters[0]++;
     }
 }
@@ -1224,6 +1267,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sparse_threads") s->sparse_threads = (int)value;
     else if (k == "sigma") s->use_sigma = (int)value;
     else if (k == "sigma_stage") s->sigma_stage = (int)value;
+    else if (k == "sigma_ab") s->sigma_ab = (int)value;
     else if (k == "graph") s->use_graph = (int)value;
     else if (k == "sigma_blocked") s->sigma_blocked = (int)value;
     else if (k == "compact") s->compact = (int)value;
@@ -1771,7 +1815,7 @@ int mqc_expectation(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask, con
         if (sec) {
             build_sector_tables(s, s->lay[w], s->na, s->nb);
             HamHost fb;
-            if (sigma) build_sigma(s, H, s->na, s->nb, SG[i], fb);
+            if (sigma) build_sigma(s, H, s->na, s->nb, SG[i], fb, s->use_compact && s->sigma_ab);
             build_sec_ham(s, sigma ? fb : H, s->lay[w].phys, ST[i]);
         } else build_ham_tables(s, H, s->lay[w].phys, T[i]);
         views.push_back(HamView{&T[i], sec ? &ST[i] : nullptr, sigma ? &SG[i] : nullptr});
@@ -1973,12 +2017,25 @@ int mqc_sigma_host_apply(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int6
         xq[t] = logical_to_qubit(xmask[t], n_qubits); zq[t] = logical_to_qubit(zmask[t], n_qubits);
         cf[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
     }
+    // same split as on the device: opposite-spin doubles -> mqc_sigma_ab.h, the rest -> link tables
+    std::vector<unsigned> astr, bstr;
+    { std::vector<int> ra, rb; mqc_sg_strings(n_qubits / 2, n_alpha, astr, ra); mqc_sg_strings(n_qubits / 2, n_beta, bstr, rb); }
+    MqcSigmaAB AB = mqc_sigma_ab_build(n_qubits / 2, n_alpha, n_beta, xq, zq, cf, astr, bstr);
+    if (AB.ok) {
+        std::vector<char> used(xq.size(), 0);
+        for (size_t t : AB.used_terms) used[t] = 1;
+        std::vector<u64> x2, z2; std::vector<double2> c2;
+        for (size_t t = 0; t < xq.size(); ++t) if (!used[t]) { x2.push_back(xq[t]); z2.push_back(zq[t]); c2.push_back(cf[t]); }
+        xq.swap(x2); zq.swap(z2); cf.swap(c2);
+    }
     MqcSigmaHost S = mqc_sigma_build(n_qubits / 2, n_alpha, n_beta, xq, zq, cf);
     if (n_rows) *n_rows = S.n_a;
     if (n_cols) *n_cols = S.n_b;
     if (n_fallback) *n_fallback = (int64_t)S.fallback_terms.size();
-    if (c_re_im && l_re_im)
+    if (c_re_im && l_re_im) {
         mqc_sigma_apply_host(S, reinterpret_cast<const double2*>(c_re_im), reinterpret_cast<double2*>(l_re_im));
+        if (AB.ok) mqc_sigma_ab_apply_host(AB, astr, reinterpret_cast<const double2*>(c_re_im), reinterpret_cast<double2*>(l_re_im));
+    }
     MQC_CATCH
 }
 
@@ -2063,6 +2120,30 @@ int mqc_load_state(mqc_solver_t* s, const double* re_im, int64_t n_amplitudes) {
         s->state_layout = 0;
     }
     s->theta_host.clear();              // the loaded state is not a function of the parameters
+    MQC_CATCH
+}
+
+// Host-only: how many Pauli terms the opposite-spin double-excitation tables (mqc_sigma_ab.h) take over
+// from the link tables, and how many non-zero weights W[ij][kl] they hold (tests).
+int mqc_sigma_ab_info(int32_t n_qubits, int32_t n_alpha, int32_t n_beta, int64_t n_terms, const uint64_t* xmask,
+                      const uint64_t* zmask, const double* coeff_re, const double* coeff_im, int64_t* n_ab_terms,
+                      int64_t* n_weights) {
+    MQC_TRY
+    if (n_qubits < 2 || n_qubits > 36 || (n_qubits & 1)) throw MqcError("n_qubits must be even, <= 36");
+    if (n_terms < 0 || (n_terms && (!xmask || !zmask || !coeff_re))) throw MqcError("bad arguments");
+    std::vector<u64> xq(n_terms), zq(n_terms);
+    std::vector<double2> cf(n_terms);
+    for (int64_t t = 0; t < n_terms; ++t) {
+        xq[t] = logical_to_qubit(xmask[t], n_qubits); zq[t] = logical_to_qubit(zmask[t], n_qubits);
+        cf[t] = make_double2(coeff_re[t], coeff_im ? coeff_im[t] : 0.0);
+    }
+    std::vector<unsigned> astr, bstr;
+    { std::vector<int> ra, rb; mqc_sg_strings(n_qubits / 2, n_alpha, astr, ra); mqc_sg_strings(n_qubits / 2, n_beta, bstr, rb); }
+    MqcSigmaAB AB = mqc_sigma_ab_build(n_qubits / 2, n_alpha, n_beta, xq, zq, cf, astr, bstr);
+    if (n_ab_terms) *n_ab_terms = AB.ok ? (int64_t)AB.used_terms.size() : 0;
+    int64_t nw = 0;
+    if (AB.ok) for (double w : AB.W) if (w != 0.0) ++nw;
+    if (n_weights) *n_weights = nw;
     MQC_CATCH
 }
 

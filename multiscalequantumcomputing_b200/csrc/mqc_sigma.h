@@ -451,7 +451,7 @@ static inline void mqc_sigma_apply_host(const MqcSigmaHost& S, const double2* C,
                 const unsigned f1 = __builtin_popcount(bp & S.sb_a2[ia]) & 1u;
                 double accr = 0, acci = 0;
                 const int c = S.cls_of_m2[ia];
-                for (int e = S.cls_off[c]; e < S.cls_off[c + 1]; ++e) {
+                if (c >= 0) for (int e = S.cls_off[c]; e < S.cls_off[c + 1]; ++e) {
                     const unsigned en = S.ell_b1[(size_t)e * nB + j];
                     const unsigned col = en & 0xffffu, ib = (en >> 16) & 0xffu, pbv = (en >> 24) & 1u, sg = (en >> 25) & 1u;
                     if (ib == (unsigned)S.n_m2) continue;                // padding
@@ -664,7 +664,8 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
                 }
             }
         }
-        const int e0 = __ldg(S.cls_off + c), e1 = __ldg(S.cls_off + c + 1);
+        // c < 0: these alpha masks have no beta partner (the opposite-spin doubles live elsewhere or vanish)
+        const int e0 = c >= 0 ? __ldg(S.cls_off + c) : 0, e1 = c >= 0 ? __ldg(S.cls_off + c + 1) : 0;
         unsigned nx[MQC_SG_R];
 #pragma unroll
         for (int r = 0; r < MQC_SG_R; ++r) nx[r] = e0 < e1 ? __ldg(S.ell_b1 + (size_t)e0 * nB + jc[r]) : 0u;

@@ -48,6 +48,9 @@ CASES = [
     (8, 8, "lex", {"tile_bits": 12, "grad_tile_bits": 10}),
     (6, 2, "blocked", {"tile_bits": 8, "grad_tile_bits": 8}),                     # dilute sector
     (8, 8, "blocked", {"sigma": 0}),                                               # compact state + X-group H kernel
+    (6, 6, "blocked", {"sigma_ab": 1, "tile_bits": 8, "grad_tile_bits": 8}),       # opposite-spin doubles in the sign-adjusted basis
+    (7, 6, "lex", {"sigma_ab": 1, "sigma_stage": 0, "tile_bits": 10, "grad_tile_bits": 10}),
+    (5, 4, "blocked", {"sigma_ab": 1}),
     (4, 4, "blocked", {"compact": 0}),
     (4, 4, "lex", {"mode": 0}),                                  # one factor per pass
     (4, 2, "lex", {"tile_bits": 6, "grad_tile_bits": 6, "low_bits": 2, "compact": 0}),

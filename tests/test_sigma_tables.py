@@ -78,3 +78,28 @@ def test_non_fermionic_terms_fall_back():
     tab = (np.concatenate([x, extra_x]), np.concatenate([z, extra_z]), np.concatenate([c, [0.3, -0.2]]))
     out, shape, nfb = _lib.sigma_host_apply(2 * n_orb, 2, 2, tab, None)
     assert nfb >= 2
+
+
+@pytest.mark.parametrize("n_orb,na,nb", [(4, 2, 2), (6, 3, 3), (6, 2, 3)])
+def test_opposite_spin_doubles_are_extracted(n_orb, na, nb):
+    """The alpha-beta double excitations go to their own tables (csrc/mqc_sigma_ab.h): for a generic two-body
+    Hamiltonian every X-mask group with two alpha and two beta flipped qubits is recognised (its weights pass the
+    spectator verification), i.e. [n (n - 1) / 2]^2 groups with 4 ordered (ij, kl) weights each."""
+    h1, eri = random_fragment_integrals(n_orb, 1234)
+    tab = fragment_term_table(h1, eri, 0, 0.0, 0.25)
+    n_terms, n_weights = _lib.sigma_ab_info(2 * n_orb, na, nb, tab)
+    npairs = n_orb * (n_orb - 1) // 2
+    assert n_weights == 4 * npairs * npairs
+    x = np.asarray(tab[0], dtype=np.uint64)
+    alpha = sum(1 << (2 * n_orb - 1 - 2 * p) for p in range(n_orb))
+    beta = alpha >> 1
+    pop = lambda v: np.array([bin(int(t)).count("1") for t in v])
+    assert n_terms == int(((pop(x & np.uint64(alpha)) == 2) & (pop(x & np.uint64(beta)) == 2)).sum())
+    # an operator that is NOT a number-conserving two-body operator keeps its terms on the generic path
+    # (a Z on a spectator qubit that is not part of the Jordan-Wigner string of the two excitations)
+    bad = (np.array([0b11110000], np.uint64), np.array([0b00000100], np.uint64), np.array([1.0]))
+    assert _lib.sigma_ab_info(8, 2, 2, bad) == (0, 0)
+    ok = (np.array([0b11110000], np.uint64), np.array([0], np.uint64), np.array([1.0]))          # XXXX on alpha0 beta0 alpha1 beta1
+    assert _lib.sigma_ab_info(8, 2, 2, ok) == (1, 4)
+    _check(4, 2, 2, ok)
+    assert _lib.sigma_host_apply(8, 2, 2, bad)[2] == 1                  # ... and is reported as a fallback term
