@@ -82,6 +82,9 @@ def load():
         except Exception as exc:  # no nvcc on the box and no prebuilt library
             if not os.path.exists(path):
                 raise MqcError("CUDA extension libmqc_b200.so is missing and could not be built: %s" % exc)
+            import warnings
+            warnings.warn("libmqc_b200.so is OLDER than its sources and the rebuild failed (%s): running the stale binary"
+                          % str(exc).splitlines()[0])
     lib = C.CDLL(path)
     lib.mqc_last_error.restype = C.c_char_p
     lib.mqc_last_error.argtypes = []

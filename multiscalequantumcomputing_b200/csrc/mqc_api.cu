@@ -183,7 +183,7 @@ struct mqc_solver {
     int sp2 = 1, sp2_warps = 4, sp2_list = 1, sp2_smem_kb = 220, sp2_team = 0;
     // compact sector storage (mqc_cplan.h): the state is the matrix C[alpha string][beta string];
     // cpsi / clam ping-pong between the layouts of consecutive passes
-    int compact = 1, csweep_threads = 128, csweep_ctas = 0;
+    int compact = 1, csweep_threads = 128, csweep_ctas = 0, csweep_snake = 1;
     bool use_compact = false;
     MqcCPlan cplan[2];
     CPlanDev cdev[2];
@@ -1274,6 +1274,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "rdm_gram") s->rdm_gram = (int)value;
     else if (k == "csweep_threads") { if (value != 32 && value != 64 && value != 128 && value != 256 && value != 512) throw MqcError("csweep_threads must be 32, 64, 128, 256 or 512"); s->csweep_threads = (int)value; }
     else if (k == "csweep_ctas") s->csweep_ctas = (int)value;
+    else if (k == "csweep_snake") s->csweep_snake = (int)value;
     else if (k == "sp2") s->sp2 = (int)value;
     else if (k == "sp2_list") s->sp2_list = (int)value;
     else if (k == "sp2_team") { if (value != 0 && value != 1 && value != 2 && value != 4) throw MqcError("sp2_team must be 0 (auto), 1, 2 or 4"); s->sp2_team = (int)value; }
@@ -1292,7 +1293,21 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
 int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value) {
     MQC_TRY
     if (!s || !key) throw MqcError("null argument");
-    for (mqc_solver* m : s->members) { invalidate_graphs(m); set_option_rank(m, key, value); }
+    // options that shape the schedules, layouts, plans and uploaded tables are frozen by mqc_set_ansatz
+    static const char* frozen[] = {"tile_bits", "low_bits", "grad_tile_bits", "mode", "sector", "sparse_tiles", "sp2", "compact",
+                                   "sigma_blocked", "csweep_snake", nullptr};
+    if (s->have_ansatz)
+        for (const char** f = frozen; *f; ++f)
+            if (std::string(key) == *f)
+                throw MqcError(std::string("option '") + key + "' must be set before mqc_set_ansatz (it shapes the schedules and device tables)");
+    for (mqc_solver* m : s->members) {
+        invalidate_graphs(m);
+        set_option_rank(m, key, value);
+        if (std::string(key) == "sigma" || std::string(key) == "sigma_ab") {      // Hamiltonian tables are rebuilt on the next evaluation
+            m->sig.ready = false;
+            m->lay[0].sham_ready = m->lay[1].sham_ready = false;
+        }
+    }
     MQC_CATCH
 }
 
@@ -1463,7 +1478,21 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
             const MqcCPlan& PL = s->cplan[w];
             D.pass.upload(PL.pass.empty() ? std::vector<MqcCPassDev>(1) : PL.pass, s->stream);
             D.cls.upload(PL.cls, s->stream); D.fac.upload(PL.fac, s->stream); D.maps.upload(PL.maps, s->stream);
-            D.tiles.upload(PL.tiles, s->stream); D.live_tab.upload(PL.live_tab, s->stream);
+            // Tiles are listed heaviest first and CTA b starts on SM b mod n_sm: deal them to the SMs in
+            // boustrophedon order (row r of n_sm tiles reversed when r is odd) so that every SM gets the same
+            // mix of heavy and light tiles (measured before: 23 % of the SM-cycles idle at the end of a pass).
+            std::vector<uint32_t> tiles = PL.tiles;
+            if (s->csweep_snake) {
+                const size_t W = (size_t)std::max(1, s->n_sm);
+                for (const MqcCPassDev& P : PL.pass) {
+                    if (!P.tiles_explicit) continue;
+                    for (size_t r0 = W; r0 < P.n_tiles; r0 += 2 * W) {
+                        const size_t r1 = std::min<size_t>(P.n_tiles, r0 + W);
+                        std::reverse(tiles.begin() + P.tile_off + r0, tiles.begin() + P.tile_off + r1);
+                    }
+                }
+            }
+            D.tiles.upload(tiles, s->stream); D.live_tab.upload(PL.live_tab, s->stream);
             D.prog_hdr.upload(PL.prog_hdr, s->stream); D.prog.upload(PL.prog, s->stream);
         }
         if (s->use_compact) {
@@ -1488,6 +1517,8 @@ int mqc_set_ansatz(mqc_solver_t* L, int32_t n_factors, const int32_t* kind, cons
         throw MqcError("bad arguments");
     if (ref_index >> L->n) throw MqcError("reference index outside the register");
     if (L->n_ranks > 1 && L->mode != 1) throw MqcError("a sharded state needs mode = 1 (tile sweep)");
+    if (L->comm_mode == 2 && L->connected)
+        throw MqcError("this rank's buffers are mapped by its peers (mqc_shard_connect): create a new handle for a new ansatz");
     for (size_t i = 0; i < L->members.size(); ++i)
         set_ansatz_rank(L->members[i], n_factors, kind, idx4, theta_index, n_theta, ref_index, i ? L : nullptr);
     MQC_CATCH

@@ -57,3 +57,20 @@ def test_no_cpu_fallback():
         hd.energy_grad(np.zeros(F.n_theta))
     with pytest.raises(_lib.MqcError, match="no CUDA device"):
         hd.state(np.zeros(F.n_theta))
+
+
+def test_schedule_options_are_frozen_by_set_ansatz():
+    """Options that shape schedules / layouts / plans cannot change under an existing ansatz (they would
+    silently desynchronise the launch path from the tables); launch-time options still can."""
+    import numpy as np
+    from multiscalequantumcomputing_b200.uccsd import uccsd_factors
+    F = uccsd_factors(4, 4)
+    h = _lib.Handle(8)
+    h.set_option("tile_bits", 6)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    for key in ("mode", "sector", "sparse_tiles", "sp2", "tile_bits", "grad_tile_bits", "low_bits", "compact"):
+        with pytest.raises(_lib.MqcError):
+            h.set_option(key, 0 if key != "tile_bits" else 7)
+    h.set_option("csweep_threads", 64)
+    h.set_option("sigma_stage", 0)
+    h.close()
