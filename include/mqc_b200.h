@@ -104,6 +104,18 @@ int mqc_update_hamiltonian_coeffs(mqc_solver_t* s, int64_t n_terms, const double
 int mqc_set_ansatz(mqc_solver_t* s, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
                    const int32_t* theta_index, int32_t n_theta, uint64_t ref_index);
 
+/* Same, with an angle scale per factor: factor k rotates by theta_scale[k] * theta[theta_index[k]] and
+ * dE/dtheta[t] = sum_{k: theta_index[k] = t} theta_scale[k] * dE/d(angle_k).  This is how a generator that is a
+ * linear combination of excitations, A = sum_m c_m (T_m - T_m^+) (the reference's spin-adapted fermionic pool,
+ * mqc/solver/dmet_solver_vqechem.py:35-41 'spin_sym': 'sa'), enters the factorised ansatz: its terms are
+ * consecutive factors with one shared parameter and theta_scale = c_m (first-order product form).  NULL = all 1.
+ * kind 3 (compact sector storage only): number-dressed single n_c (a_a^+ a_i - h.c.), idx = {i, a, c, -1}: the
+ * rotation of kind 1 restricted to determinants with spin orbital c occupied (what normal ordering leaves of a
+ * two-body generator whose creation and annihilation index sets overlap). */
+int mqc_set_ansatz_scaled(mqc_solver_t* s, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
+                          const int32_t* theta_index, const double* theta_scale, int32_t n_theta,
+                          uint64_t ref_index);
+
 /* Replaces: `ansatz.energy(params)`, called by scipy.optimize.minimize at
  * mqc/solver/dmet_interface.py:295. */
 int mqc_energy(mqc_solver_t* s, const double* theta, double* energy);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "mqc_set_option": [_H, C.c_char_p, C.c_int64],
     "mqc_set_hamiltonian": [_H, C.c_int64, _u64p, _u64p, _f64p, _f64p],
     "mqc_set_ansatz": [_H, C.c_int32, _i32p, _i32p, _i32p, C.c_int32, C.c_uint64],
+    "mqc_set_ansatz_scaled": [_H, C.c_int32, _i32p, _i32p, _i32p, _f64p, C.c_int32, C.c_uint64],
     "mqc_update_hamiltonian_coeffs": [_H, C.c_int64, _f64p, _f64p],
     "mqc_energy": [_H, _f64p, _f64p],
     "mqc_energy_grad": [_H, _f64p, _f64p, _f64p],
@@ -187,11 +188,18 @@ class Handle:
         ci = np.ascontiguousarray(c.imag)
         check(self.lib.mqc_update_hamiltonian_coeffs(self.h, len(c), ptr(cr, _f64p), ptr(ci, _f64p)))
 
-    def set_ansatz(self, kind, idx, theta_index, n_theta, ref_index):
+    def set_ansatz(self, kind, idx, theta_index, n_theta, ref_index, theta_scale=None):
         k = np.ascontiguousarray(kind, dtype=np.int32)
         ix = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, 4)
         ti = np.ascontiguousarray(theta_index, dtype=np.int32)
-        check(self.lib.mqc_set_ansatz(self.h, len(k), ptr(k, _i32p), ptr(ix, _i32p), ptr(ti, _i32p), int(n_theta), int(ref_index)))
+        if theta_scale is None:
+            check(self.lib.mqc_set_ansatz(self.h, len(k), ptr(k, _i32p), ptr(ix, _i32p), ptr(ti, _i32p), int(n_theta), int(ref_index)))
+        else:
+            sc = np.ascontiguousarray(theta_scale, dtype=np.float64)
+            if sc.shape != (len(k),):
+                raise ValueError("theta_scale must have one entry per factor")
+            check(self.lib.mqc_set_ansatz_scaled(self.h, len(k), ptr(k, _i32p), ptr(ix, _i32p), ptr(ti, _i32p), ptr(sc, _f64p),
+                                                 int(n_theta), int(ref_index)))
         self.n_theta = int(n_theta)
 
     def _theta(self, theta):

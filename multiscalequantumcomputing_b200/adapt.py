@@ -8,9 +8,10 @@ iteration by `ansatz.update(params, niter)` inside `imp_optimizer.run`
 VQEChem is not in the tree, so this is the published ADAPT-VQE algorithm (Grimsley et al.,
 Nat. Commun. 10, 3007) on the same surface:
 
-* pool: every spin-conserving generalized single `a_q^+ a_p - h.c.` and double
-  `a_r^+ a_s^+ a_q a_p - h.c.` over spin orbitals (Jordan-Wigner, factorised form - the same factor
-  type the UCCSD sweep applies);
+* pool (`pools.py`): ``"sa"`` - the reference's spin-adapted fermionic pool (singlet generalized singles and
+  doubles, 66 operators for four orbitals as in `test/testlog_vqe:23-24`; every operator is a linear combination
+  of excitations that enters the ansatz in product form with one parameter, `mqc_set_ansatz_scaled`) - or
+  ``"generalized"``: every spin-conserving generalized single and double over spin orbitals;
 * pool gradient: dE/dtheta_k at theta_k = 0 of operator k appended AFTER the current ansatz.  The
   adjoint sweep yields all of them in ONE energy+gradient evaluation of the ansatz
   "chosen factors followed by the whole pool at zero angle" (zero-angle factors are identities, so
@@ -25,6 +26,7 @@ from itertools import combinations
 
 import numpy as np
 
+from .pools import generalized_spin_orbital_pool, singlet_gsd_pool
 from .uccsd import FactorList, reference_index
 
 
@@ -50,11 +52,20 @@ class ADAPTAnsatz:
     `mqc_set_ansatz` whenever the ansatz grows."""
 
     def __init__(self, n_qubits, term_table, n_elec, device=0, options=None, nu=10, eps=1e-5,
-                 max_ops=200, backend=None):
+                 max_ops=200, backend=None, pool="sa"):
         self.n_qubits, self.table, self.n_elec = n_qubits, term_table, n_elec
         self.n_orb = n_qubits // 2
         self.ref_index = reference_index(n_qubits, n_elec)
-        self.pool_kind, self.pool_idx = generalized_pool(self.n_orb)
+        if pool == "sa":
+            self.pool_ops = singlet_gsd_pool(self.n_orb)
+        elif pool == "generalized":
+            self.pool_ops = generalized_spin_orbital_pool(self.n_orb)
+        else:
+            raise ValueError("unknown operator pool %r ('sa' or 'generalized')" % (pool,))
+        self.pool_name = pool
+        print_pool = (options or {}).get("verbose") if isinstance(options, dict) else False
+        if print_pool:
+            print(" Number of Operator: %6d" % len(self.pool_ops))
         self.nu, self.eps, self.max_ops = nu, eps, max_ops
         self.chosen = []
         self.converged = False
@@ -71,11 +82,18 @@ class ADAPTAnsatz:
 
     # -- factor lists ---------------------------------------------------------------------
     def _factors(self, with_pool):
-        ids = list(self.chosen) + (list(range(len(self.pool_kind))) if with_pool else [])
-        kind = self.pool_kind[ids] if ids else np.zeros(0, np.int32)
-        idx = self.pool_idx[ids] if ids else np.zeros((0, 4), np.int32)
-        n = len(ids)
-        return FactorList(self.n_qubits, kind, idx, np.arange(n, dtype=np.int32), n, self.ref_index)
+        """Chosen operators (one parameter each, possibly several factors) followed, for the gradient screen, by the
+        whole pool at zero angle."""
+        ids = list(self.chosen) + (list(range(len(self.pool_ops))) if with_pool else [])
+        if not ids:
+            return FactorList(self.n_qubits, np.zeros(0, np.int32), np.zeros((0, 4), np.int32), np.zeros(0, np.int32), 0,
+                              self.ref_index)
+        kind = np.concatenate([self.pool_ops[k][0] for k in ids])
+        idx = np.concatenate([self.pool_ops[k][1] for k in ids])
+        scale = np.concatenate([self.pool_ops[k][2] for k in ids])
+        theta_index = np.concatenate([np.full(len(self.pool_ops[k][0]), t, dtype=np.int32) for t, k in enumerate(ids)])
+        plain = bool(np.all(scale == 1.0))
+        return FactorList(self.n_qubits, kind, idx, theta_index, len(ids), self.ref_index, None if plain else scale)
 
     @property
     def factors(self):
@@ -90,7 +108,8 @@ class ADAPTAnsatz:
             self._ans = UCCSDAnsatz(self.n_qubits, self.table, factors, device=self._device, options=self._options)
         else:                                   # same handle, same Hamiltonian tables: only the ansatz changes
             self._ans.factors = factors
-            self._ans.handle.set_ansatz(factors.kind, factors.idx, factors.theta_index, factors.n_theta, factors.ref_index)
+            self._ans.handle.set_ansatz(factors.kind, factors.idx, factors.theta_index, factors.n_theta, factors.ref_index,
+                                        getattr(factors, "theta_scale", None))
             self._ans._cache_theta = None
 
     # -- reference surface ----------------------------------------------------------------
@@ -104,7 +123,7 @@ class ADAPTAnsatz:
         """dE/dtheta of every pool operator appended at zero angle after the current ansatz."""
         full = self._factors(with_pool=True)
         self._program(full)
-        th = np.concatenate([np.asarray(params, dtype=np.float64), np.zeros(len(self.pool_kind))])
+        th = np.concatenate([np.asarray(params, dtype=np.float64), np.zeros(len(self.pool_ops))])
         e, g = self._ans._eval(th) if hasattr(self._ans, "_eval") else self._ans.energy_grad(th)
         self.n_evals += 1
         return e, np.array(g[len(self.chosen):])

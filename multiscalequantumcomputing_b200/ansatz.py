@@ -27,7 +27,8 @@ class UCCSDAnsatz:
         for k, v in (options or {}).items():
             self.handle.set_option(k, v)
         self.handle.set_hamiltonian(self.xmask, self.zmask, self.coeff)
-        self.handle.set_ansatz(factors.kind, factors.idx, factors.theta_index, factors.n_theta, factors.ref_index)
+        self.handle.set_ansatz(factors.kind, factors.idx, factors.theta_index, factors.n_theta, factors.ref_index,
+                               getattr(factors, "theta_scale", None))
         self._params = np.zeros(factors.n_theta)
         self._niter = 0
         self._energy = None

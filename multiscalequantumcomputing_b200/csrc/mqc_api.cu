@@ -171,6 +171,7 @@ struct mqc_solver {
     DevBuf<double> theta, mail, red, rdm_acc, rdm_gpart, rdm_g1part, rdm_out;
     int rdm_gram = 1;                // K4 on the compact matrix as a Gram update (mqc_rdm.cuh); 0: literal loops with atomics
     DevBuf<int> theta_index, err;
+    DevBuf<double> theta_scale, gtheta;      // per-factor angle scale; gradient with respect to the parameters
     DevBuf<MqcTileFactor> tf[2];
     DevBuf<uint16_t> dlut[2];       // pair-address tables of the dense tile kernel
     MqcSparsePlan plan[2];          // compressed-sector tile plan per schedule (host copy of the pass records)
@@ -209,7 +210,8 @@ struct mqc_solver {
     bool have_ham = false, have_ansatz = false;
 
     std::vector<MqcFactor> fac;     // logical coordinates
-    std::vector<int> fac_theta;
+    std::vector<int> fac_theta;     // parameter index of factor k (host copy)
+    std::vector<double> fac_scale;  // angle of factor k = fac_scale[k] * theta[fac_theta[k]]
     int n_theta = 0;
     u64 ref_index = 0;
     bool conserving = false;
@@ -265,6 +267,18 @@ static MqcFactor make_factor(int n, int kind, const int32_t* ix, int slot, int t
         u64 D = 1ull << i;
         int p1 = ladder(D, i, 0), p2 = ladder(D, a, 1);
         sign0 = (p1 + p2) & 1;
+    } else if (kind == 3) {
+        // number-dressed single n_c (a_a^+ a_i - h.c.): the rotation of kind 1 on the determinants with c occupied
+        const int i = ix[0], a = ix[1], c = ix[2];
+        chk(i); chk(a); chk(c);
+        if (i == a || c == i || c == a) throw MqcError("dressed single needs three distinct orbitals");
+        mq = (1ull << i) | (1ull << a);
+        vq = 1ull << i;
+        zq = between_mask_qubits(i, a);
+        u64 D = 1ull << i;
+        int p1 = ladder(D, i, 0), p2 = ladder(D, a, 1);
+        sign0 = (p1 + p2) & 1;
+        f.ctrl = qubit_to_logical(1ull << c, n);
     } else if (kind == 2) {
         const int i = ix[0], j = ix[1], a = ix[2], b = ix[3];
         chk(i); chk(j); chk(a); chk(b);
@@ -276,7 +290,7 @@ static MqcFactor make_factor(int n, int kind, const int32_t* ix, int slot, int t
         int p1 = ladder(D, i, 0), p2 = ladder(D, j, 0), p3 = ladder(D, b, 1), p4 = ladder(D, a, 1);
         sign0 = (p1 + p2 + p3 + p4) & 1;
     } else {
-        throw MqcError("unknown factor kind (1 = single, 2 = double)");
+        throw MqcError("unknown factor kind (1 = single, 2 = double, 3 = number-dressed single)");
     }
     f.m = qubit_to_logical(mq, n);
     f.v = qubit_to_logical(vq, n);
@@ -802,7 +816,7 @@ static void forward_compact(mqc_solver* s, int which, const double* theta) {
         s->theta_host.assign(theta, theta + s->n_theta);
         CK(cudaMemcpyAsync(s->theta.p, s->theta_host.data(), sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
     }
-    if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->cs.p, nfac); s->counters[0]++; }
+    if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->theta_scale.p, s->cs.p, nfac); s->counters[0]++; }
     s->ccur = 0;
     const size_t cnt = (size_t)PL.nA * PL.nB;
     CK(cudaMemsetAsync(s->cpsi[0].p, 0, sizeof(double2) * cnt, s->stream));
@@ -826,7 +840,7 @@ static void forward(mqc_solver* L, int which, const double* theta) {
             s->theta_host.assign(theta, theta + s->n_theta);
             CK(cudaMemcpyAsync(s->theta.p, s->theta_host.data(), sizeof(double) * s->n_theta, cudaMemcpyHostToDevice, s->stream));
         }
-        if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->cs.p, nfac); s->counters[0]++; }
+        if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->theta_scale.p, s->cs.p, nfac); s->counters[0]++; }
         CK(cudaMemsetAsync(s->psi.p, 0, sizeof(double2) * s->dim, s->stream));
         const u64 ref_phys = (s->mode == 1) ? mqc_map_mask(s->ref_index, s->sched[which].phys_init) : s->ref_index;
         if ((int)(ref_phys >> s->n_local) == s->rank) {
@@ -1047,7 +1061,7 @@ static void happly(mqc_solver* L, int which, const std::vector<HamView>& views, 
 static void reverse_sweep(mqc_solver* L, int which) {
     for (mqc_solver* s : L->members) {
         CK(cudaSetDevice(s->device));
-        CK(cudaMemsetAsync(s->grad_p(), 0, sizeof(double) * std::max(1, s->n_theta), s->stream));
+        CK(cudaMemsetAsync(s->grad_p(), 0, sizeof(double) * std::max<size_t>(1, s->fac.size()), s->stream));
     }
     const int nfac = (int)L->fac.size();
     if (L->use_compact) {
@@ -1353,7 +1367,8 @@ int mqc_update_hamiltonian_coeffs(mqc_solver_t* L, int64_t n_terms, const double
 }
 
 static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
-                            const int32_t* theta_index, int32_t n_theta, uint64_t ref_index, const mqc_solver* copy_from) {
+                            const int32_t* theta_index, const double* theta_scale, int32_t n_theta, uint64_t ref_index,
+                            const mqc_solver* copy_from) {
     const int n = s->n;
     if (copy_from) {
         s->fac = copy_from->fac; s->conserving = copy_from->conserving;
@@ -1364,9 +1379,9 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         bool conserving = (n % 2 == 0);
         for (int k = 0; k < n_factors; ++k) {
             if (theta_index[k] < 0 || theta_index[k] >= n_theta) throw MqcError("theta_index out of range");
-            fac.push_back(make_factor(n, kind[k], idx4 + 4 * k, k, theta_index[k]));
+            fac.push_back(make_factor(n, kind[k], idx4 + 4 * k, k, k));          // gradients accumulate per factor (k_grad_combine)
             const int32_t* ix = idx4 + 4 * k;
-            if (kind[k] == 1) { if ((ix[0] ^ ix[1]) & 1) conserving = false; }
+            if (kind[k] == 1 || kind[k] == 3) { if ((ix[0] ^ ix[1]) & 1) conserving = false; }
             else {
                 const int sa = (ix[0] & 1) + (ix[1] & 1), sc = (ix[2] & 1) + (ix[3] & 1);
                 if (sa != sc) conserving = false;
@@ -1396,6 +1411,9 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         }
     }
     s->n_theta = n_theta;
+    s->fac_theta.assign(theta_index, theta_index + n_factors);
+    s->fac_scale.assign(n_factors, 1.0);
+    if (theta_scale) s->fac_scale.assign(theta_scale, theta_scale + n_factors);
     s->ref_index = ref_index;
     s->na = s->nb = 0;
     for (int q = 0; q < n; ++q)
@@ -1425,6 +1443,10 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         }
         s->use_compact = ok;
     }
+    for (const MqcFactor& f : s->fac)
+        if (f.ctrl && !s->use_compact)
+            throw MqcError("number-dressed factors (kind 3) need the compact sector storage: an unsharded handle, an ansatz that "
+                           "conserves (N_alpha, N_beta), options compact = 1, mode = 1, sector = 1");
     for (int w = 0; w < 2; ++w) {
         s->lay[w].reset();
         s->lay[w].phys = s->sched[w].phys_final;
@@ -1440,9 +1462,13 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         require_gpu(s);
         std::vector<int> ti(n_factors);
         for (int k = 0; k < n_factors; ++k) ti[k] = theta_index[k];
-        s->theta_index.upload(ti, s->stream);
+        s->theta_index.upload(ti.empty() ? std::vector<int>(1, 0) : ti, s->stream);
+        std::vector<double> sc(std::max(1, n_factors), 1.0);
+        if (theta_scale) for (int k = 0; k < n_factors; ++k) sc[k] = theta_scale[k];
+        s->theta_scale.upload(sc, s->stream);
         s->theta.alloc(std::max(1, n_theta));
-        s->mail.alloc(MQC_MAIL_GRAD + std::max(1, n_theta));
+        s->gtheta.alloc(std::max(1, n_theta));
+        s->mail.alloc(MQC_MAIL_GRAD + std::max(1, n_factors));
         CK(cudaMemsetAsync(s->mail.p, 0, sizeof(double) * s->mail.n, s->stream));
         s->err.alloc(1);
         CK(cudaMemsetAsync(s->err.p, 0, sizeof(int), s->stream));
@@ -1512,8 +1538,16 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
     }
 }
 
+int mqc_set_ansatz_scaled(mqc_solver_t* L, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
+                          const int32_t* theta_index, const double* theta_scale, int32_t n_theta, uint64_t ref_index);
+
 int mqc_set_ansatz(mqc_solver_t* L, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
                    const int32_t* theta_index, int32_t n_theta, uint64_t ref_index) {
+    return mqc_set_ansatz_scaled(L, n_factors, kind, idx4, theta_index, nullptr, n_theta, ref_index);
+}
+
+int mqc_set_ansatz_scaled(mqc_solver_t* L, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
+                          const int32_t* theta_index, const double* theta_scale, int32_t n_theta, uint64_t ref_index) {
     MQC_TRY
     if (!L || n_factors < 0 || n_theta < 0 || (n_factors && (!kind || !idx4 || !theta_index)))
         throw MqcError("bad arguments");
@@ -1522,7 +1556,7 @@ int mqc_set_ansatz(mqc_solver_t* L, int32_t n_factors, const int32_t* kind, cons
     if (L->comm_mode == 2 && L->connected)
         throw MqcError("this rank's buffers are mapped by its peers (mqc_shard_connect): create a new handle for a new ansatz");
     for (size_t i = 0; i < L->members.size(); ++i)
-        set_ansatz_rank(L->members[i], n_factors, kind, idx4, theta_index, n_theta, ref_index, i ? L : nullptr);
+        set_ansatz_rank(L->members[i], n_factors, kind, idx4, theta_index, theta_scale, n_theta, ref_index, i ? L : nullptr);
     MQC_CATCH
 }
 
@@ -1631,7 +1665,13 @@ static void evaluation_body(mqc_solver* s, int which, const double* theta) {
     record_ev(s, 2);
     if (which == 1) {
         reverse_sweep(s, which);
-        reduce_mail(s, MQC_MAIL_GRAD + s->n_theta);
+        reduce_mail(s, MQC_MAIL_GRAD + (int)s->fac.size());
+        {   // per-factor gradients -> parameters (tied parameters, angle scales)
+            CK(cudaSetDevice(s->device));
+            CK(cudaMemsetAsync(s->gtheta.p, 0, sizeof(double) * std::max(1, s->n_theta), s->stream));
+            const int nfac = (int)s->fac.size();
+            if (nfac) { k_grad_combine<<<(nfac + 255) / 256, 256, 0, s->stream>>>(reduced_grad(s), s->theta_index.p, s->theta_scale.p, s->gtheta.p, nfac); s->counters[0]++; }
+        }
         record_ev(s, 3);
     }
 }
@@ -1716,7 +1756,7 @@ static void run_energy_grad(mqc_solver* s, const double* theta, double* energy, 
     CK(cudaSetDevice(s->device));
     CK(cudaMemcpyAsync(val, reduced_scalars(s), 2 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     if (grad && s->n_theta)
-        CK(cudaMemcpyAsync(grad, reduced_grad(s), sizeof(double) * s->n_theta, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaMemcpyAsync(grad, s->gtheta.p, sizeof(double) * s->n_theta, cudaMemcpyDeviceToHost, s->stream));
     sync_all(s);
     finish_timing(s, true);
     *energy = val[0];
@@ -2024,7 +2064,7 @@ int mqc_sparse_plan_host_state(mqc_solver_t* s, int32_t which, const double* the
     if (!PL.ok) throw MqcError("no sparse plan for this schedule");
     const size_t dim = (size_t)1 << s->n;
     std::vector<double> re(dim, 0.0), im(dim, 0.0), cv(s->fac.size()), sv(s->fac.size());
-    for (size_t k = 0; k < s->fac.size(); ++k) { cv[k] = std::cos(theta[s->fac[k].theta]); sv[k] = std::sin(theta[s->fac[k].theta]); }
+    for (size_t k = 0; k < s->fac.size(); ++k) { const double ang = s->fac_scale[k] * theta[s->fac_theta[k]]; cv[k] = std::cos(ang); sv[k] = std::sin(ang); }
     re[mqc_map_mask(s->ref_index, S.phys_init)] = 1.0;
     mqc_sparse_plan_forward_host(S, PL, re, im, cv, sv);
     for (size_t i = 0; i < dim; ++i) {
@@ -2082,7 +2122,7 @@ int mqc_cplan_host_state(mqc_solver_t* s, int32_t which, const double* theta, do
     if (!s->use_compact || !s->cplan[which].ok) throw MqcError("no compact-sector plan (the ansatz must conserve N_alpha and N_beta; option compact=1)");
     const MqcCPlan& PL = s->cplan[which];
     std::vector<double> cv(s->fac.size()), sv(s->fac.size());
-    for (size_t k = 0; k < s->fac.size(); ++k) { cv[k] = std::cos(theta[s->fac[k].theta]); sv[k] = std::sin(theta[s->fac[k].theta]); }
+    for (size_t k = 0; k < s->fac.size(); ++k) { const double ang = s->fac_scale[k] * theta[s->fac_theta[k]]; cv[k] = std::cos(ang); sv[k] = std::sin(ang); }
     const std::vector<double> C = mqc_cplan_forward_host(PL, cv, sv);
     std::memset(re_im, 0, sizeof(double) * 2 * (size_t)n_amplitudes);
     const int n = s->n;

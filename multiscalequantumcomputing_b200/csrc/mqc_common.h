@@ -29,6 +29,8 @@ typedef unsigned long long u64;
 #define MQC_MAX_PASS_FACTORS 320
 
 struct MqcFactor {          // one excitation factor in some bit coordinate system
+    u64 ctrl;               // control mask: the factor only acts on determinants with these bits set (number-dressed
+                            // single n_c (a_a^+ a_i - h.c.)); 0 for plain singles / doubles.  Compact sector path only.
     u64 m;                  // flip mask (2 or 4 bits)
     u64 v;                  // pattern of the "lower" partner on the m bits
     u64 z;                  // parity mask (never overlaps m)

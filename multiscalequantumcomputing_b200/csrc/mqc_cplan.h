@@ -293,12 +293,12 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
         }
         // factors in orbital space
         D.fac_off = PL.fac.size();
-        std::vector<uint32_t> mA(D.nf), vA(D.nf), zAi(D.nf), mB(D.nf), vB(D.nf), zBi(D.nf);
+        std::vector<uint32_t> mA(D.nf), vA(D.nf), zAi(D.nf), mB(D.nf), vB(D.nf), zBi(D.nf), cA(D.nf), cB(D.nf);
         for (int f = 0; f < D.nf; ++f) {
             const MqcFactor& F = fac[S.tf[P.f0 + f].slot];
             uint32_t za, zb;
-            split(F.m, mA[f], mB[f]); split(F.v, vA[f], vB[f]); split(F.z, za, zb);
-            if ((mA[f] & ~SA[p]) || (mB[f] & ~SB[p])) { PL.why = "factor moves an inactive orbital"; return PL; }      // the schedule guarantees this
+            split(F.m, mA[f], mB[f]); split(F.v, vA[f], vB[f]); split(F.z, za, zb); split(F.ctrl, cA[f], cB[f]);
+            if ((mA[f] & ~SA[p]) || (mB[f] & ~SB[p]) || (cA[f] & ~SA[p]) || (cB[f] & ~SB[p])) { PL.why = "factor touches an inactive orbital"; return PL; }      // the schedule guarantees this
             zAi[f] = za & SA[p]; zBi[f] = zb & SB[p];
             MqcCFactor C{};
             C.zA_out = za & ~SA[p]; C.zB_out = zb & ~SB[p];
@@ -315,6 +315,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
             const std::vector<uint32_t>& fm = side ? mB : mA;
             const std::vector<uint32_t>& fv = side ? vB : vA;
             const std::vector<uint32_t>& fz = side ? zBi : zAi;
+            const std::vector<uint32_t>& fc = side ? cB : cA;
             std::vector<std::vector<uint32_t>> pats(MQC_C_KMAX);
             {
                 uint32_t sub = 0;
@@ -328,7 +329,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
                 for (int f = 0; f < D.nf; ++f) {
                     std::vector<uint32_t>& L = lists[side][(size_t)f * MQC_C_KMAX + k];
                     for (uint32_t t : pk) {
-                        if ((t & fm[f]) != fv[f]) continue;
+                        if ((t & fm[f]) != fv[f] || (t & fc[f]) != fc[f]) continue;      // lower partner; control orbitals occupied
                         L.push_back(rank(t) | (rank(t ^ fm[f]) << 7) | (((uint32_t)__builtin_popcount(t & fz[f]) & 1u) << 14));
                     }
                 }

@@ -68,13 +68,26 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ------------------------------------------------------------------------------------------
 // small utility kernels
 // ------------------------------------------------------------------------------------------
-__global__ void k_sincos(const double* __restrict__ theta, const int* __restrict__ theta_index,
+// angle of factor f = scale[f] * theta[theta_index[f]]  (scale: coefficient of the factor inside a generator that is
+// a linear combination of excitations, e.g. a spin-adapted pool operator; 1 for plain UCCSD)
+__global__ void k_sincos(const double* __restrict__ theta, const int* __restrict__ theta_index, const double* __restrict__ scale,
                          double2* __restrict__ cs, int n) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < n) {
         double s, c;
-        sincos(theta[theta_index[f]], &s, &c);
+        sincos(scale[f] * theta[theta_index[f]], &s, &c);
         cs[f] = make_double2(c, s);
+    }
+}
+
+// The sweep kernels accumulate dE/d(angle of factor f) per FACTOR; chain rule onto the parameters:
+// g_theta[theta_index[f]] += scale[f] * g_factor[f]
+__global__ void k_grad_combine(const double* __restrict__ g_factor, const int* __restrict__ theta_index, const double* __restrict__ scale,
+                               double* __restrict__ g_theta, int n) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n) {
+        const double g = g_factor[f] * scale[f];
+        if (g != 0.0) atomicAdd(g_theta + theta_index[f], g);
     }
 }
 

@@ -88,7 +88,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
     const size_t n = fac.size();
     // first factor at or after `from` that moves logical bit `bit` (n + 1: never again)
     auto next_use = [&](int bit, size_t from) -> size_t {
-        for (size_t t = from; t < n; ++t) if ((fac[t].m >> bit) & 1ull) return t;
+        for (size_t t = from; t < n; ++t) if (((fac[t].m | fac[t].ctrl) >> bit) & 1ull) return t;
         return n + 1;
     };
     auto swap_to = [&](int b, int target) {          // put logical bit b at physical position target
@@ -102,7 +102,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
         int placed = 0;
         u64 seen = 0;
         for (size_t t = 0; t < n && placed < L; ++t) {
-            u64 mm = fac[t].m & ~seen;
+            u64 mm = (fac[t].m | fac[t].ctrl) & ~seen;
             while (mm && placed < L) {
                 const int b = __builtin_ctzll(mm); mm &= mm - 1; seen |= 1ull << b;
                 swap_to(b, placed);
@@ -124,7 +124,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
         for (int p = 0; p < L; ++p) A |= 1ull << inv[p];
         size_t j = i;
         while (j < n && (int)(j - i) < cap) {
-            const u64 U = A | fac[j].m;
+            const u64 U = A | fac[j].m | fac[j].ctrl;
             if (MQC_POPC64(U) > K) break;
             A = U; ++j;
         }
@@ -135,7 +135,7 @@ static inline MqcSchedule mqc_build_schedule(int n_bits, int k_req, int low_req,
         std::vector<int> ahead;
         u64 seen = 0;
         for (size_t t = j; t < n && (int)ahead.size() < NT; ++t) {
-            u64 mm = fac[t].m & ~seen;
+            u64 mm = (fac[t].m | fac[t].ctrl) & ~seen;
             while (mm) { int b = __builtin_ctzll(mm); mm &= mm - 1; ahead.push_back(b); seen |= 1ull << b; }
             if ((int)ahead.size() >= 2 * K) break;
         }

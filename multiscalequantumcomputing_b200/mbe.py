@@ -72,7 +72,7 @@ def vqechem(h_mo, eri_mo, n_elec: int, e_nuc: float = 0.0, ncas=None, ncore=None
         aopt = (options or {}).get("adapt", {})
         ansatz = ADAPTAnsatz(2 * n_act, table, ne_act, device=device, options=(options or {}).get("gpu"),
                              nu=aopt.get("nu", 10), eps=aopt.get("eps", 1e-5), max_ops=aopt.get("max_ops", 200),
-                             backend=_ansatz_factory)
+                             backend=_ansatz_factory, pool=aopt.get("pool", "sa"))
     else:
         factors = uccsd_factors(n_act, ne_act, "blocked")
         make = _ansatz_factory or (lambda nq, tab, fac: UCCSDAnsatz(nq, tab, fac, device=device, options=(options or {}).get("gpu")))

@@ -196,7 +196,8 @@ def solve(oei_mo, one_body_mo, two_body_mo, n_imp: int, n_imp_orbs: int, chempot
         aopt = (options or {}).get("adapt", {})
         ansatz = ADAPTAnsatz(n_qubits, prob["table"], n_elec, device=device, options=(options or {}).get("gpu"),
                              nu=aopt.get("nu", 10), eps=aopt.get("eps", 1e-5), max_ops=aopt.get("max_ops", 200),
-                             backend=_ansatz_factory)
+                             backend=_ansatz_factory,
+                             pool=aopt.get("pool", "generalized" if (options or {}).get("devices") else "sa"))
         warm_start = False
     else:
         ansatz = None

@@ -34,14 +34,17 @@ class FactorList:
     theta_index: np.ndarray  # int32[n]
     n_theta: int
     ref_index: int           # amplitude index of the reference determinant
+    theta_scale: np.ndarray = None   # float64[n] angle of factor k = theta_scale[k] * theta[theta_index[k]] (None: 1)
 
     def __len__(self):
         return len(self.kind)
 
     def as_tuples(self):
+        """(kind, indices): kind 1 (i, a), kind 2 (i, j, a, b), kind 3 (i, a, c) = n_c-dressed single."""
         out = []
         for k, ix in zip(self.kind, self.idx):
-            out.append((int(k), tuple(int(v) for v in (ix[:2] if k == 1 else ix))))
+            nix = {1: 2, 2: 4, 3: 3}[int(k)]
+            out.append((int(k), tuple(int(v) for v in ix[:nix])))
         return out
 
 

@@ -69,9 +69,14 @@ def _apply_ladder_sequence(D, ops):
 
 
 def excitation_ops(kind, idx):
+    """T of the factor exp(theta (T - T^+)): kind 1 a_a^+ a_i, kind 2 a_a^+ a_b^+ a_j a_i, kind 3 the number-dressed
+    single n_c a_a^+ a_i = a_c^+ a_c a_a^+ a_i (idx = i, a, c)."""
     if kind == 1:
         i, a = idx[0], idx[1]
         return ((a, 1), (i, 0))
+    if kind == 3:
+        i, a, c = idx[0], idx[1], idx[2]
+        return ((c, 1), (c, 0), (a, 1), (i, 0))
     i, j, a, b = idx
     return ((a, 1), (b, 1), (j, 0), (i, 0))
 
@@ -124,7 +129,8 @@ def excitation_generator_matrix(kind, idx, n_qubits):
 class UCCSDOracle:
     """Dense-vector CPU restatement of the VQEChem ansatz object for a fixed factor list."""
 
-    def __init__(self, n_qubits, factors, theta_index, ref_index, ham_terms):
+    def __init__(self, n_qubits, factors, theta_index, ref_index, ham_terms, theta_scale=None):
+        """theta_scale[k]: factor k rotates by theta_scale[k] * theta[theta_index[k]] (None: 1)."""
         self.n = n_qubits
         self.factors = list(factors)
         self.theta_index = np.asarray(theta_index, dtype=np.int64)
@@ -132,12 +138,13 @@ class UCCSDOracle:
         self.ref_index = int(ref_index)
         self.xm, self.zm, self.cf = ham_terms
         self.rev = bit_reverse_table(n_qubits)
+        self.scale = np.ones(len(self.factors)) if theta_scale is None else np.asarray(theta_scale, dtype=np.float64)
 
     def state(self, theta):
         psi = np.zeros(1 << self.n, dtype=np.complex128)
         psi[self.ref_index] = 1.0
-        for (kind, idx), ti in zip(self.factors, self.theta_index):
-            psi = apply_excitation(kind, idx, theta[ti], psi, self.n, self.rev)
+        for k, ((kind, idx), ti) in enumerate(zip(self.factors, self.theta_index)):
+            psi = apply_excitation(kind, idx, self.scale[k] * theta[ti], psi, self.n, self.rev)
         return psi
 
     def h_apply(self, psi):
@@ -155,9 +162,9 @@ class UCCSDOracle:
         for k in range(len(self.factors) - 1, -1, -1):
             kind, idx = self.factors[k]
             ti = self.theta_index[k]
-            g[ti] += 2.0 * np.vdot(lam, apply_generator(kind, idx, psi, self.n, self.rev)).real
-            psi = apply_excitation(kind, idx, -theta[ti], psi, self.n, self.rev)
-            lam = apply_excitation(kind, idx, -theta[ti], lam, self.n, self.rev)
+            g[ti] += self.scale[k] * 2.0 * np.vdot(lam, apply_generator(kind, idx, psi, self.n, self.rev)).real
+            psi = apply_excitation(kind, idx, -self.scale[k] * theta[ti], psi, self.n, self.rev)
+            lam = apply_excitation(kind, idx, -self.scale[k] * theta[ti], lam, self.n, self.rev)
         return e, g
 
     def gradient(self, theta):

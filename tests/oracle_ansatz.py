@@ -13,7 +13,8 @@ class OracleAnsatz:
         self.n_qubits = n_qubits
         self.factors = factors
         self.table = term_table
-        self.orc = UCCSDOracle(n_qubits, factors.as_tuples(), factors.theta_index, factors.ref_index, term_table)
+        self.orc = UCCSDOracle(n_qubits, factors.as_tuples(), factors.theta_index, factors.ref_index, term_table,
+                               getattr(factors, "theta_scale", None))
         self._params = np.zeros(factors.n_theta)
         self._niter = 0
         self._energy = None

@@ -119,3 +119,48 @@ def test_odd_electron_reference(n, ne):
     ref = UCCSDOracle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, EMPTY).state(th)
     assert abs(h.cplan_host_state(th, 0) - ref).max() < 1e-14
     h.close()
+
+
+def test_dressed_singles_and_scaled_tied_parameters():
+    """kind 3 = n_c (a_a^+ a_i - h.c.) and per-factor angle scales (the building blocks of a spin-adapted pool
+    operator in product form): compact plan on the host against the oracle, several passes."""
+    n = 5
+    rng = np.random.default_rng(21)
+    kind, idx = [], []
+    for _ in range(70):
+        r = rng.random()
+        s1, s2 = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        if r < 0.35:
+            p, q = rng.choice(n, 2, replace=False)
+            c = int(rng.integers(0, 2 * n))
+            while c in (2 * p + s1, 2 * q + s1):
+                c = int(rng.integers(0, 2 * n))
+            kind.append(3); idx.append((2 * p + s1, 2 * q + s1, c, -1))
+        elif r < 0.55:
+            p, q = rng.choice(n, 2, replace=False)
+            kind.append(1); idx.append((2 * p + s1, 2 * q + s1, -1, -1))
+        else:
+            while True:
+                p, q, r2, t = (int(v) for v in rng.integers(0, n, 4))
+                if len({2 * p + s1, 2 * q + s2, 2 * r2 + s1, 2 * t + s2}) == 4:
+                    break
+            kind.append(2); idx.append((2 * p + s1, 2 * q + s2, 2 * r2 + s1, 2 * t + s2))
+    kind = np.array(kind, np.int32); idx = np.array(idx, np.int32)
+    ti = (np.arange(len(kind)) // 4).astype(np.int32)
+    nth = int(ti.max()) + 1
+    scale = rng.normal(0, 1, len(kind))
+    ref_index = 0b1111000000
+    h = _lib.Handle(2 * n)
+    h.set_option("tile_bits", 6)
+    h.set_ansatz(kind, idx, ti, nth, ref_index, theta_scale=scale)
+    assert h.cplan_info(0)["n_passes"] > 1
+    th = rng.normal(0, 0.3, nth)
+    tup = [(int(k), tuple(int(v) for v in ix[:{1: 2, 2: 4, 3: 3}[int(k)]])) for k, ix in zip(kind, idx)]
+    ref = UCCSDOracle(2 * n, tup, ti, ref_index, EMPTY, scale).state(th)
+    assert abs(h.cplan_host_state(th, 0) - ref).max() < 1e-14
+    # a dressed single needs the compact storage
+    hd = _lib.Handle(2 * n)
+    hd.set_option("compact", 0)
+    with pytest.raises(_lib.MqcError):
+        hd.set_ansatz(kind, idx, ti, nth, ref_index)
+    h.close(); hd.close()
