@@ -1297,8 +1297,8 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sp2_smem_kb") { if (value < 16 || value > 220) throw MqcError("sp2_smem_kb must be in [16,220]"); s->sp2_smem_kb = (int)value; }
     else if (k == "sp2_warps") { if (value < 1 || value > 8) throw MqcError("sp2_warps must be in [1,8]"); s->sp2_warps = (int)value; }
     else throw MqcError("unknown option: " + k);
-    if (s->tile_bits < 5 || s->tile_bits > 14 || s->grad_tile_bits < 5 || s->grad_tile_bits > 14)
-        throw MqcError("tile_bits and grad_tile_bits must be in [5,14] (dense tiles: <= 13 / 12)");
+    if (s->tile_bits < 5 || s->tile_bits > 16 || s->grad_tile_bits < 5 || s->grad_tile_bits > 16)
+        throw MqcError("tile_bits and grad_tile_bits must be in [5,16] (compact sector storage: <= 16; sector tiles of the dense register: <= 14; dense tiles: <= 13 / 12)");
     if (s->low_bits < -1 || s->low_bits > 6) throw MqcError("low_bits must be in [0,6] (-1: 3 for dense tiles, 0 for sector tiles)");
     if (s->tile_threads < 32 || s->tile_threads > 512 || (s->tile_threads & (s->tile_threads - 1)))
         throw MqcError("tile_threads must be a power of two in [32,512]");
