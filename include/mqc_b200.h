@@ -189,6 +189,15 @@ int mqc_cplan_host_state(mqc_solver_t* s, int32_t which, const double* theta, do
 int mqc_cplan_info(mqc_solver_t* s, int32_t which, int32_t* n_passes, int64_t* n_rows, int64_t* n_cols,
                    int64_t* smem_forward, int64_t* smem_adjoint);
 
+/* Storage of the compact sector matrix: 8 = real amplitudes, 16 = complex, 0 = the handle works on the
+ * dense register.  Every factor of the reference's ansatz (qc_uccsd/vqechem/uccsd_vqe.py:66-87, T - T^+ of
+ * real excitation operators) is a real rotation of the occupation basis and a Jordan-Wigner Hamiltonian with
+ * real integrals (dmet_interface.py:200-241) has real matrix elements, so psi and H psi never acquire an
+ * imaginary part: the handle then keeps doubles (option "real_amplitudes", default 1) and returns to complex
+ * storage by itself when a Hamiltonian term has an odd number of Y, a complex coefficient or no place in
+ * the link tables, or when mqc_load_state is given a complex vector. */
+int mqc_amplitude_bytes(mqc_solver_t* s, int32_t* bytes);
+
 /* Replaces: the `fcivec` argument of mqc/tools/rdm.py:131-138 (make_rdm1) and :157-172
  * (make_rdm12): loads a caller-supplied wave function (OpenFermion order, 2^N amplitudes,
  * interleaved re/im) as the prepared state, so that mqc_rdm12 / mqc_expectation evaluate it.

@@ -51,6 +51,7 @@ SIGNATURES = {
     "mqc_sparse_plan_host_state": [_H, C.c_int32, _f64p, _f64p, C.c_int64],
     "mqc_cplan_host_state": [_H, C.c_int32, _f64p, _f64p, C.c_int64],
     "mqc_cplan_info": [_H, C.c_int32, _i32p, _i64p, _i64p, _i64p, _i64p],
+    "mqc_amplitude_bytes": [_H, _i32p],
     "mqc_load_state": [_H, _f64p, C.c_int64],
     "mqc_sigma_host_apply": [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _u64p, _u64p, _f64p, _f64p, _f64p, _f64p,
                              _i64p, _i64p, _i64p],
@@ -269,6 +270,12 @@ class Handle:
         nr, nc, sf, sa = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         check(self.lib.mqc_cplan_info(self.h, which, C.byref(npass), C.byref(nr), C.byref(nc), C.byref(sf), C.byref(sa)))
         return dict(n_passes=npass.value, n_rows=nr.value, n_cols=nc.value, smem_forward=sf.value, smem_adjoint=sa.value)
+
+    def amplitude_bytes(self) -> int:
+        """8: real compact storage, 16: complex compact storage, 0: dense register."""
+        b = C.c_int32()
+        check(self.lib.mqc_amplitude_bytes(self.h, C.byref(b)))
+        return b.value
 
     def load_state(self, psi):
         """Make ``psi`` (OpenFermion order, 2^N complex amplitudes) the prepared state."""

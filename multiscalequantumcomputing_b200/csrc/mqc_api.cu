@@ -186,6 +186,13 @@ struct mqc_solver {
     // cpsi / clam ping-pong between the layouts of consecutive passes
     int compact = 1, csweep_threads = 128, csweep_ctas = 0, csweep_snake = 1;
     bool use_compact = false;
+    // Real amplitudes: every ansatz factor is a real rotation, so with a real Hamiltonian (even number of Y per
+    // term, real coefficients, all of it on the link-table kernel) psi and lambda never get an imaginary part
+    // and the compact buffers hold 8-byte amplitudes (half the shared-memory traffic and arithmetic of every
+    // kernel).  The handle falls back to complex storage by itself when a Hamiltonian or a loaded state is not real.
+    int real_amplitudes = 1;         // option: 0 = always complex
+    bool creal = false;              // the compact buffers hold doubles
+    DevBuf<double2> cscratch;        // complex copy of the real state for the consumers that want one
     MqcCPlan cplan[2];
     CPlanDev cdev[2];
     DevBuf<double2> cpsi[2], clam[2];
@@ -198,6 +205,7 @@ struct mqc_solver {
 
     HamHost ham, ham_fb;            // all terms / the terms the link-table kernel leaves to k_happly_sector
     SigmaTables sig;
+    int sigma_split = -1;                                 // K2 row split: -1 auto, 0 off, k: part 0 takes the first k alpha single links
     int use_sigma = 1, sigma_stage = 1, sigma_ab = 0;     // sigma_ab: opposite-spin doubles through k_sigma_ab (measured: no faster, both are shared-memory-gather bound)
     // The launch sequence of an evaluation depends on theta only through device buffers, so a
     // single-rank handle replays it as a CUDA graph from the third call on (first call: eager,
@@ -227,6 +235,10 @@ struct mqc_solver {
 };
 
 static void invalidate_graphs(mqc_solver* s);
+extern "C" {                      // defined inside the extern "C" block below
+static void drop_real(mqc_solver* s);
+static bool ham_is_real(const HamHost& H);
+}
 
 // ---------------------------------------------------------------------------------------
 // host helpers
@@ -328,16 +340,20 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_tile_sp2<true, true, TW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     MQC_SP2_ATTR(1) MQC_SP2_ATTR(2) MQC_SP2_ATTR(4)
 #define MQC_CS_ATTR(NT_, CH_) \
-    CK(cudaFuncSetAttribute(k_csweep<false, NT_, CH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); \
-    CK(cudaFuncSetAttribute(k_csweep<true, NT_, CH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    CK(cudaFuncSetAttribute(k_csweep<false, NT_, CH_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); \
+    CK(cudaFuncSetAttribute(k_csweep<true, NT_, CH_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); \
+    CK(cudaFuncSetAttribute(k_csweep<false, NT_, CH_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448)); \
+    CK(cudaFuncSetAttribute(k_csweep<true, NT_, CH_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     MQC_CS_ATTR(32, 256) MQC_CS_ATTR(64, 256) MQC_CS_ATTR(128, 256) MQC_CS_ATTR(256, 256) MQC_CS_ATTR(512, 256)
     MQC_CS_ATTR(32, 1024) MQC_CS_ATTR(64, 1024) MQC_CS_ATTR(128, 1024) MQC_CS_ATTR(256, 1024) MQC_CS_ATTR(512, 1024)
     CK(cudaFuncSetAttribute(k_sigma_ab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma_ab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_rdm_gram<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_rdm_gram<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
-    CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     s->gpu_ready = true;
 }
 
@@ -625,6 +641,7 @@ static void ensure_layout_ready(mqc_solver* s, int which) {
         build_sector_tables(s, L, s->na, s->nb);
         const bool sigma = s->use_sigma && s->n / 2 <= 18;
         if (sigma && !s->sig.ready) { invalidate_graphs(s); build_sigma(s, s->ham, s->na, s->nb, s->sig, s->ham_fb, s->use_compact && s->sigma_ab); }
+        if (s->creal && !(sigma && s->sig.ready && !s->sig.n_fallback && !s->sig.ab_ready)) drop_real(s);   // part of H is outside the link tables
         if (!L.sham_ready) { invalidate_graphs(s); build_sec_ham(s, sigma ? s->ham_fb : s->ham, L.phys, L.sham); L.sham_ready = true; }
     }
 }
@@ -783,14 +800,15 @@ static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     A.pass = D.pass.p + pass; A.cls = D.cls.p; A.fac = D.fac.p; A.maps = D.maps.p; A.tiles = D.tiles.p;
     A.live_tab = D.live_tab.p; A.prog_hdr = D.prog_hdr.p; A.prog = D.prog.p; A.cs = s->cs.p;
     A.psi_in = s->cpsi[s->ccur].p; A.psi_out = s->cpsi[s->ccur ^ 1].p;
-    A.lam_in = adj ? s->clam[s->clcur].p : nullptr; A.lam_out = adj ? s->clam[s->clcur ^ 1].p : nullptr;
+    A.lam_in = adj ? (const void*)s->clam[s->clcur].p : nullptr; A.lam_out = adj ? (void*)s->clam[s->clcur ^ 1].p : nullptr;
     A.grad = adj ? s->grad_p() : nullptr;
     A.nB = PL.nB;
     int nt = s->csweep_threads;
     // small tiles do not feed many threads: most factor visits of a tile couple <= capA * capB / 4 pairs
     while (nt > 128 && P.capA * P.capB < 2 * nt) nt >>= 1;
-    const size_t smem = mqc_c_smem_bytes(P, adj, nt / 32, PL.chunk);
+    const size_t smem = mqc_c_smem_bytes(P, adj, nt / 32, PL.chunk, PL.elem);
     if (smem > 232448) throw MqcError("compact tile does not fit shared memory");
+    const bool real = s->creal;
     int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / (smem + 1024));
     per_sm = std::max(1, std::min(per_sm, std::min(32, 2048 / nt)));
     // a few thousand tiles: one CTA per tile, the hardware deals them out as SM slots free up (measured 1-3 % better
@@ -798,9 +816,10 @@ static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     unsigned grid = (unsigned)std::min<u64>(P.n_tiles, std::max<u64>((u64)s->n_sm * per_sm, 2048));
     if (s->csweep_ctas > 0) grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->csweep_ctas);
     CK(cudaSetDevice(s->device));
-#define MQC_CS_LAUNCH(NT_) do { \
-        if (PL.chunk == 256) { if (adj) k_csweep<true, NT_, 256><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_, 256><<<grid, NT_, smem, s->stream>>>(A); } \
-        else { if (adj) k_csweep<true, NT_, 1024><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_, 1024><<<grid, NT_, smem, s->stream>>>(A); } } while (0)
+#define MQC_CS_LAUNCH2(NT_, CH_) do { \
+        if (real) { if (adj) k_csweep<true, NT_, CH_, true><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_, CH_, true><<<grid, NT_, smem, s->stream>>>(A); } \
+        else { if (adj) k_csweep<true, NT_, CH_, false><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_, CH_, false><<<grid, NT_, smem, s->stream>>>(A); } } while (0)
+#define MQC_CS_LAUNCH(NT_) do { if (PL.chunk == 256) MQC_CS_LAUNCH2(NT_, 256); else MQC_CS_LAUNCH2(NT_, 1024); } while (0)
     if (nt >= 512) MQC_CS_LAUNCH(512); else if (nt >= 256) MQC_CS_LAUNCH(256); else if (nt >= 128) MQC_CS_LAUNCH(128);
     else if (nt >= 64) MQC_CS_LAUNCH(64); else MQC_CS_LAUNCH(32);
     s->counters[0]++;
@@ -819,8 +838,9 @@ static void forward_compact(mqc_solver* s, int which, const double* theta) {
     if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->theta_scale.p, s->cs.p, nfac); s->counters[0]++; }
     s->ccur = 0;
     const size_t cnt = (size_t)PL.nA * PL.nB;
-    CK(cudaMemsetAsync(s->cpsi[0].p, 0, sizeof(double2) * cnt, s->stream));
-    k_set_amplitude<<<1, 32, 0, s->stream>>>(s->cpsi[0].p, (u64)PL.ref_row * PL.nB + PL.ref_col, 1.0, 0.0);
+    CK(cudaMemsetAsync(s->cpsi[0].p, 0, (s->creal ? sizeof(double) : sizeof(double2)) * cnt, s->stream));
+    if (s->creal) k_set_real<<<1, 32, 0, s->stream>>>(reinterpret_cast<double*>(s->cpsi[0].p), (u64)PL.ref_row * PL.nB + PL.ref_col, 1.0);
+    else k_set_amplitude<<<1, 32, 0, s->stream>>>(s->cpsi[0].p, (u64)PL.ref_row * PL.nB + PL.ref_col, 1.0, 0.0);
     s->counters[0]++;
     const int np = (int)PL.pass.size();
     for (int p = 0; p < np; ++p) launch_csweep(s, which, p, false);
@@ -897,14 +917,35 @@ static void alloc_blocked(mqc_solver* s) {
 
 static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Cown, const double2* Csrc, double2* Lp,
                          unsigned nB, unsigned r0, unsigned r1, unsigned src_lo, unsigned src_hi, unsigned own_lo,
-                         unsigned l_lo, int accumulate) {
+                         unsigned l_lo, int accumulate, bool may_split = false, bool real = false) {
+    // real: the three buffers hold doubles (compact storage with real amplitudes)
     MqcSigmaDev D = SG->dev;
     D.src_lo = src_lo; D.src_hi = src_hi; D.own_lo = own_lo; D.l_lo = l_lo; D.accumulate = accumulate;
-    const bool stage = s->sigma_stage && (size_t)MQC_SG_LB * nB * sizeof(double2) <= 98304;
-    const size_t smem = mqc_sigma_smem_bytes(D, stage, MQC_SG_LB);
+    const int elem = real ? 8 : 16;
+    const bool stage = s->sigma_stage && (size_t)MQC_SG_LB * nB * elem <= 98304;
+    const size_t smem = mqc_sigma_smem_bytes(D, stage, MQC_SG_LB, elem);
     dim3 grid(r1 - r0, (nB + MQC_SG_THREADS * MQC_SG_R - 1) / (MQC_SG_THREADS * MQC_SG_R));
-    if (stage) k_sigma<true, MQC_SG_LB><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p());
-    else k_sigma<false, MQC_SG_LB><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p());
+    // Few CTAs per SM (924 rows on 444 slots at 24 qubits: the third wave is 8 % full): halve the work per CTA.
+    // sigma_split: -1 auto, 0 off, k > 0: part 0 takes the first k alpha single links.
+    D.split_l = 0;
+    if (may_split && !accumulate && s->sigma_split != 0 && D.e1a >= 2 * MQC_SG_LB) {
+        const u64 ctas = (u64)grid.x * grid.y;
+        if (s->sigma_split > 0 || ctas < (u64)24 * s->n_sm) {
+            int k = s->sigma_split > 0 ? s->sigma_split : (int)(0.6 * D.e1a);
+            k = std::max(MQC_SG_LB, std::min(k / MQC_SG_LB * MQC_SG_LB, (D.e1a - 1) / MQC_SG_LB * MQC_SG_LB));
+            D.split_l = k;
+            grid.z = 2;
+            if (Lp) CK(cudaMemsetAsync(Lp, 0, (size_t)(r1 - r0) * nB * elem, s->stream));
+        }
+    }
+    if (real) {
+        const double* co = reinterpret_cast<const double*>(Cown);
+        const double* cs = reinterpret_cast<const double*>(Csrc);
+        double* lp = reinterpret_cast<double*>(Lp);
+        if (stage) k_sigma<true, MQC_SG_LB, true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(co, cs, lp, D, s->scalars_p());
+        else k_sigma<false, MQC_SG_LB, true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(co, cs, lp, D, s->scalars_p());
+    } else if (stage) k_sigma<true, MQC_SG_LB, false><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p());
+    else k_sigma<false, MQC_SG_LB, false><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p());
     s->counters[0]++;
 }
 
@@ -919,7 +960,9 @@ static void happly_compact(mqc_solver* s, int which, const HamView& view, bool w
     double2* Lm = want_lam ? s->clam[0].p : nullptr;
     const SigmaTables* SG = view.SG;
     bool have = false;
-    if (SG && SG->ready) { launch_sigma(s, SG, C, C, Lm, nB, 0u, nA, 0u, nA, 0u, 0u, 0); have = true; }
+    if (s->creal && !(SG && SG->ready && !SG->n_fallback && !SG->ab_ready))
+        throw MqcError("internal: real amplitudes with a Hamiltonian part outside the link tables");
+    if (SG && SG->ready) { launch_sigma(s, SG, C, C, Lm, nB, 0u, nA, 0u, nA, 0u, 0u, 0, true, s->creal); have = true; }
     if (!have || SG->n_fallback) {
         unsigned bd = 256;
         while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
@@ -1283,6 +1326,8 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sparse_threads") s->sparse_threads = (int)value;
     else if (k == "sigma") s->use_sigma = (int)value;
     else if (k == "sigma_stage") s->sigma_stage = (int)value;
+    else if (k == "sigma_split") s->sigma_split = (int)value;
+    else if (k == "real_amplitudes") s->real_amplitudes = (int)value;
     else if (k == "sigma_ab") s->sigma_ab = (int)value;
     else if (k == "graph") s->use_graph = (int)value;
     else if (k == "sigma_blocked") s->sigma_blocked = (int)value;
@@ -1344,6 +1389,7 @@ int mqc_set_hamiltonian(mqc_solver_t* L, int64_t n_terms, const uint64_t* xmask,
         s->lay[0].sham_ready = s->lay[1].sham_ready = false;
         s->sig.ready = false;
         invalidate_graphs(s);
+        if (s->creal && !ham_is_real(s->ham)) drop_real(s);
     }
     MQC_CATCH
 }
@@ -1362,8 +1408,87 @@ int mqc_update_hamiltonian_coeffs(mqc_solver_t* L, int64_t n_terms, const double
         s->lay[0].sham_ready = s->lay[1].sham_ready = false;
         s->sig.ready = false;
         invalidate_graphs(s);
+        if (s->creal && !ham_is_real(s->ham)) drop_real(s);
     }
     MQC_CATCH
+}
+
+
+// ---- compact sector storage: plans for 8-byte (real) or 16-byte (complex) amplitudes -----------
+static bool ham_is_real(const HamHost& H) {
+    for (size_t t = 0; t < H.x.size(); ++t) {
+        if (H.c[t].x == 0.0 && H.c[t].y == 0.0) continue;
+        if (H.c[t].y != 0.0 || (__builtin_popcountll(H.x[t] & H.z[t]) & 1)) return false;    // odd number of Y: imaginary matrix elements
+    }
+    return true;
+}
+static bool want_real(const mqc_solver* s) {
+    return s->real_amplitudes != 0 && s->use_sigma && !s->sigma_ab && s->n / 2 <= 18 && (!s->have_ham || ham_is_real(s->ham));
+}
+static void build_compact_plans(mqc_solver* s, bool real) {
+    s->use_compact = false; s->cvalid = false; s->creal = false;
+    for (int w = 0; w < 2; ++w) s->cplan[w] = MqcCPlan();
+    if (!(s->compact && s->conserving && s->use_sector && s->mode == 1 && s->n_ranks == 1)) return;
+    for (int attempt = real ? 0 : 1; attempt < 2; ++attempt) {
+        const int elem = attempt == 0 ? 8 : 16;
+        bool ok = true;
+        for (int w = 0; w < 2 && ok; ++w) {
+            s->cplan[w] = mqc_build_cplan(s->sched[w], s->fac, s->na, s->nb, s->ref_index, elem);
+            ok = s->cplan[w].ok && s->cplan[w].max_smem[w] <= 232448 && (elem == 16 || !(s->cplan[w].nB & 1u));   // bulk copies of real rows need an even pitch
+            if (!ok && getenv("MQC_DEBUG")) fprintf(stderr, "[mqc] compact plan %d (%d-byte amplitudes) not used: %s (smem %zu)\n", w, elem, s->cplan[w].why, s->cplan[w].max_smem[w]);
+        }
+        if (ok) { s->use_compact = true; s->creal = elem == 8; return; }
+    }
+    for (int w = 0; w < 2; ++w) s->cplan[w] = MqcCPlan();
+}
+static size_t cbuf_len(const mqc_solver* s, int w) {       // double2 units of one compact buffer
+    const size_t cnt = (size_t)s->cplan[w].nA * s->cplan[w].nB;
+    return s->creal ? (cnt + 1) / 2 : cnt;
+}
+static void upload_compact(mqc_solver* s) {
+        for (int w = 0; w < 2; ++w) {
+            CPlanDev& D = s->cdev[w];
+            D.reset();
+            if (!s->use_compact) continue;
+            const MqcCPlan& PL = s->cplan[w];
+            D.pass.upload(PL.pass.empty() ? std::vector<MqcCPassDev>(1) : PL.pass, s->stream);
+            D.cls.upload(PL.cls, s->stream); D.fac.upload(PL.fac, s->stream); D.maps.upload(PL.maps, s->stream);
+            // Tiles are listed heaviest first and CTA b starts on SM b mod n_sm: deal them to the SMs in
+            // boustrophedon order (row r of n_sm tiles reversed when r is odd) so that every SM gets the same
+            // mix of heavy and light tiles (measured before: 23 % of the SM-cycles idle at the end of a pass).
+            std::vector<uint32_t> tiles = PL.tiles;
+            if (s->csweep_snake) {
+                const size_t W = (size_t)std::max(1, s->n_sm);
+                for (const MqcCPassDev& P : PL.pass) {
+                    if (!P.tiles_explicit) continue;
+                    for (size_t r0 = W; r0 < P.n_tiles; r0 += 2 * W) {
+                        const size_t r1 = std::min<size_t>(P.n_tiles, r0 + W);
+                        std::reverse(tiles.begin() + P.tile_off + r0, tiles.begin() + P.tile_off + r1);
+                    }
+                }
+            }
+            D.tiles.upload(tiles, s->stream); D.live_tab.upload(PL.live_tab, s->stream);
+            D.prog_hdr.upload(PL.prog_hdr, s->stream); D.prog.upload(PL.prog, s->stream);
+        }
+        if (s->use_compact) {
+            const size_t cnt = cbuf_len(s, 0);
+            for (int b = 0; b < 2; ++b) if (s->cpsi[b].n != cnt) s->cpsi[b].alloc(cnt);
+            s->cscratch.release();
+            for (int b = 0; b < 2; ++b) s->clam[b].release();
+            s->psi.release(); s->lam.release();          // the dense register is only allocated on demand (bridge_to_dense)
+        } else {
+            for (int b = 0; b < 2; ++b) { s->cpsi[b].release(); s->clam[b].release(); }
+            if (s->n_ranks == 1) alloc_state(s, false);
+        }
+}
+// real storage no longer applies (complex Hamiltonian or state): same schedules, complex plans and buffers
+static void drop_real(mqc_solver* s) {
+    if (!(s->use_compact && s->creal)) return;
+    invalidate_graphs(s);
+    build_compact_plans(s, false);
+    if (!s->use_compact) throw MqcError("the compact plan does not fit with complex amplitudes; set option real_amplitudes = 0 and lower tile_bits");
+    if (s->gpu_ready) { upload_compact(s); CK(cudaStreamSynchronize(s->stream)); }
+    s->state_layout = -1;
 }
 
 static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kind, const int32_t* idx4,
@@ -1432,17 +1557,7 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         else if (s->conserving && s->mode == 1) s->plan[w] = mqc_build_sparse_plan(s->sched[w], s->na, s->nb);
         else s->plan[w] = MqcSparsePlan();
     }
-    s->use_compact = false; s->cvalid = false;
-    for (int w = 0; w < 2; ++w) s->cplan[w] = MqcCPlan();
-    if (s->compact && s->conserving && s->use_sector && s->mode == 1 && s->n_ranks == 1) {
-        bool ok = true;
-        for (int w = 0; w < 2 && ok; ++w) {
-            s->cplan[w] = mqc_build_cplan(s->sched[w], s->fac, s->na, s->nb, ref_index);
-            ok = s->cplan[w].ok && s->cplan[w].max_smem[w] <= 232448;
-            if (!ok && getenv("MQC_DEBUG")) fprintf(stderr, "[mqc] compact plan %d not used: %s (smem %zu)\n", w, s->cplan[w].why, s->cplan[w].max_smem[w]);
-        }
-        s->use_compact = ok;
-    }
+    build_compact_plans(s, want_real(s));
     for (const MqcFactor& f : s->fac)
         if (f.ctrl && !s->use_compact)
             throw MqcError("number-dressed factors (kind 3) need the compact sector storage: an unsharded handle, an ansatz that "
@@ -1499,39 +1614,7 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
             std::vector<int> ph = s->lay[w].phys;
             s->lay[w].phys_dev.upload(ph, s->stream);
         }
-        for (int w = 0; w < 2; ++w) {
-            CPlanDev& D = s->cdev[w];
-            D.reset();
-            if (!s->use_compact) continue;
-            const MqcCPlan& PL = s->cplan[w];
-            D.pass.upload(PL.pass.empty() ? std::vector<MqcCPassDev>(1) : PL.pass, s->stream);
-            D.cls.upload(PL.cls, s->stream); D.fac.upload(PL.fac, s->stream); D.maps.upload(PL.maps, s->stream);
-            // Tiles are listed heaviest first and CTA b starts on SM b mod n_sm: deal them to the SMs in
-            // boustrophedon order (row r of n_sm tiles reversed when r is odd) so that every SM gets the same
-            // mix of heavy and light tiles (measured before: 23 % of the SM-cycles idle at the end of a pass).
-            std::vector<uint32_t> tiles = PL.tiles;
-            if (s->csweep_snake) {
-                const size_t W = (size_t)std::max(1, s->n_sm);
-                for (const MqcCPassDev& P : PL.pass) {
-                    if (!P.tiles_explicit) continue;
-                    for (size_t r0 = W; r0 < P.n_tiles; r0 += 2 * W) {
-                        const size_t r1 = std::min<size_t>(P.n_tiles, r0 + W);
-                        std::reverse(tiles.begin() + P.tile_off + r0, tiles.begin() + P.tile_off + r1);
-                    }
-                }
-            }
-            D.tiles.upload(tiles, s->stream); D.live_tab.upload(PL.live_tab, s->stream);
-            D.prog_hdr.upload(PL.prog_hdr, s->stream); D.prog.upload(PL.prog, s->stream);
-        }
-        if (s->use_compact) {
-            const size_t cnt = (size_t)s->cplan[0].nA * s->cplan[0].nB;
-            for (int b = 0; b < 2; ++b) if (s->cpsi[b].n != cnt) s->cpsi[b].alloc(cnt);
-            for (int b = 0; b < 2; ++b) s->clam[b].release();
-            s->psi.release(); s->lam.release();          // the dense register is only allocated on demand (bridge_to_dense)
-        } else {
-            for (int b = 0; b < 2; ++b) { s->cpsi[b].release(); s->clam[b].release(); }
-            if (s->n_ranks == 1) alloc_state(s, false);
-        }
+        upload_compact(s);
         CK(cudaStreamSynchronize(s->stream));
     } else {
         cudaGetLastError();
@@ -1744,7 +1827,7 @@ static void run_energy_grad(mqc_solver* s, const double* theta, double* energy, 
     for (mqc_solver* m : s->members) {
         ensure_layout_ready(m, 1);
         if (m->use_compact) {
-            const size_t cnt = (size_t)m->cplan[1].nA * m->cplan[1].nB;
+            const size_t cnt = cbuf_len(m, 1);
             for (int b = 0; b < 2; ++b) if (m->clam[b].n != cnt) { invalidate_graphs(m); m->clam[b].alloc(cnt); }
         } else if (!m->lam.p) {
             if (m->n_ranks > 1) throw MqcError("sharded handle was exported without lambda");
@@ -1809,6 +1892,15 @@ static void ensure_prepared(mqc_solver* s, const double* theta) {
     connect_group(s, false);
     forward(s, 0, th.data());
 }
+// the compact state as complex amplitudes (canonical order): the buffer itself, or a converted copy of the real one
+static const double2* compact_complex_view(mqc_solver* s) {
+    if (!s->creal) return s->cpsi[s->ccur].p;
+    const size_t cnt = (size_t)s->cplan[s->cwhich].nA * s->cplan[s->cwhich].nB;
+    if (s->cscratch.n != cnt) s->cscratch.alloc(cnt);
+    k_real_to_complex<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 16), 256, 0, s->stream>>>(
+        reinterpret_cast<const double*>(s->cpsi[s->ccur].p), s->cscratch.p, cnt);
+    return s->cscratch.p;
+}
 // compact storage -> dense register in the physical layout of schedule cwhich (for the consumers
 // that still address 2^N amplitudes: mqc_state and RDM sectors other than the ansatz's)
 static void bridge_to_dense(mqc_solver* s) {
@@ -1823,7 +1915,7 @@ static void bridge_to_dense(mqc_solver* s) {
     const u64 cnt = (u64)nA * nB;
     MqcPeers PR = peers_of(s);
     PR.lam[0] = s->psi.p;               // k_sector_scatter writes through the lambda table: point it at psi
-    k_sector_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(PR, s->cpsi[s->ccur].p, Lt.astr.p, Lt.bstr.p, 0u, nA, nB, 0u);
+    k_sector_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, s->stream>>>(PR, compact_complex_view(s), Lt.astr.p, Lt.bstr.p, 0u, nA, nB, 0u);
     s->state_layout = w;
 }
 static void ensure_state(mqc_solver* s, const double* theta) {
@@ -1922,7 +2014,7 @@ int mqc_rdm12(mqc_solver_t* L, int32_t n_orb, int32_t n_alpha, int32_t n_beta, d
         const int T = n2i <= 144 ? 9 : 8, BS = 16 * T;
         const int nblk = (n2i + BS - 1) / BS;
         MqcRdmC R{};
-        R.C = s->cpsi[s->ccur].p; R.aorb = Lt.aorb.p; R.borb = Lt.borb.p; R.rank_a = Lt.rank_a.p; R.rank_b = Lt.rank_b.p;
+        R.C = compact_complex_view(s); R.aorb = Lt.aorb.p; R.borb = Lt.borb.p; R.rank_a = Lt.rank_a.p; R.rank_b = Lt.rank_b.p;
         R.nA = s->cplan[s->cwhich].nA; R.nB = s->cplan[s->cwhich].nB; R.n = n_orb; R.n2 = n2i; R.nblk = nblk;
         const u64 n_blocks = (u64)R.nA * ((R.nB + MQC_RDM_KB - 1) / MQC_RDM_KB);
         const int groups = (int)std::min<u64>(n_blocks, (u64)std::max(1, s->n_sm / (nblk * nblk)));
@@ -2137,6 +2229,14 @@ int mqc_cplan_host_state(mqc_solver_t* s, int32_t which, const double* theta, do
     MQC_CATCH
 }
 
+// 8: the compact sector matrix holds real amplitudes, 16: complex, 0: no compact storage (dense register)
+int mqc_amplitude_bytes(mqc_solver_t* s, int32_t* bytes) {
+    MQC_TRY
+    if (!s || !bytes) throw MqcError("bad arguments");
+    *bytes = s->use_compact ? (s->creal ? 8 : 16) : 0;
+    MQC_CATCH
+}
+
 int mqc_cplan_info(mqc_solver_t* s, int32_t which, int32_t* n_passes, int64_t* n_rows, int64_t* n_cols, int64_t* smem_forward,
                    int64_t* smem_adjoint) {
     MQC_TRY
@@ -2180,8 +2280,20 @@ int mqc_load_state(mqc_solver_t* s, const double* re_im, int64_t n_amplitudes) {
         if (norm_in - norm_sec > 1e-12 * std::max(1.0, norm_in))
             throw MqcError("mqc_load_state: the vector has weight outside the (N_alpha, N_beta) sector of the handle's reference determinant");
         s->ccur = 0;
-        CK(cudaMemcpyAsync(s->cpsi[0].p, C.data(), sizeof(double2) * C.size(), cudaMemcpyHostToDevice, s->stream));
-        CK(cudaStreamSynchronize(s->stream));
+        if (s->creal) {
+            bool real = true;
+            for (const double2& v : C) if (v.y != 0.0) { real = false; break; }
+            if (!real) drop_real(s);
+        }
+        if (s->creal) {
+            std::vector<double> R(C.size());
+            for (size_t i = 0; i < C.size(); ++i) R[i] = C[i].x;
+            CK(cudaMemcpyAsync(s->cpsi[0].p, R.data(), sizeof(double) * R.size(), cudaMemcpyHostToDevice, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+        } else {
+            CK(cudaMemcpyAsync(s->cpsi[0].p, C.data(), sizeof(double2) * C.size(), cudaMemcpyHostToDevice, s->stream));
+            CK(cudaStreamSynchronize(s->stream));
+        }
         s->cvalid = true; s->cwhich = 0; s->state_layout = -1;
     } else {
         const std::vector<int>& ph = s->lay[0].phys;

@@ -92,6 +92,7 @@ struct MqcCPlan {
     std::vector<uint32_t> astr, bstr;        // canonical (ascending) strings, orbital space
     int chunk = 256;                         // pair words per ring slot (256 or 1024)
     uint32_t max_step_pairs = 0;
+    int elem = 16;                           // bytes per amplitude the programs were laid out for (row stride, bank order)
     size_t max_smem[2] = {0, 0};             // shared memory a CTA needs: forward, adjoint (any pass)
     const char* why = "";                    // why ok == false
 };
@@ -114,7 +115,7 @@ static inline void mqc_c_strings(int n_orb, int k, std::vector<uint32_t>& out) {
 // The pairs of a step are independent, so their order is free: arrange them so that the eight
 // threads of a quarter-warp (one 128-byte shared-memory wavefront of 16-byte amplitudes) hit eight
 // different bank groups, for the lower AND the upper partner (greedy, bounded look-ahead).
-static inline void mqc_c_bank_order(std::vector<uint32_t>& w) {
+static inline void mqc_c_bank_order(std::vector<uint32_t>& w, int elem = 16) {
     const size_t n = w.size();
     if (n < 3) return;
     std::vector<char> used(n, 0);
@@ -123,18 +124,21 @@ static inline void mqc_c_bank_order(std::vector<uint32_t>& w) {
     size_t first = 0;
     while (out.size() < n) {
         unsigned m0 = 0, m1 = 0;
-        for (int slot = 0; slot < 8 && out.size() < n; ++slot) {
+        // 8-byte (real) amplitudes: sixteen threads share a wavefront, bank pair = slot mod 16
+        const int lanes = elem == 8 ? 16 : 8;
+        const unsigned bm = (unsigned)lanes - 1u;
+        for (int slot = 0; slot < lanes && out.size() < n; ++slot) {
             while (first < n && used[first]) ++first;
             size_t pick = n, seen = 0;
             for (size_t c = first; c < n && seen < 96; ++c) {
                 if (used[c]) continue;
                 ++seen;
-                const unsigned b0 = 1u << (w[c] & 7u), b1 = 1u << ((w[c] >> 14) & 7u);
+                const unsigned b0 = 1u << (w[c] & bm), b1 = 1u << ((w[c] >> 14) & bm);
                 if (!(m0 & b0) && !(m1 & b1)) { pick = c; break; }
             }
             if (pick == n) pick = first;
             used[pick] = 1;
-            m0 |= 1u << (w[pick] & 7u); m1 |= 1u << ((w[pick] >> 14) & 7u);
+            m0 |= 1u << (w[pick] & bm); m1 |= 1u << ((w[pick] >> 14) & bm);
             out.push_back(w[pick]);
         }
     }
@@ -172,10 +176,10 @@ static inline void mqc_c_ring_flags(MqcCProgHdr* H, int n, uint32_t n_words, int
 }
 
 // shared memory of one CTA (bytes) for a pass; must match the carve-up in k_csweep
-static inline size_t mqc_c_smem_bytes(const MqcCPassDev& P, bool adj, int n_warps, int chunk) {
+static inline size_t mqc_c_smem_bytes(const MqcCPassDev& P, bool adj, int n_warps, int chunk, int elem = 16) {
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
     size_t b = 0;
-    b += (size_t)(adj ? 2 : 1) * P.capA * P.strideB * 16;
+    b += (size_t)(adj ? 2 : 1) * al((size_t)P.capA * P.strideB * elem);
     b += al((size_t)P.max_live * 8);              // class program headers
     b += (size_t)MQC_C_RING_SLOTS * chunk * 4;    // pair-word ring
     b += (size_t)P.nf * 16;                       // cos / sin
@@ -187,8 +191,13 @@ static inline size_t mqc_c_smem_bytes(const MqcCPassDev& P, bool adj, int n_warp
 }
 
 // fac: logical-coordinate factors (make_factor), sched: the pass structure built from them
-static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<MqcFactor>& fac, int na, int nb, u64 ref_index) {
+// elem: bytes per amplitude in the device buffers, 16 (complex) or 8 (real: the ansatz factors are real
+// rotations, so with a real Hamiltonian nothing ever has an imaginary part).  Real tiles take an even row
+// stride with two spare slots per row: the bulk copies move whole 16-byte units, a row that starts on an odd
+// column is loaded from the element before it (k_csweep).
+static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<MqcFactor>& fac, int na, int nb, u64 ref_index, int elem = 16) {
     MqcCPlan PL;
+    PL.elem = elem;
     const int n = S.n_bits;
     if (n & 1) return PL;
     const int n_orb = n / 2;
@@ -269,6 +278,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
         if (capA > 127 || capB > 127) { PL.why = "more than 127 patterns per class"; return PL; }   // 7-bit pattern ranks
         D.capA = capA; D.capB = capB;
         D.strideB = capB | 1;                                 // odd row stride: bank-conflict-free row pairs
+        if (elem == 8) { D.strideB = (capB + 3) & ~1; if (!(D.strideB & 2)) D.strideB += 2; }   // even, >= capB + 2, not a multiple of 4
         if (capA * D.strideB > 16383) { PL.why = "tile larger than 16383 slots"; return PL; }      // 14-bit slots in the pair words
         // maps: layout p position -> layout p + 1 position
         D.map_row_off = PL.maps.size();
@@ -362,7 +372,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
                     const uint32_t e1 = ((la >> 7) & 0x7fu) * (uint32_t)D.strideB + ((lb >> 7) & 0x7fu);
                     words.push_back(e0 | (e1 << 14) | ((((la ^ lb) >> 14) & 1u) << 28));
                 }
-                mqc_c_bank_order(words);
+                mqc_c_bank_order(words, elem);
                 PL.prog.insert(PL.prog.end(), words.begin(), words.end());
                 Lv.cnt++;
             }
@@ -376,7 +386,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
     PL.chunk = PL.max_step_pairs <= (uint32_t)MQC_C_MAX_STEP_PAIRS(256) ? 256 : 1024;
     for (const MqcCLive& Lv : PL.live_tab) if (Lv.cnt) mqc_c_ring_flags(&PL.prog_hdr[Lv.off], (int)Lv.cnt, Lv.n_words, PL.chunk);
     for (const MqcCPassDev& D : PL.pass)
-        for (int adj = 0; adj < 2; ++adj) PL.max_smem[adj] = std::max(PL.max_smem[adj], mqc_c_smem_bytes(D, adj != 0, 4, PL.chunk));
+        for (int adj = 0; adj < 2; ++adj) PL.max_smem[adj] = std::max(PL.max_smem[adj], mqc_c_smem_bytes(D, adj != 0, 4, PL.chunk, elem));
     if (PL.cls.empty()) PL.cls.push_back(MqcCClass{});
     if (PL.fac.empty()) PL.fac.push_back(MqcCFactor{});
     if (PL.maps.empty()) PL.maps.push_back(0);

@@ -29,10 +29,10 @@ struct MqcCArgs {
     const MqcCProgHdr* prog_hdr;
     const uint32_t* prog;
     const double2* cs;
-    const double2* psi_in;
-    double2* psi_out;
-    const double2* lam_in;
-    double2* lam_out;
+    const void* psi_in;              // double2 (complex) or double (REAL) amplitudes
+    void* psi_out;
+    const void* lam_in;
+    void* lam_out;
     double* grad;
     uint32_t nB;
 };
@@ -66,6 +66,11 @@ __device__ __forceinline__ void mqc_fence_async() { asm volatile("fence.proxy.as
 __device__ __forceinline__ void mqc_cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(mqc_smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void mqc_cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(mqc_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void mqc_cp_async_amp(double2* d, const double2* g) { mqc_cp_async16(d, g); }
+__device__ __forceinline__ void mqc_cp_async_amp(double* d, const double* g) { mqc_cp_async8(d, g); }
 __device__ __forceinline__ void mqc_cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 // one pair rotation on psi (and lambda, with the gradient partial): w = slot0 | slot1 << 14 | parity << 28
@@ -89,9 +94,39 @@ __device__ __forceinline__ double mqc_rotate_pair(double2* __restrict__ sp, doub
     return g;
 }
 
-template <bool ADJ, int NT, int CH>
+// real amplitudes: the same rotation on 8-byte slots (half the shared-memory traffic and arithmetic)
+template <bool ADJ>
+__device__ __forceinline__ double mqc_rotate_pair(double* __restrict__ sp, double* __restrict__ sl, const uint32_t w,
+                                                  const double c, const double s) {
+    const int e0 = (int)(w & 0x3fffu), e1 = (int)((w >> 14) & 0x3fffu);
+    const int sgn = (int)((w << 3) & 0x80000000u);
+    const double ssn = __hiloint2double(__double2hiint(s) ^ sgn, __double2loint(s));
+    const double a = sp[e0], b = sp[e1];
+    double g = 0.0;
+    if (ADJ) {
+        const double xa = sl[e0], xb = sl[e1];
+        const double gv = xb * a - xa * b;
+        g = __hiloint2double(__double2hiint(gv) ^ sgn, __double2loint(gv));
+        sl[e0] = c * xa - ssn * xb;
+        sl[e1] = c * xb + ssn * xa;
+    }
+    sp[e0] = c * a - ssn * b;
+    sp[e1] = c * b + ssn * a;
+    return g;
+}
+
+template <bool REAL> struct MqcAmp { typedef double2 T; };
+template <> struct MqcAmp<true> { typedef double T; };
+
+// REAL: 8-byte amplitudes.  Needs an even row pitch nB (host-checked): a tile row then starts on a 16-byte
+// boundary or one element after it (`shift`), the same for all rows of the tile; bulk copies move the
+// 16-byte units that cover the row (forward: the neighbours' elements that come along are never addressed;
+// adjoint stores: the aligned interior goes by bulk copy, up to two edge elements by plain stores).
+template <bool ADJ, int NT, int CH, bool REAL = false>
 __global__ void __launch_bounds__(NT, (1024 / NT) > 16 ? 16 : (1024 / NT))
 k_csweep(const __grid_constant__ MqcCArgs A) {
+    typedef typename MqcAmp<REAL>::T AT;
+    constexpr int ES = (int)sizeof(AT);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -100,8 +135,9 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
     const uint32_t nB = A.nB;
     // ---- shared memory carve-up (mqc_c_smem_bytes) -------------------------------------------
     unsigned char* q = smem_raw;
-    double2* sp = reinterpret_cast<double2*>(q);              q += (size_t)capA * strideB * 16;
-    double2* sl = reinterpret_cast<double2*>(q);              if (ADJ) q += (size_t)capA * strideB * 16;
+    const size_t tile_bytes = ((size_t)capA * strideB * ES + 15) & ~(size_t)15;
+    AT* sp0 = reinterpret_cast<AT*>(q);                       q += tile_bytes;
+    AT* sl0 = reinterpret_cast<AT*>(q);                       if (ADJ) q += tile_bytes;
     uint2* shdr = reinterpret_cast<uint2*>(q);                q += ((size_t)P->max_live * 8 + 15) & ~(size_t)15;
     uint32_t* ring = reinterpret_cast<uint32_t*>(q);          q += (size_t)MQC_C_RING_SLOTS * CH * 4;
     double2* hcs = reinterpret_cast<double2*>(q);             q += (size_t)nf * 16;
@@ -154,20 +190,25 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
         };
         const uint32_t magicB = mqc_c_magic((uint32_t)nBl);
         const int cnt = nAl * nBl;
+        const uint32_t shift = REAL ? (col0 & 1u) : 0u;               // slot 0 of a row sits `shift` elements into the buffer row
+        AT* const sp = sp0 + shift;
+        AT* const sl = sl0 + shift;
+        const uint32_t row_units = REAL ? ((shift + (uint32_t)nBl + 1u) & ~1u) : (uint32_t)nBl;   // elements a row load moves
 
         // ---- asynchronous fetch: program headers (and the rows, forward) -> one mbarrier phase ------
         if (warp == 0) {
             const uint32_t bH = ((uint32_t)n_live * 8u + 15u) & ~15u;
             if (lane == 0) {
                 mqc_fence_async();              // generic-proxy accesses of the previous tile before async-proxy writes
-                mqc_mbar_expect_tx(bar, bH + (ADJ ? 0u : (uint32_t)cnt * 16u));
+                mqc_mbar_expect_tx(bar, bH + (ADJ ? 0u : (uint32_t)nAl * row_units * (uint32_t)ES));
             }
             __syncwarp();
             if (lane == 31 && bH) mqc_bulk_g2s(shdr, A.prog_hdr + lt4.x, bH, bar);
             if (lane == 0) { for (; issued < NC && issued < MQC_C_RING_SLOTS; ++issued) issue_chunk(issued); }
             if (!ADJ)
                 for (int ja = lane; ja < nAl; ja += 32)
-                    mqc_bulk_g2s(sp + (size_t)ja * strideB, A.psi_in + (size_t)(row0 + ja) * nB + col0, (uint32_t)nBl * 16u, bar);
+                    mqc_bulk_g2s(sp0 + (size_t)ja * strideB, static_cast<const AT*>(A.psi_in) + (size_t)(row0 + ja) * nB + col0 - shift,
+                                 row_units * (uint32_t)ES, bar);
         }
         // ---- per-tile factor constants and the tile's row / column map ------------------------------
         for (int f = tid; f < nf; f += NT) {
@@ -186,8 +227,8 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
             for (int e = tid; e < cnt; e += NT) {
                 const int ja = (nBl == 1) ? e : (int)__umulhi((uint32_t)e, magicB), jb = e - ja * nBl;
                 const size_t g = (size_t)smap[ja] * nB + smap[nAl + jb];
-                mqc_cp_async16(sp + ja * strideB + jb, A.psi_in + g);
-                mqc_cp_async16(sl + ja * strideB + jb, A.lam_in + g);
+                mqc_cp_async_amp(sp + ja * strideB + jb, static_cast<const AT*>(A.psi_in) + g);
+                mqc_cp_async_amp(sl + ja * strideB + jb, static_cast<const AT*>(A.lam_in) + g);
             }
             mqc_cp_async_wait_all();
         }
@@ -279,16 +320,28 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
         if (!ADJ) {
             for (int e = tid; e < cnt; e += NT) {
                 const int ja = (nBl == 1) ? e : (int)__umulhi((uint32_t)e, magicB), jb = e - ja * nBl;
-                A.psi_out[(size_t)smap[ja] * nB + smap[nAl + jb]] = sp[ja * strideB + jb];
+                static_cast<AT*>(A.psi_out)[(size_t)smap[ja] * nB + smap[nAl + jb]] = sp[ja * strideB + jb];
             }
         } else {
             // rows leave by bulk copies (generic-proxy writes made visible to the async proxy first)
             mqc_fence_async();
             __syncthreads();
             if (warp == 0) {
+                const uint32_t first = shift;                                   // REAL: leading element off the 16-byte grid
+                const uint32_t ni = REAL ? (((uint32_t)nBl - first) & ~1u) : (uint32_t)nBl;
                 for (int ja = lane; ja < nAl; ja += 32) {
-                    mqc_bulk_s2g(A.psi_out + (size_t)(row0 + ja) * nB + col0, sp + (size_t)ja * strideB, (uint32_t)nBl * 16u);
-                    mqc_bulk_s2g(A.lam_out + (size_t)(row0 + ja) * nB + col0, sl + (size_t)ja * strideB, (uint32_t)nBl * 16u);
+                    AT* po = static_cast<AT*>(A.psi_out) + (size_t)(row0 + ja) * nB + col0;
+                    AT* lo = static_cast<AT*>(A.lam_out) + (size_t)(row0 + ja) * nB + col0;
+                    const AT* ps = sp + (size_t)ja * strideB;
+                    const AT* ls = sl + (size_t)ja * strideB;
+                    if (ni) {
+                        mqc_bulk_s2g(po + first, ps + first, ni * (uint32_t)ES);
+                        mqc_bulk_s2g(lo + first, ls + first, ni * (uint32_t)ES);
+                    }
+                    if (REAL) {
+                        if (first) { po[0] = ps[0]; lo[0] = ls[0]; }
+                        if (first + ni < (uint32_t)nBl) { po[nBl - 1] = ps[nBl - 1]; lo[nBl - 1] = ls[nBl - 1]; }
+                    }
                 }
                 mqc_bulk_commit();
                 mqc_bulk_wait_read();

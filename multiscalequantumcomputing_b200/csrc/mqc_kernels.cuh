@@ -95,6 +95,14 @@ __global__ void k_set_amplitude(double2* psi, u64 index, double re, double im) {
     if (blockIdx.x == 0 && threadIdx.x == 0) psi[index] = make_double2(re, im);
 }
 
+__global__ void k_set_real(double* psi, u64 index, double v) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) psi[index] = v;
+}
+// real compact state -> complex copy
+__global__ void k_real_to_complex(const double* __restrict__ in, double2* __restrict__ out, const u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = make_double2(in[i], 0.0);
+}
+
 // out[logical index] = psi[physical index]; phys_pos[l] = physical position of logical bit l
 __global__ void k_gather_logical(const double2* __restrict__ psi, double2* __restrict__ out,
                                  const int* __restrict__ phys_pos, int n_bits, u64 dim) {

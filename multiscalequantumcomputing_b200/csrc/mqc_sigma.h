@@ -77,6 +77,10 @@ struct MqcSigmaDev {
     // (first row own_lo).  Replicated matrix: one block [0, n_a), all three offsets 0.
     unsigned src_lo, src_hi, own_lo, l_lo;
     int accumulate;                // L += instead of L =  (rounds after the first)
+    // Row split (replicated matrix only): gridDim.z == 2, part z = 0 does phase 0 and the alpha single
+    // links [0, split_l), part 1 the remaining links and phase 2; both ADD into a zeroed L with
+    // atomics (two addends per element: the sum does not depend on their order).  0: one CTA per row.
+    int split_l;
 };
 
 // ---- host side -----------------------------------------------------------------------------
@@ -488,6 +492,7 @@ static inline void mqc_sigma_apply_host(const MqcSigmaHost& S, const double2* C,
 // ---- device side ---------------------------------------------------------------------------
 #if defined(__CUDACC__)
 #define MQC_SG_R 4           // output beta strings per thread
+struct __align__(16) MqcSgA2 { unsigned src, zb; double w; };   // one resolved alpha-alpha double link
 
 // hdiag[row - row0][jb] = sum over diagonal Pauli terms c_t (-1)^popc(x & z_t)
 __global__ void k_sigma_hdiag(const u64* __restrict__ aq, const u64* __restrict__ bq, const u64* __restrict__ dz,
@@ -512,17 +517,35 @@ __device__ __forceinline__ double mqc_sg_flip(double w, unsigned s) {      // s 
 // One CTA per (output alpha string, block of MQC_SG_THREADS * MQC_SG_R output beta strings).
 // STAGE: the source row of C is copied to shared memory per link (rows up to 64 KB); otherwise
 // the gathers go to L1/L2 directly.
-template <bool STAGE, int LB>
+template <bool REAL> struct MqcSgAmp { typedef double2 T; };
+template <> struct MqcSgAmp<true> { typedef double T; };
+__device__ __forceinline__ void mqc_sg_acc(const double w, const double2 v, double& ar, double& ai) { ar = fma(w, v.x, ar); ai = fma(w, v.y, ai); }
+__device__ __forceinline__ void mqc_sg_acc(const double w, const double v, double& ar, double&) { ar = fma(w, v, ar); }
+__device__ __forceinline__ double2 mqc_sg_flipv(const double2 v, const unsigned s) { return make_double2(mqc_sg_flip(v.x, s), mqc_sg_flip(v.y, s)); }
+__device__ __forceinline__ double mqc_sg_flipv(const double v, const unsigned s) { return mqc_sg_flip(v, s); }
+__device__ __forceinline__ void mqc_sg_store(double2* p, double ar, double ai) { *p = make_double2(ar, ai); }
+__device__ __forceinline__ void mqc_sg_store(double* p, double ar, double) { *p = ar; }
+__device__ __forceinline__ void mqc_sg_add(double2* p, double ar, double ai) { const double2 o = *p; *p = make_double2(o.x + ar, o.y + ai); }
+__device__ __forceinline__ void mqc_sg_add(double* p, double ar, double) { *p += ar; }
+__device__ __forceinline__ void mqc_sg_atomic(double2* p, double ar, double ai) { atomicAdd(&p->x, ar); atomicAdd(&p->y, ai); }
+__device__ __forceinline__ void mqc_sg_atomic(double* p, double ar, double) { atomicAdd(p, ar); }
+__device__ __forceinline__ void mqc_sg_dot(const double2 py, double ar, double ai, double& er, double& ei) {
+    er += py.x * ar + py.y * ai; ei += py.x * ai - py.y * ar;
+}
+__device__ __forceinline__ void mqc_sg_dot(const double py, double ar, double, double& er, double&) { er += py * ar; }
+
+template <bool STAGE, int LB, bool REAL>
 __global__ void __launch_bounds__(MQC_SG_THREADS, 3)
-k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, double2* __restrict__ L,
-        const __grid_constant__ MqcSigmaDev S, double* __restrict__ e_out) {
+k_sigma(const typename MqcSgAmp<REAL>::T* __restrict__ Cown, const typename MqcSgAmp<REAL>::T* __restrict__ Csrc,
+        typename MqcSgAmp<REAL>::T* __restrict__ L, const __grid_constant__ MqcSigmaDev S, double* __restrict__ e_out) {
+    typedef typename MqcSgAmp<REAL>::T AT;
     extern __shared__ __align__(16) unsigned char sg_smem[];
-    const double2* __restrict__ C = Csrc - (size_t)S.src_lo * S.n_b;      // C[src * nB + j] for src in the block
+    const AT* __restrict__ C = Csrc - (size_t)S.src_lo * S.n_b;           // C[src * nB + j] for src in the block
     const unsigned nA = S.n_a, nB = S.n_b;
     const int M2 = S.n_m2 > 0 ? S.n_m2 : 1;
     const int WS = 2 * (S.n_m2 + 1);                               // weight-table stride; last pair = 0 (padding)
-    double2* srow = reinterpret_cast<double2*>(sg_smem);
-    double* wl = reinterpret_cast<double*>(sg_smem + (STAGE ? (size_t)LB * nB * sizeof(double2) : 0));
+    AT* srow = reinterpret_cast<AT*>(sg_smem);
+    double* wl = reinterpret_cast<double*>(sg_smem + (STAGE ? (((size_t)LB * nB * sizeof(AT) + 15) & ~(size_t)15) : 0));
     double* sxd = wl + (size_t)LB * WS;
     unsigned char* sg4 = reinterpret_cast<unsigned char*>(sxd + (S.n_m2 + 1));
     __shared__ double red[2][MQC_SG_THREADS / 32];
@@ -541,7 +564,9 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
     }
 
     // ---- phase 0: beta-only part on the own row ---------------------------------------------
-    if (i >= S.src_lo && i < S.src_hi) {                          // uniform over the CTA
+    const bool part0 = blockIdx.z == 0, part1 = blockIdx.z + 1 == gridDim.z;
+    const int l_begin = part0 ? 0 : S.split_l, l_end = (part0 && !part1) ? S.split_l : S.e1a;
+    if (part0 && i >= S.src_lo && i < S.src_hi) {               // uniform over the CTA
         const int c0 = __ldg(S.cls_of_m2 + S.n_m2);
         for (int k = tid; k < WS; k += MQC_SG_THREADS) {
             const int ib = k >> 1, pbv = k & 1;
@@ -555,10 +580,10 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
             if (pbv == 0) sxd[ib] = sd;
         }
         for (int k = tid; k <= S.n_m4; k += MQC_SG_THREADS) sg4[k] = (unsigned char)(__popc(ap & __ldg(S.sa_b4 + k)) & 1u);
-        const double2* __restrict__ Crow = C + (size_t)i * nB;
+        const AT* __restrict__ Crow = C + (size_t)i * nB;
         if (STAGE) for (unsigned j = tid; j < nB; j += MQC_SG_THREADS) srow[j] = Crow[j];
         __syncthreads();
-        const double2* __restrict__ row = STAGE ? srow : Crow;
+        const AT* __restrict__ row = STAGE ? srow : Crow;
         if (c0 >= 0) {
             const int e0 = __ldg(S.cls_off + c0), e1 = __ldg(S.cls_off + c0 + 1);
             unsigned nx[MQC_SG_R];
@@ -574,33 +599,44 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
                     const unsigned widx = (ib << 1) | ((en[r] >> 24) & 1u);
                     double w = fma(sxd[ib], __ldg(S.tbb + (size_t)ib * nB + col), wl[widx]);
                     w = mqc_sg_flip(w, (en[r] >> 25) & 1u);
-                    const double2 v = row[col];
-                    ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
+                    const AT v = row[col];
+                    mqc_sg_acc(w, v, ar[r], ai[r]);
                 }
             }
         }
         {
-            unsigned nx[MQC_SG_R];
+            // entry e + 2 and the weight of entry e + 1 are in flight while entry e is applied
+            unsigned nx[MQC_SG_R], en[MQC_SG_R];
+            double wn[MQC_SG_R];
 #pragma unroll
-            for (int r = 0; r < MQC_SG_R; ++r) nx[r] = S.e2b > 0 ? __ldg(S.ell_b2 + jc[r]) : 0u;
+            for (int r = 0; r < MQC_SG_R; ++r) {
+                en[r] = S.e2b > 0 ? __ldg(S.ell_b2 + jc[r]) : 0u;
+                nx[r] = S.e2b > 1 ? __ldg(S.ell_b2 + (size_t)nB + jc[r]) : 0u;
+                wn[r] = S.e2b > 0 ? __ldg(S.w4b + (size_t)((en[r] >> 16) & 0xfffu) * 6 + ((en[r] >> 28) & 7u)) : 0.0;
+            }
             for (int e = 0; e < S.e2b; ++e) {
-                unsigned en[MQC_SG_R];
-#pragma unroll
-                for (int r = 0; r < MQC_SG_R; ++r) { en[r] = nx[r]; if (e + 1 < S.e2b) nx[r] = __ldg(S.ell_b2 + (size_t)(e + 1) * nB + jc[r]); }
+                unsigned cur[MQC_SG_R];
+                double wc[MQC_SG_R];
 #pragma unroll
                 for (int r = 0; r < MQC_SG_R; ++r) {
-                    const unsigned col = en[r] & 0xffffu, i4 = (en[r] >> 16) & 0xfffu, p6 = (en[r] >> 28) & 7u;
-                    const double w = mqc_sg_flip(__ldg(S.w4b + (size_t)i4 * 6 + p6), (unsigned)sg4[i4] ^ (en[r] >> 31));
-                    const double2 v = row[col];
-                    ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
+                    cur[r] = en[r]; wc[r] = wn[r]; en[r] = nx[r];
+                    if (e + 2 < S.e2b) nx[r] = __ldg(S.ell_b2 + (size_t)(e + 2) * nB + jc[r]);
+                    if (e + 1 < S.e2b) wn[r] = __ldg(S.w4b + (size_t)((en[r] >> 16) & 0xfffu) * 6 + ((en[r] >> 28) & 7u));
+                }
+#pragma unroll
+                for (int r = 0; r < MQC_SG_R; ++r) {
+                    const unsigned col = cur[r] & 0xffffu, i4 = (cur[r] >> 16) & 0xfffu;
+                    const double w = mqc_sg_flip(wc[r], (unsigned)sg4[i4] ^ (cur[r] >> 31));
+                    const AT v = row[col];
+                    mqc_sg_acc(w, v, ar[r], ai[r]);
                 }
             }
         }
 #pragma unroll
         for (int r = 0; r < MQC_SG_R; ++r) {
             const double d = __ldg(S.hdiag + (size_t)(i - S.row0) * nB + jc[r]);
-            const double2 v = row[jc[r]];
-            ar[r] = fma(d, v.x, ar[r]); ai[r] = fma(d, v.y, ai[r]);
+            const AT v = row[jc[r]];
+            mqc_sg_acc(d, v, ar[r], ai[r]);
         }
     }
 
@@ -608,14 +644,14 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
     // LB links per batch: their source rows are staged together and every ELL entry (column,
     // weight index, sign) is loaded and decoded once for all of them; the next entry is in
     // flight while the current one is applied.
-    for (int l0 = 0; l0 < S.e1a; l0 += LB) {
+    for (int l0 = l_begin; l0 < l_end; l0 += LB) {
         unsigned src[LB], ia[LB], pav[LB], sga[LB], zb[LB];
         bool ok[LB];
         bool any = false;
         int c = -1;
 #pragma unroll
         for (int l = 0; l < LB; ++l) {
-            const unsigned ln = __ldg(S.lnk_a1 + (size_t)(l0 + l) * nA + i);
+            const unsigned ln = l0 + l < l_end ? __ldg(S.lnk_a1 + (size_t)(l0 + l) * nA + i) : MQC_SG_INVALID;
             ok[l] = ln != MQC_SG_INVALID && (ln & 0xffffu) >= S.src_lo && (ln & 0xffffu) < S.src_hi;
             src[l] = ok[l] ? (ln & 0xffffu) : S.src_lo;
             ia[l] = ok[l] ? ((ln >> 16) & 0xffu) : 0u;
@@ -634,18 +670,27 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
                 if (ok[l] && ib < S.n_m2) {
                     const unsigned mb = __ldg(S.m2_mask + ib);
                     const unsigned dest = pbv ? (mb & (0u - mb)) : (mb & (mb - 1u));   // output string's bit on mb
-                    const unsigned sx = (__popc(a & __ldg(S.sa_b2 + ib) & ~ma) + __popc(dest & zb[l])) & 1u;
+                    // STAGE: the staged row carries (-1)^popc(source beta string & zb), the output string differs
+                    // from it by mb, and the link's own sign goes here too: no per-(output, link) sign is left
+                    const unsigned sx = (__popc(a & __ldg(S.sa_b2 + ib) & ~ma) + __popc(dest & zb[l]) +
+                                         (STAGE ? __popc(mb & zb[l]) + sga[l] : 0u)) & 1u;
                     w = mqc_sg_flip(__ldg(S.w22 + ((size_t)ia[l] * M2 + ib) * 4 + pav[l] * 2 + pbv), sx);
                 }
                 wl[l * WS + k] = w;
             }
             if (STAGE) {
-                const double2* __restrict__ Crow = C + (size_t)src[l] * nB;
-                for (unsigned j = tid; j < nB; j += MQC_SG_THREADS) srow[(size_t)l * nB + j] = Crow[j];
+                const AT* __restrict__ Crow = C + (size_t)src[l] * nB;
+                const unsigned z = zb[l];
+#pragma unroll 4
+                for (unsigned j = tid; j < nB; j += MQC_SG_THREADS) {
+                    const AT v = Crow[j];
+                    const unsigned sg = __popc(__ldg(S.borb + j) & z) & 1u;
+                    srow[(size_t)l * nB + j] = mqc_sg_flipv(v, sg);
+                }
             }
         }
         __syncthreads();
-        const double2* row[LB];
+        const AT* row[LB];
         unsigned sl[MQC_SG_R];                                    // bit l: sign of link l for output r
 #pragma unroll
         for (int r = 0; r < MQC_SG_R; ++r) sl[r] = 0u;
@@ -655,12 +700,12 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
             const double al = ok[l] ? __ldg(S.ta1 + (size_t)ia[l] * nA + src[l]) : 0.0;
 #pragma unroll
             for (int r = 0; r < MQC_SG_R; ++r) {
-                const unsigned sg = (__popc(bp[r] & zb[l]) + sga[l]) & 1u;
-                sl[r] |= sg << l;
+                const unsigned sg = STAGE ? sga[l] : ((__popc(bp[r] & zb[l]) + sga[l]) & 1u);
+                if (!STAGE) sl[r] |= sg << l;
                 if (ok[l]) {
                     const double w = mqc_sg_flip(al + __ldg(S.tb1 + ((size_t)ia[l] * 2 + pav[l]) * nB + jc[r]), sg);
-                    const double2 v = row[l][jc[r]];
-                    ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
+                    const AT v = row[l][jc[r]];
+                    mqc_sg_acc(w, v, ar[r], ai[r]);
                 }
             }
         }
@@ -680,31 +725,53 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
                 const unsigned sg = (en[r] >> 25) & 1u;
 #pragma unroll
                 for (int l = 0; l < LB; ++l) {
-                    const double w = mqc_sg_flip(wl[l * WS + widx], sg ^ (sl[r] >> l));
-                    const double2 v = row[l][col];
-                    ar[r] = fma(w, v.x, ar[r]); ai[r] = fma(w, v.y, ai[r]);
+                    const double w = mqc_sg_flip(wl[l * WS + widx], STAGE ? sg : (sg ^ (sl[r] >> l)));
+                    const AT v = row[l][col];
+                    mqc_sg_acc(w, v, ar[r], ai[r]);
                 }
             }
         }
     }
 
     // ---- phase 2: alpha-alpha double links (diagonal in beta, coalesced row reads) -----------
-    {
-        unsigned lnx = S.e2a > 0 ? __ldg(S.lnk_a2 + i) : MQC_SG_INVALID;
-        for (int l = 0; l < S.e2a; ++l) {
-            const unsigned ln = lnx;
-            if (l + 1 < S.e2a) lnx = __ldg(S.lnk_a2 + (size_t)(l + 1) * nA + i);
-            if (ln == MQC_SG_INVALID) continue;
-            const unsigned src = ln & 0xffffu, i4 = (ln >> 16) & 0xfffu, p6 = (ln >> 28) & 7u, sga = ln >> 31;
-            if (src < S.src_lo || src >= S.src_hi) continue;
-            const double w = __ldg(S.w4a + (size_t)i4 * 6 + p6);
-            const unsigned zb = __ldg(S.sb_a4 + i4);
-            const double2* __restrict__ Crow = C + (size_t)src * nB;
+    // The row's links are resolved once into shared memory (source row, signed weight, JW beta mask; links
+    // that are absent or whose source row another rank holds are squeezed out, in order), so the row
+    // reads of consecutive links are independent loads.
+    if (part1) {
+        MqcSgA2* a2 = reinterpret_cast<MqcSgA2*>((reinterpret_cast<uintptr_t>(sg4) + (size_t)S.n_m4 + 1 + 15) & ~(uintptr_t)15);
+        __shared__ int wcnt[MQC_SG_THREADS / 32];
+        const int warp = tid >> 5, lane = tid & 31;
+        int n2 = 0;
+        __syncthreads();                                          // phase 1 is done with the shared tables
+        for (int l0 = 0; l0 < S.e2a; l0 += MQC_SG_THREADS) {
+            const int l = l0 + tid;
+            MqcSgA2 ent;
+            bool ok = false;
+            if (l < S.e2a) {
+                const unsigned ln = __ldg(S.lnk_a2 + (size_t)l * nA + i);
+                const unsigned src = ln & 0xffffu, i4 = (ln >> 16) & 0xfffu, p6 = (ln >> 28) & 7u;
+                ok = ln != MQC_SG_INVALID && src >= S.src_lo && src < S.src_hi;
+                if (ok) { ent.src = src; ent.zb = __ldg(S.sb_a4 + i4); ent.w = mqc_sg_flip(__ldg(S.w4a + (size_t)i4 * 6 + p6), ln >> 31); }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0) wcnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = n2 + __popc(bal & ((1u << lane) - 1u)), tot = 0;
+#pragma unroll
+            for (int w = 0; w < MQC_SG_THREADS / 32; ++w) { const int c = wcnt[w]; if (w < warp) off += c; tot += c; }
+            if (ok) a2[off] = ent;
+            n2 += tot;
+            __syncthreads();
+        }
+#pragma unroll 2
+        for (int l = 0; l < n2; ++l) {
+            const MqcSgA2 ent = a2[l];
+            const AT* __restrict__ Crow = C + (size_t)ent.src * nB;
 #pragma unroll
             for (int r = 0; r < MQC_SG_R; ++r) {
-                const double2 v = Crow[jc[r]];
-                const double ws = mqc_sg_flip(w, (__popc(bp[r] & zb) + sga) & 1u);
-                ar[r] = fma(ws, v.x, ar[r]); ai[r] = fma(ws, v.y, ai[r]);
+                const AT v = Crow[jc[r]];
+                const double ws = mqc_sg_flip(ent.w, __popc(bp[r] & ent.zb) & 1u);
+                mqc_sg_acc(ws, v, ar[r], ai[r]);
             }
         }
     }
@@ -716,12 +783,11 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
         if (jb[r] < nB) {
             if (L) {
                 const size_t o = (size_t)(i - S.l_lo) * nB + jb[r];
-                if (S.accumulate) { const double2 o0 = L[o]; L[o] = make_double2(o0.x + ar[r], o0.y + ai[r]); }
-                else L[o] = make_double2(ar[r], ai[r]);
+                if (gridDim.z > 1) mqc_sg_atomic(L + o, ar[r], ai[r]);
+                else if (S.accumulate) mqc_sg_add(L + o, ar[r], ai[r]);
+                else mqc_sg_store(L + o, ar[r], ai[r]);
             }
-            const double2 py = Cown[(size_t)(i - S.own_lo) * nB + jb[r]];
-            er += py.x * ar[r] + py.y * ai[r];
-            ei += py.x * ai[r] - py.y * ar[r];
+            mqc_sg_dot(Cown[(size_t)(i - S.own_lo) * nB + jb[r]], ar[r], ai[r], er, ei);
         }
     }
 #pragma unroll
@@ -741,12 +807,13 @@ k_sigma(const double2* __restrict__ Cown, const double2* __restrict__ Csrc, doub
     }
 }
 
-static inline size_t mqc_sigma_smem_bytes(const MqcSigmaDev& S, bool stage, int lb) {
+static inline size_t mqc_sigma_smem_bytes(const MqcSigmaDev& S, bool stage, int lb, int elem = 16) {
     const int M2 = S.n_m2 > 0 ? S.n_m2 : 1;
-    size_t b = stage ? (size_t)lb * S.n_b * sizeof(double2) : 0;
+    size_t b = stage ? (((size_t)lb * S.n_b * elem + 15) & ~(size_t)15) : 0;
     (void)M2;
     b += ((size_t)lb * 2 * (S.n_m2 + 1) + (size_t)(S.n_m2 + 1)) * sizeof(double);
-    b += (size_t)S.n_m4 + 1;
+    b += (((size_t)S.n_m4 + 1 + 15) & ~(size_t)15) + 16;
+    b += (size_t)(S.e2a > 0 ? S.e2a : 1) * 16;                  // resolved alpha-alpha links (MqcSgA2)
     return (b + 15) & ~(size_t)15;
 }
 #endif
