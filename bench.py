@@ -55,7 +55,7 @@ CONFIG = {"workload": "uccsd_statevector_24q_H12chain_sto3g_energy+adjoint_gradi
           "ansatz": "JW-UCCSD, blocked order", "fragments_per_gpu": 1,
           "l2_policy": "explicit flush: a 256 MB device buffer (2x the 126 MB L2) is overwritten between timed steps, outside "
                        "the timed region (per-step CUDA events / per-call clocks are summed); within a step the compact "
-                       "sector working set (psi + lambda ping-pong, 55 MB) is L2 resident by design"}
+                       "sector working set (psi + lambda ping-pong, 27 MB of real amplitudes) is L2 resident by design"}
 
 
 class ClockSampler:
@@ -181,7 +181,7 @@ def run_reference(args):
     ph = np.mean(phases, axis=0)
     out = {"impl": "reference", "metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)",
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": dict(CONFIG),
            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE,
                             "phase_s": {"forward": ph[0], "hamiltonian": ph[1], "reverse": ph[2]}},
@@ -421,7 +421,8 @@ def run_ours(args):
         S = 16.0 * (1 << factors.n_qubits)
         from math import comb
         n_det = comb(N_ORB, N_ELEC // 2) ** 2
-        sector_bytes = 16.0 * n_det
+        amp_bytes = h.amplitude_bytes() or 16          # 8: real compact storage (real Hamiltonian), 16: complex
+        sector_bytes = float(amp_bytes) * n_det
         phase /= args.steps
         names = ("k_tile_sp2<false> (forward sweep)", "k_sigma (H|psi>)", "k_tile_sp2<true> (adjoint reverse sweep)")
         sparse = tim["forward_passes"] > 0 and "sparse_tiles=0" not in args.opt and "sector=0" not in args.opt
@@ -441,7 +442,7 @@ def run_ours(args):
         achieved = per_launch[dom] / (avg_ms * 1e-3) / 1e9
         roof = {"kernel": names[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": per_launch[dom], "avg_launch_ms": avg_ms,
+                "algorithmic_bytes_per_launch": per_launch[dom], "amplitude_bytes": amp_bytes, "avg_launch_ms": avg_ms,
                 "launches_per_step": n_launch[dom], "share_of_step": float(phase[dom] / phase.sum()),
                 "phase_ms": {"forward": phase[0], "hamiltonian": phase[1], "reverse": phase[2]},
                 "unfused_equivalent": {
@@ -522,7 +523,7 @@ def run_ours(args):
                 variants = {"unavailable": str(exc)}
         out = {"metric": "uccsd_energy_grad_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128 state)", "data": "synthetic",
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": dict(CONFIG, n_theta=factors.n_theta, n_factors=len(factors), n_pauli_terms=len(table[0]),
                               n_x_groups=n_groups, passes_per_sweep=tim["forward_passes"],
                               parallelism="fragment-parallel x%d" % world, options=args.opt),

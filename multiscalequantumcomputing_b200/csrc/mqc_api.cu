@@ -185,6 +185,7 @@ struct mqc_solver {
     // compact sector storage (mqc_cplan.h): the state is the matrix C[alpha string][beta string];
     // cpsi / clam ping-pong between the layouts of consecutive passes
     int compact = 1, csweep_threads = 128, csweep_ctas = 0, csweep_snake = 1;
+    int csweep_adj_threads = 0;      // threads per tile of the adjoint sweep; 0: 64 with real amplitudes (measured), else csweep_threads
     bool use_compact = false;
     // Real amplitudes: every ansatz factor is a real rotation, so with a real Hamiltonian (even number of Y per
     // term, real coefficients, all of it on the link-table kernel) psi and lambda never get an imaginary part
@@ -236,6 +237,7 @@ struct mqc_solver {
 
 static void invalidate_graphs(mqc_solver* s);
 extern "C" {                      // defined inside the extern "C" block below
+static const double2* compact_complex_view(mqc_solver* s);
 static void drop_real(mqc_solver* s);
 static bool ham_is_real(const HamHost& H);
 }
@@ -804,6 +806,7 @@ static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     A.grad = adj ? s->grad_p() : nullptr;
     A.nB = PL.nB;
     int nt = s->csweep_threads;
+    if (adj) nt = s->csweep_adj_threads > 0 ? s->csweep_adj_threads : (s->creal ? std::min(64, s->csweep_threads) : s->csweep_threads);
     // small tiles do not feed many threads: most factor visits of a tile couple <= capA * capB / 4 pairs
     while (nt > 128 && P.capA * P.capB < 2 * nt) nt >>= 1;
     const size_t smem = mqc_c_smem_bytes(P, adj, nt / 32, PL.chunk, PL.elem);
@@ -960,9 +963,15 @@ static void happly_compact(mqc_solver* s, int which, const HamView& view, bool w
     double2* Lm = want_lam ? s->clam[0].p : nullptr;
     const SigmaTables* SG = view.SG;
     bool have = false;
-    if (s->creal && !(SG && SG->ready && !SG->n_fallback && !SG->ab_ready))
-        throw MqcError("internal: real amplitudes with a Hamiltonian part outside the link tables");
-    if (SG && SG->ready) { launch_sigma(s, SG, C, C, Lm, nB, 0u, nA, 0u, nA, 0u, 0u, 0, true, s->creal); have = true; }
+    bool real = s->creal;
+    if (real && !(SG && SG->ready && !SG->n_fallback && !SG->ab_ready)) {
+        // an operator with a part outside the link tables (mqc_expectation of arbitrary Pauli terms): expectation
+        // value on a complex copy of the state.  The handle's own Hamiltonian never gets here (ensure_layout_ready).
+        if (want_lam) throw MqcError("internal: real amplitudes with a Hamiltonian part outside the link tables");
+        C = compact_complex_view(s);
+        real = false;
+    }
+    if (SG && SG->ready) { launch_sigma(s, SG, C, C, Lm, nB, 0u, nA, 0u, nA, 0u, 0u, 0, true, real); have = true; }
     if (!have || SG->n_fallback) {
         unsigned bd = 256;
         while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
@@ -1328,6 +1337,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sigma_stage") s->sigma_stage = (int)value;
     else if (k == "sigma_split") s->sigma_split = (int)value;
     else if (k == "real_amplitudes") s->real_amplitudes = (int)value;
+    else if (k == "csweep_adj_threads") s->csweep_adj_threads = (int)value;
     else if (k == "sigma_ab") s->sigma_ab = (int)value;
     else if (k == "graph") s->use_graph = (int)value;
     else if (k == "sigma_blocked") s->sigma_blocked = (int)value;

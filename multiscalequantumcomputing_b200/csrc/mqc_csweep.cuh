@@ -115,6 +115,30 @@ __device__ __forceinline__ double mqc_rotate_pair(double* __restrict__ sp, doubl
     return g;
 }
 
+// two independent pairs of one step at once (the pairs of a step are disjoint): all loads are issued before
+// the first store, so the two rotations overlap instead of running back to back
+template <bool ADJ>
+__device__ __forceinline__ double mqc_rotate_pair2(double* __restrict__ sp, double* __restrict__ sl, const uint32_t w0, const uint32_t w1,
+                                                   const double c, const double s) {
+    const int a0 = (int)(w0 & 0x3fffu), a1 = (int)((w0 >> 14) & 0x3fffu);
+    const int b0 = (int)(w1 & 0x3fffu), b1 = (int)((w1 >> 14) & 0x3fffu);
+    const int sg0 = (int)((w0 << 3) & 0x80000000u), sg1 = (int)((w1 << 3) & 0x80000000u);
+    const double s0 = __hiloint2double(__double2hiint(s) ^ sg0, __double2loint(s));
+    const double s1 = __hiloint2double(__double2hiint(s) ^ sg1, __double2loint(s));
+    const double pa0 = sp[a0], pa1 = sp[a1], pb0 = sp[b0], pb1 = sp[b1];
+    double g = 0.0;
+    if (ADJ) {
+        const double xa0 = sl[a0], xa1 = sl[a1], xb0 = sl[b0], xb1 = sl[b1];
+        const double g0 = xa1 * pa0 - xa0 * pa1, g1 = xb1 * pb0 - xb0 * pb1;
+        g = __hiloint2double(__double2hiint(g0) ^ sg0, __double2loint(g0)) + __hiloint2double(__double2hiint(g1) ^ sg1, __double2loint(g1));
+        sl[a0] = c * xa0 - s0 * xa1; sl[a1] = c * xa1 + s0 * xa0;
+        sl[b0] = c * xb0 - s1 * xb1; sl[b1] = c * xb1 + s1 * xb0;
+    }
+    sp[a0] = c * pa0 - s0 * pa1; sp[a1] = c * pa1 + s0 * pa0;
+    sp[b0] = c * pb0 - s1 * pb1; sp[b1] = c * pb1 + s1 * pb0;
+    return g;
+}
+
 template <bool REAL> struct MqcAmp { typedef double2 T; };
 template <> struct MqcAmp<true> { typedef double T; };
 
@@ -123,7 +147,7 @@ template <> struct MqcAmp<true> { typedef double T; };
 // 16-byte units that cover the row (forward: the neighbours' elements that come along are never addressed;
 // adjoint stores: the aligned interior goes by bulk copy, up to two edge elements by plain stores).
 template <bool ADJ, int NT, int CH, bool REAL = false>
-__global__ void __launch_bounds__(NT, (1024 / NT) > 16 ? 16 : (1024 / NT))
+__global__ void __launch_bounds__(NT, (1024 / NT) > (ADJ ? 8 : 16) ? (ADJ ? 8 : 16) : (1024 / NT))   // adjoint tiles: shared memory allows <= 8 CTAs per SM anyway
 k_csweep(const __grid_constant__ MqcCArgs A) {
     typedef typename MqcAmp<REAL>::T AT;
     constexpr int ES = (int)sizeof(AT);
@@ -262,13 +286,24 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
                         double gacc = 0.0;
                         if ((uint32_t)(warp * 32) < npairs) {           // warps without a pair in this step only keep step
                             const double2 csv = hcs[MQC_C_F(hc.y)];
-                            if ((uint32_t)tid < npairs) gacc = mqc_rotate_pair<ADJ>(sp, sl, wc, csv.x, csv.y);
-                            for (uint32_t u = (uint32_t)tid + NT; u < npairs; u += NT)
-                                gacc += mqc_rotate_pair<ADJ>(sp, sl, ring[(hc.x + u) & RMASK], csv.x, csv.y);
+                            if (REAL) {
+                                uint32_t u = (uint32_t)tid;
+                                uint32_t w0 = wc;
+                                for (; u + NT < npairs; u += 2 * NT) {
+                                    gacc += mqc_rotate_pair2<ADJ>(reinterpret_cast<double*>(sp), reinterpret_cast<double*>(sl), w0,
+                                                                  ring[(hc.x + u + NT) & RMASK], csv.x, csv.y);
+                                    w0 = ring[(hc.x + u + 2 * NT) & RMASK];               // stale words past the step's end are never used
+                                }
+                                if (u < npairs) gacc += mqc_rotate_pair<ADJ>(sp, sl, w0, csv.x, csv.y);
+                            } else {
+                                if ((uint32_t)tid < npairs) gacc = mqc_rotate_pair<ADJ>(sp, sl, wc, csv.x, csv.y);
+                                for (uint32_t u = (uint32_t)tid + NT; u < npairs; u += NT)
+                                    gacc += mqc_rotate_pair<ADJ>(sp, sl, ring[(hc.x + u) & RMASK], csv.x, csv.y);
+                            }
                         }
                         if ((uint32_t)(warp * 32) < MQC_C_NP(hn.y)) wn = ring[(hn.x + (uint32_t)tid) & RMASK];
                         if (ADJ) acc8[j] = gacc;
-                        __syncthreads();
+                        if (NT == 32) __syncwarp(); else __syncthreads();       // one warp per tile: no CTA barrier between steps
                         if (tid == 0) {                                 // slots the next step no longer needs get new chunks
                             uint32_t cnt_is = (hc.y >> ISH) & 3u;
                             if (cnt_is) {

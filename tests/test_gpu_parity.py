@@ -51,6 +51,10 @@ CASES = [
     (6, 6, "blocked", {"sigma_ab": 1, "tile_bits": 8, "grad_tile_bits": 8}),       # opposite-spin doubles in the sign-adjusted basis
     (7, 6, "lex", {"sigma_ab": 1, "sigma_stage": 0, "tile_bits": 10, "grad_tile_bits": 10}),
     (5, 4, "blocked", {"sigma_ab": 1}),
+    (6, 6, "lex", {"tile_bits": 9, "grad_tile_bits": 8, "real_amplitudes": 0}),      # complex compact storage (default here: real)
+    (8, 8, "blocked", {"real_amplitudes": 0, "sigma_split": 0}),
+    (8, 8, "blocked", {"sigma_split": 8, "csweep_adj_threads": 128}),
+    (6, 4, "blocked", {"tile_bits": 8, "grad_tile_bits": 8, "csweep_adj_threads": 32}),   # real rows starting on odd columns, one warp per tile
     (4, 4, "blocked", {"compact": 0}),
     (4, 4, "lex", {"mode": 0}),                                  # one factor per pass
     (4, 2, "lex", {"tile_bits": 6, "grad_tile_bits": 6, "low_bits": 2, "compact": 0}),
@@ -149,6 +153,62 @@ def test_rdm_golden_vector(golden):
     with pytest.raises(_lib.MqcError):
         h.load_state(bad)
     h.close()
+
+
+def test_real_and_complex_storage_selection():
+    """The compact matrix holds doubles when the Hamiltonian is real (include/mqc_b200.h, mqc_amplitude_bytes) and
+    goes back to complex storage by itself: option, odd row pitch, a Hamiltonian term with an odd number of Y,
+    a complex loaded state.  Results agree with the oracle in every case."""
+    h, orc, F, tab, th = _setup(6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 8})
+    assert h.amplitude_bytes() == 8
+    e_ref, g_ref = orc.energy_grad(th)
+    e, g = h.energy_grad(th)
+    assert abs(e - e_ref) < E_TOL and abs(g - g_ref).max() < G_TOL
+    assert h.amplitude_bytes() == 8
+    # i (a^+_0 a_2 - a^+_2 a_0) on the alpha orbitals 0 and 2 = (X0 Z Z Z Y4 - Y0 Z Z Z X4) / 2 in logical qubits
+    # (bit n - 1 - q): Hermitian, imaginary matrix elements
+    n = 12
+    bit = lambda q: np.uint64(1) << np.uint64(n - 1 - q)
+    zs = bit(1) | bit(2) | bit(3)
+    x2 = np.concatenate([tab[0], [bit(0) | bit(4), bit(0) | bit(4)]]).astype(np.uint64)
+    z2 = np.concatenate([tab[1], [zs | bit(4), zs | bit(0)]]).astype(np.uint64)
+    c2 = np.concatenate([tab[2], [0.35, -0.35]])
+    h.set_hamiltonian(x2, z2, c2)
+    orc2 = UCCSDOracle(n, F.as_tuples(), F.theta_index, F.ref_index, (x2, z2, c2))
+    e2_ref, g2_ref = orc2.energy_grad(th)
+    e2, g2 = h.energy_grad(th)
+    assert h.amplitude_bytes() == 16
+    assert abs(e2 - e2_ref) < E_TOL and abs(g2 - g2_ref).max() < G_TOL
+    assert abs(h.state(th) - orc2.state(th)).max() < S_TOL
+    h.close()
+    # option and odd pitch
+    h, orc, F, tab, th = _setup(6, 6, "blocked", {"real_amplitudes": 0})
+    assert h.amplitude_bytes() == 16
+    h.close()
+    h, orc, F, tab, th = _setup(7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 9})     # C(7, 3) = 35 columns
+    assert h.amplitude_bytes() == 16
+    h.close()
+    h, orc, F, tab, th = _setup(5, 4, "blocked", {"compact": 0})
+    assert h.amplitude_bytes() == 0
+    h.close()
+    # a complex state loaded into a real handle
+    h, orc, F, tab, th = _setup(5, 4, "blocked", {})
+    assert h.amplitude_bytes() == 8
+    psi = orc.state(th) * np.exp(0.3j)
+    h.load_state(psi)
+    assert h.amplitude_bytes() == 16
+    assert abs(h.state() - psi).max() == 0.0
+    r1, r2 = h.rdm12(5, 2, 2)
+    o1, o2 = ordm.get_rdm12(psi, 4, 5)
+    assert abs(r1 - o1).max() < R_TOL and abs(r2 - o2).max() < R_TOL
+    assert abs(h.expectation(*tab).real - np.vdot(psi, apply_terms(*tab, psi)).real) < 1e-11
+    # ... and a real one stays real
+    h2, orc, F, tab, th = _setup(5, 4, "blocked", {})
+    h2.load_state(orc.state(th).real.astype(np.complex128))
+    assert h2.amplitude_bytes() == 8
+    r1b, r2b = h2.rdm12(5, 2, 2)
+    assert abs(r1b - o1).max() < R_TOL and abs(r2b - o2).max() < R_TOL
+    h.close(); h2.close()
 
 
 def _c_oracle_check(tab, F, th, e, g):
