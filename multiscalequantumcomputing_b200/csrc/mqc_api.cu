@@ -350,8 +350,10 @@ static void require_gpu(mqc_solver* s) {
     MQC_CS_ATTR(32, 1024) MQC_CS_ATTR(64, 1024) MQC_CS_ATTR(128, 1024) MQC_CS_ATTR(256, 1024) MQC_CS_ATTR(512, 1024)
     CK(cudaFuncSetAttribute(k_sigma_ab<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma_ab<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
-    CK(cudaFuncSetAttribute(k_rdm_gram<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
-    CK(cudaFuncSetAttribute(k_rdm_gram<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_rdm_gram<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_rdm_gram<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_rdm_gram<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_rdm_gram<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
@@ -804,7 +806,7 @@ static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     A.psi_in = s->cpsi[s->ccur].p; A.psi_out = s->cpsi[s->ccur ^ 1].p;
     A.lam_in = adj ? (const void*)s->clam[s->clcur].p : nullptr; A.lam_out = adj ? (void*)s->clam[s->clcur ^ 1].p : nullptr;
     A.grad = adj ? s->grad_p() : nullptr;
-    A.nB = PL.nB;
+    A.nB = PL.pitch;                                   // the kernel only uses it as the row pitch
     int nt = s->csweep_threads;
     if (adj) nt = s->csweep_adj_threads > 0 ? s->csweep_adj_threads : (s->creal ? std::min(64, s->csweep_threads) : s->csweep_threads);
     // small tiles do not feed many threads: most factor visits of a tile couple <= capA * capB / 4 pairs
@@ -840,10 +842,10 @@ static void forward_compact(mqc_solver* s, int which, const double* theta) {
     }
     if (nfac) { k_sincos<<<(nfac + 255) / 256, 256, 0, s->stream>>>(s->theta.p, s->theta_index.p, s->theta_scale.p, s->cs.p, nfac); s->counters[0]++; }
     s->ccur = 0;
-    const size_t cnt = (size_t)PL.nA * PL.nB;
+    const size_t cnt = (size_t)PL.nA * PL.pitch;
     CK(cudaMemsetAsync(s->cpsi[0].p, 0, (s->creal ? sizeof(double) : sizeof(double2)) * cnt, s->stream));
-    if (s->creal) k_set_real<<<1, 32, 0, s->stream>>>(reinterpret_cast<double*>(s->cpsi[0].p), (u64)PL.ref_row * PL.nB + PL.ref_col, 1.0);
-    else k_set_amplitude<<<1, 32, 0, s->stream>>>(s->cpsi[0].p, (u64)PL.ref_row * PL.nB + PL.ref_col, 1.0, 0.0);
+    if (s->creal) k_set_real<<<1, 32, 0, s->stream>>>(reinterpret_cast<double*>(s->cpsi[0].p), (u64)PL.ref_row * PL.pitch + PL.ref_col, 1.0);
+    else k_set_amplitude<<<1, 32, 0, s->stream>>>(s->cpsi[0].p, (u64)PL.ref_row * PL.pitch + PL.ref_col, 1.0, 0.0);
     s->counters[0]++;
     const int np = (int)PL.pass.size();
     for (int p = 0; p < np; ++p) launch_csweep(s, which, p, false);
@@ -920,10 +922,11 @@ static void alloc_blocked(mqc_solver* s) {
 
 static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Cown, const double2* Csrc, double2* Lp,
                          unsigned nB, unsigned r0, unsigned r1, unsigned src_lo, unsigned src_hi, unsigned own_lo,
-                         unsigned l_lo, int accumulate, bool may_split = false, bool real = false) {
+                         unsigned l_lo, int accumulate, bool may_split = false, bool real = false, unsigned pitch = 0) {
     // real: the three buffers hold doubles (compact storage with real amplitudes)
     MqcSigmaDev D = SG->dev;
     D.src_lo = src_lo; D.src_hi = src_hi; D.own_lo = own_lo; D.l_lo = l_lo; D.accumulate = accumulate;
+    D.pitch = pitch ? pitch : nB;
     const int elem = real ? 8 : 16;
     const bool stage = s->sigma_stage && (size_t)MQC_SG_LB * nB * elem <= 98304;
     const size_t smem = mqc_sigma_smem_bytes(D, stage, MQC_SG_LB, elem);
@@ -938,7 +941,7 @@ static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Co
             k = std::max(MQC_SG_LB, std::min(k / MQC_SG_LB * MQC_SG_LB, (D.e1a - 1) / MQC_SG_LB * MQC_SG_LB));
             D.split_l = k;
             grid.z = 2;
-            if (Lp) CK(cudaMemsetAsync(Lp, 0, (size_t)(r1 - r0) * nB * elem, s->stream));
+            if (Lp) CK(cudaMemsetAsync(Lp, 0, (size_t)(r1 - r0) * D.pitch * elem, s->stream));
         }
     }
     if (real) {
@@ -971,7 +974,7 @@ static void happly_compact(mqc_solver* s, int which, const HamView& view, bool w
         C = compact_complex_view(s);
         real = false;
     }
-    if (SG && SG->ready) { launch_sigma(s, SG, C, C, Lm, nB, 0u, nA, 0u, nA, 0u, 0u, 0, true, real); have = true; }
+    if (SG && SG->ready) { launch_sigma(s, SG, C, C, Lm, nB, 0u, nA, 0u, nA, 0u, 0u, 0, true, real, real ? s->cplan[which].pitch : nB); have = true; }
     if (!have || SG->n_fallback) {
         unsigned bd = 256;
         while (bd > 32 && (u64)(bd / 2) * MQC_HS_R >= nB) bd >>= 1;
@@ -1444,7 +1447,7 @@ static void build_compact_plans(mqc_solver* s, bool real) {
         bool ok = true;
         for (int w = 0; w < 2 && ok; ++w) {
             s->cplan[w] = mqc_build_cplan(s->sched[w], s->fac, s->na, s->nb, s->ref_index, elem);
-            ok = s->cplan[w].ok && s->cplan[w].max_smem[w] <= 232448 && (elem == 16 || !(s->cplan[w].nB & 1u));   // bulk copies of real rows need an even pitch
+            ok = s->cplan[w].ok && s->cplan[w].max_smem[w] <= 232448;
             if (!ok && getenv("MQC_DEBUG")) fprintf(stderr, "[mqc] compact plan %d (%d-byte amplitudes) not used: %s (smem %zu)\n", w, elem, s->cplan[w].why, s->cplan[w].max_smem[w]);
         }
         if (ok) { s->use_compact = true; s->creal = elem == 8; return; }
@@ -1452,7 +1455,7 @@ static void build_compact_plans(mqc_solver* s, bool real) {
     for (int w = 0; w < 2; ++w) s->cplan[w] = MqcCPlan();
 }
 static size_t cbuf_len(const mqc_solver* s, int w) {       // double2 units of one compact buffer
-    const size_t cnt = (size_t)s->cplan[w].nA * s->cplan[w].nB;
+    const size_t cnt = (size_t)s->cplan[w].nA * s->cplan[w].pitch;
     return s->creal ? (cnt + 1) / 2 : cnt;
 }
 static void upload_compact(mqc_solver* s) {
@@ -1908,7 +1911,7 @@ static const double2* compact_complex_view(mqc_solver* s) {
     const size_t cnt = (size_t)s->cplan[s->cwhich].nA * s->cplan[s->cwhich].nB;
     if (s->cscratch.n != cnt) s->cscratch.alloc(cnt);
     k_real_to_complex<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 16), 256, 0, s->stream>>>(
-        reinterpret_cast<const double*>(s->cpsi[s->ccur].p), s->cscratch.p, cnt);
+        reinterpret_cast<const double*>(s->cpsi[s->ccur].p), s->cscratch.p, cnt, s->cplan[s->cwhich].nB, s->cplan[s->cwhich].pitch);
     return s->cscratch.p;
 }
 // compact storage -> dense register in the physical layout of schedule cwhich (for the consumers
@@ -2024,8 +2027,8 @@ int mqc_rdm12(mqc_solver_t* L, int32_t n_orb, int32_t n_alpha, int32_t n_beta, d
         const int T = n2i <= 144 ? 9 : 8, BS = 16 * T;
         const int nblk = (n2i + BS - 1) / BS;
         MqcRdmC R{};
-        R.C = compact_complex_view(s); R.aorb = Lt.aorb.p; R.borb = Lt.borb.p; R.rank_a = Lt.rank_a.p; R.rank_b = Lt.rank_b.p;
-        R.nA = s->cplan[s->cwhich].nA; R.nB = s->cplan[s->cwhich].nB; R.n = n_orb; R.n2 = n2i; R.nblk = nblk;
+        R.C = s->cpsi[s->ccur].p; R.aorb = Lt.aorb.p; R.borb = Lt.borb.p; R.rank_a = Lt.rank_a.p; R.rank_b = Lt.rank_b.p;
+        R.nA = s->cplan[s->cwhich].nA; R.nB = s->cplan[s->cwhich].nB; R.pitch = s->cplan[s->cwhich].pitch; R.n = n_orb; R.n2 = n2i; R.nblk = nblk;
         const u64 n_blocks = (u64)R.nA * ((R.nB + MQC_RDM_KB - 1) / MQC_RDM_KB);
         const int groups = (int)std::min<u64>(n_blocks, (u64)std::max(1, s->n_sm / (nblk * nblk)));
         const size_t gsz = (size_t)groups * nblk * nblk * BS * BS, g1sz = (size_t)groups * n2i;
@@ -2035,10 +2038,13 @@ int mqc_rdm12(mqc_solver_t* L, int32_t n_orb, int32_t n_alpha, int32_t n_beta, d
         if (s->rdm_out.n < n2s + n4s) s->rdm_out.alloc(n2s + n4s);
         R.gpart = s->rdm_gpart.p; R.g1part = s->rdm_g1part.p;
         CK(cudaMemsetAsync(s->rdm_g1part.p, 0, sizeof(double) * g1sz, s->stream));
-        const size_t smem = (size_t)(nblk > 1 ? 2 : 1) * MQC_RDM_KB * BS * sizeof(double2);
+        const size_t smem = (size_t)(nblk > 1 ? 2 : 1) * MQC_RDM_KB * BS * (s->creal ? sizeof(double) : sizeof(double2));
         dim3 grid(groups, nblk * nblk);
-        if (T == 9) k_rdm_gram<9><<<grid, MQC_RDM_THREADS, smem, s->stream>>>(R);
-        else k_rdm_gram<8><<<grid, MQC_RDM_THREADS, smem, s->stream>>>(R);
+        if (s->creal) {
+            if (T == 9) k_rdm_gram<9, true><<<grid, MQC_RDM_THREADS, smem, s->stream>>>(R);
+            else k_rdm_gram<8, true><<<grid, MQC_RDM_THREADS, smem, s->stream>>>(R);
+        } else if (T == 9) k_rdm_gram<9, false><<<grid, MQC_RDM_THREADS, smem, s->stream>>>(R);
+        else k_rdm_gram<8, false><<<grid, MQC_RDM_THREADS, smem, s->stream>>>(R);
         const size_t work = rdm2 ? n4s : n2s;
         k_rdm_finish<<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->rdm_gpart.p, s->rdm_g1part.p, groups, n_orb, nblk, BS,
                                                                           s->rdm_out.p, rdm2 ? s->rdm_out.p + n2s : nullptr);
@@ -2296,8 +2302,9 @@ int mqc_load_state(mqc_solver_t* s, const double* re_im, int64_t n_amplitudes) {
             if (!real) drop_real(s);
         }
         if (s->creal) {
-            std::vector<double> R(C.size());
-            for (size_t i = 0; i < C.size(); ++i) R[i] = C[i].x;
+            const MqcCPlan& PR = s->cplan[0];                     // (drop_real may have rebuilt the plans: re-read)
+            std::vector<double> R((size_t)PR.nA * PR.pitch, 0.0);
+            for (uint32_t ia = 0; ia < PR.nA; ++ia) for (uint32_t ib = 0; ib < PR.nB; ++ib) R[(size_t)ia * PR.pitch + ib] = C[(size_t)ia * PR.nB + ib].x;
             CK(cudaMemcpyAsync(s->cpsi[0].p, R.data(), sizeof(double) * R.size(), cudaMemcpyHostToDevice, s->stream));
             CK(cudaStreamSynchronize(s->stream));
         } else {

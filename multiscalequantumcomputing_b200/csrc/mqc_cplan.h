@@ -92,6 +92,7 @@ struct MqcCPlan {
     std::vector<uint32_t> astr, bstr;        // canonical (ascending) strings, orbital space
     int chunk = 256;                         // pair words per ring slot (256 or 1024)
     uint32_t max_step_pairs = 0;
+    uint32_t pitch = 0;                      // elements between consecutive rows of the device matrix: nB, rounded up to even for 8-byte amplitudes
     int elem = 16;                           // bytes per amplitude the programs were laid out for (row stride, bank order)
     size_t max_smem[2] = {0, 0};             // shared memory a CTA needs: forward, adjoint (any pass)
     const char* why = "";                    // why ok == false
@@ -208,6 +209,7 @@ static inline MqcCPlan mqc_build_cplan(const MqcSchedule& S, const std::vector<M
     if (PL.astr.empty() || PL.bstr.empty()) return PL;
     if ((double)PL.astr.size() * (double)PL.bstr.size() > 4.0e9) return PL;
     PL.nA = (uint32_t)PL.astr.size(); PL.nB = (uint32_t)PL.bstr.size();
+    PL.pitch = elem == 8 ? ((PL.nB + 1u) & ~1u) : PL.nB;
     // logical bit l = n - 1 - q, qubit q = 2 p + spin
     auto split = [&](u64 lmask, uint32_t& a, uint32_t& b) {
         a = b = 0;

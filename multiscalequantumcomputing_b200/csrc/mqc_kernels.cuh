@@ -99,8 +99,11 @@ __global__ void k_set_real(double* psi, u64 index, double v) {
     if (blockIdx.x == 0 && threadIdx.x == 0) psi[index] = v;
 }
 // real compact state -> complex copy
-__global__ void k_real_to_complex(const double* __restrict__ in, double2* __restrict__ out, const u64 n) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) out[i] = make_double2(in[i], 0.0);
+__global__ void k_real_to_complex(const double* __restrict__ in, double2* __restrict__ out, const u64 n, const unsigned n_b, const unsigned pitch) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 r = i / n_b;
+        out[i] = make_double2(in[r * pitch + (i - r * n_b)], 0.0);          // rows of the real matrix are `pitch` apart
+    }
 }
 
 // out[logical index] = psi[physical index]; phys_pos[l] = physical position of logical bit l

@@ -23,12 +23,13 @@
 #define MQC_RDM_THREADS 256    // 16 x 16 threads, T x T accumulators each
 
 struct MqcRdmC {
-    const double2* C;          // compact state, canonical order
+    const void* C;             // compact state, canonical order: double2, or double with real amplitudes
     const unsigned* aorb;      // [nA] alpha strings (orbital space), ascending
     const unsigned* borb;      // [nB]
     const unsigned* rank_a;    // [2^n] string -> row (0xffffffff: not in the sector)
     const unsigned* rank_b;
     unsigned nA, nB;
+    unsigned pitch;            // elements between consecutive rows of C
     int n;                     // spatial orbitals
     int n2;                    // n * n
     int nblk;                  // blocks of BS = 16 T rows the n^2 x n^2 matrix is cut into
@@ -46,14 +47,29 @@ __device__ __forceinline__ unsigned mqc_rdm_sign(const unsigned own, const unsig
     return (unsigned)(__popc(own & strictly) + __popc(other & cross)) & 1u;
 }
 
-template <int T>
+template <bool REAL> struct MqcRdmAmp { typedef double2 T; };
+template <> struct MqcRdmAmp<true> { typedef double T; };
+__device__ __forceinline__ double2 mqc_rdm_zero(double2) { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ double mqc_rdm_zero(double) { return 0.0; }
+__device__ __forceinline__ void mqc_rdm_add(double2& v, const double2 c, const unsigned neg) {
+    if (neg) { v.x -= c.x; v.y -= c.y; } else { v.x += c.x; v.y += c.y; }
+}
+__device__ __forceinline__ void mqc_rdm_add(double& v, const double c, const unsigned neg) { v += neg ? -c : c; }
+// acc + Re(conj(a) b)
+__device__ __forceinline__ double mqc_rdm_dot(const double2 a, const double2 b, const double acc) { return fma(a.x, b.x, fma(a.y, b.y, acc)); }
+__device__ __forceinline__ double mqc_rdm_dot(const double a, const double b, const double acc) { return fma(a, b, acc); }
+
+// REAL: real amplitudes (8-byte compact storage): D is real, half the shared memory and half the FMAs
+template <int T, bool REAL>
 __global__ void __launch_bounds__(MQC_RDM_THREADS, 1)
 k_rdm_gram(const __grid_constant__ MqcRdmC R) {
+    typedef typename MqcRdmAmp<REAL>::T AT;
+    const AT* __restrict__ Cst = static_cast<const AT*>(R.C);
     constexpr int BS = 16 * T;
     extern __shared__ __align__(16) unsigned char rdm_smem[];
-    double2* Dx = reinterpret_cast<double2*>(rdm_smem);                      // [KB][BS]  rows of block bx, transposed
-    double2* Dy = Dx + MQC_RDM_KB * BS;                                       // [KB][BS]  rows of block by (== Dx when bx == by)
-    __shared__ double2 ck[MQC_RDM_KB];
+    AT* Dx = reinterpret_cast<AT*>(rdm_smem);                      // [KB][BS]  rows of block bx, transposed
+    AT* Dy = Dx + MQC_RDM_KB * BS;                                       // [KB][BS]  rows of block by (== Dx when bx == by)
+    __shared__ AT ck[MQC_RDM_KB];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int bx = blockIdx.y / R.nblk, by = blockIdx.y - bx * R.nblk;
     const bool same = bx == by;
@@ -73,34 +89,32 @@ k_rdm_gram(const __grid_constant__ MqcRdmC R) {
         const unsigned ia = (unsigned)(blk / cols_blocks), ib0 = (unsigned)(blk - (unsigned long long)ia * cols_blocks) * MQC_RDM_KB;
         const unsigned Ka = __ldg(R.aorb + ia);
         const int kv = min((int)MQC_RDM_KB, (int)(nB - ib0));                  // valid determinants of this block
-        const double2* __restrict__ Crow = R.C + (size_t)ia * nB;
+        const AT* __restrict__ Crow = Cst + (size_t)ia * R.pitch;
         __syncthreads();                                                      // previous block's Gram pass is done with Dx / Dy
-        if (tid < MQC_RDM_KB) ck[tid] = tid < kv ? Crow[ib0 + tid] : make_double2(0.0, 0.0);
+        if (tid < MQC_RDM_KB) ck[tid] = tid < kv ? Crow[ib0 + tid] : mqc_rdm_zero(AT());
         for (int half = 0; half < (same ? 1 : 2); ++half) {
-            double2* D = half ? Dy : Dx;
+            AT* D = half ? Dy : Dx;
             const int r0 = (half ? by : bx) * BS;
             for (int e = tid; e < MQC_RDM_KB * BS; e += MQC_RDM_THREADS) {
                 const int i = e % BS, k = e / BS;
                 const int rs = r0 + i;
-                double2 val = make_double2(0.0, 0.0);
+                AT val = mqc_rdm_zero(AT());
                 if (rs < n2 && k < kv) {
                     const int r = rs / n, s = rs - r * n;
                     const unsigned Kb = __ldg(R.borb + ib0 + k);
                     // alpha: K has r_alpha, J = K with r -> s
                     if ((Ka >> r) & 1u) {
-                        if (r == s) { const double2 c = Crow[ib0 + k]; val.x += c.x; val.y += c.y; }
+                        if (r == s) mqc_rdm_add(val, Crow[ib0 + k], 0u);
                         else if (!((Ka >> s) & 1u)) {
                             const unsigned Ja = Ka ^ (1u << r) ^ (1u << s);
-                            const double2 c = R.C[(size_t)__ldg(R.rank_a + Ja) * nB + ib0 + k];
-                            if (mqc_rdm_sign(Ka, Kb, r, s, false)) { val.x -= c.x; val.y -= c.y; } else { val.x += c.x; val.y += c.y; }
+                            mqc_rdm_add(val, Cst[(size_t)__ldg(R.rank_a + Ja) * R.pitch + ib0 + k], mqc_rdm_sign(Ka, Kb, r, s, false));
                         }
                     }
                     if ((Kb >> r) & 1u) {
-                        if (r == s) { const double2 c = Crow[ib0 + k]; val.x += c.x; val.y += c.y; }
+                        if (r == s) mqc_rdm_add(val, Crow[ib0 + k], 0u);
                         else if (!((Kb >> s) & 1u)) {
                             const unsigned Jb = Kb ^ (1u << r) ^ (1u << s);
-                            const double2 c = Crow[__ldg(R.rank_b + Jb)];
-                            if (mqc_rdm_sign(Kb, Ka, r, s, true)) { val.x -= c.x; val.y -= c.y; } else { val.x += c.x; val.y += c.y; }
+                            mqc_rdm_add(val, Crow[__ldg(R.rank_b + Jb)], mqc_rdm_sign(Kb, Ka, r, s, true));
                         }
                     }
                 }
@@ -112,20 +126,20 @@ k_rdm_gram(const __grid_constant__ MqcRdmC R) {
         if (by == 0 && tid < BS) {
             double a1 = 0.0;
 #pragma unroll 8
-            for (int k = 0; k < MQC_RDM_KB; ++k) { const double2 d = Dx[k * BS + tid], c = ck[k]; a1 = fma(c.x, d.x, fma(c.y, d.y, a1)); }
+            for (int k = 0; k < MQC_RDM_KB; ++k) a1 = mqc_rdm_dot(ck[k], Dx[k * BS + tid], a1);
             acc1 += a1;
         }
         // Gram update: acc[a][b] += sum_k Re(conj(Dx[ty + 16 a][k]) Dy[tx + 16 b][k])
 #pragma unroll 1
         for (int k = 0; k < MQC_RDM_KB; ++k) {
-            double2 yb[T];
+            AT yb[T];
 #pragma unroll
             for (int b = 0; b < T; ++b) yb[b] = Dy[k * BS + tx + 16 * b];
 #pragma unroll
             for (int a = 0; a < T; ++a) {
-                const double2 xa = Dx[k * BS + ty + 16 * a];
+                const AT xa = Dx[k * BS + ty + 16 * a];
 #pragma unroll
-                for (int b = 0; b < T; ++b) acc[a][b] = fma(xa.x, yb[b].x, fma(xa.y, yb[b].y, acc[a][b]));
+                for (int b = 0; b < T; ++b) acc[a][b] = mqc_rdm_dot(xa, yb[b], acc[a][b]);
             }
         }
     }

@@ -77,6 +77,7 @@ struct MqcSigmaDev {
     // (first row own_lo).  Replicated matrix: one block [0, n_a), all three offsets 0.
     unsigned src_lo, src_hi, own_lo, l_lo;
     int accumulate;                // L += instead of L =  (rounds after the first)
+    unsigned pitch;                // elements between consecutive rows of Cown / Csrc / L (0: n_b)
     // Row split (replicated matrix only): gridDim.z == 2, part z = 0 does phase 0 and the alpha single
     // links [0, split_l), part 1 the remaining links and phase 2; both ADD into a zeroed L with
     // atomics (two addends per element: the sum does not depend on their order).  0: one CTA per row.
@@ -540,7 +541,8 @@ k_sigma(const typename MqcSgAmp<REAL>::T* __restrict__ Cown, const typename MqcS
         typename MqcSgAmp<REAL>::T* __restrict__ L, const __grid_constant__ MqcSigmaDev S, double* __restrict__ e_out) {
     typedef typename MqcSgAmp<REAL>::T AT;
     extern __shared__ __align__(16) unsigned char sg_smem[];
-    const AT* __restrict__ C = Csrc - (size_t)S.src_lo * S.n_b;           // C[src * nB + j] for src in the block
+    const size_t pitch = S.pitch ? S.pitch : S.n_b;                       // row pitch of the three state buffers
+    const AT* __restrict__ C = Csrc - (size_t)S.src_lo * pitch;           // C[src * pitch + j] for src in the block
     const unsigned nA = S.n_a, nB = S.n_b;
     const int M2 = S.n_m2 > 0 ? S.n_m2 : 1;
     const int WS = 2 * (S.n_m2 + 1);                               // weight-table stride; last pair = 0 (padding)
@@ -580,7 +582,7 @@ k_sigma(const typename MqcSgAmp<REAL>::T* __restrict__ Cown, const typename MqcS
             if (pbv == 0) sxd[ib] = sd;
         }
         for (int k = tid; k <= S.n_m4; k += MQC_SG_THREADS) sg4[k] = (unsigned char)(__popc(ap & __ldg(S.sa_b4 + k)) & 1u);
-        const AT* __restrict__ Crow = C + (size_t)i * nB;
+        const AT* __restrict__ Crow = C + (size_t)i * pitch;
         if (STAGE) for (unsigned j = tid; j < nB; j += MQC_SG_THREADS) srow[j] = Crow[j];
         __syncthreads();
         const AT* __restrict__ row = STAGE ? srow : Crow;
@@ -679,7 +681,7 @@ k_sigma(const typename MqcSgAmp<REAL>::T* __restrict__ Cown, const typename MqcS
                 wl[l * WS + k] = w;
             }
             if (STAGE) {
-                const AT* __restrict__ Crow = C + (size_t)src[l] * nB;
+                const AT* __restrict__ Crow = C + (size_t)src[l] * pitch;
                 const unsigned z = zb[l];
 #pragma unroll 4
                 for (unsigned j = tid; j < nB; j += MQC_SG_THREADS) {
@@ -696,7 +698,7 @@ k_sigma(const typename MqcSgAmp<REAL>::T* __restrict__ Cown, const typename MqcS
         for (int r = 0; r < MQC_SG_R; ++r) sl[r] = 0u;
 #pragma unroll
         for (int l = 0; l < LB; ++l) {
-            row[l] = STAGE ? (srow + (size_t)l * nB) : (C + (size_t)src[l] * nB);
+            row[l] = STAGE ? (srow + (size_t)l * nB) : (C + (size_t)src[l] * pitch);
             const double al = ok[l] ? __ldg(S.ta1 + (size_t)ia[l] * nA + src[l]) : 0.0;
 #pragma unroll
             for (int r = 0; r < MQC_SG_R; ++r) {
@@ -766,7 +768,7 @@ k_sigma(const typename MqcSgAmp<REAL>::T* __restrict__ Cown, const typename MqcS
 #pragma unroll 2
         for (int l = 0; l < n2; ++l) {
             const MqcSgA2 ent = a2[l];
-            const AT* __restrict__ Crow = C + (size_t)ent.src * nB;
+            const AT* __restrict__ Crow = C + (size_t)ent.src * pitch;
 #pragma unroll
             for (int r = 0; r < MQC_SG_R; ++r) {
                 const AT v = Crow[jc[r]];
@@ -782,12 +784,12 @@ k_sigma(const typename MqcSgAmp<REAL>::T* __restrict__ Cown, const typename MqcS
     for (int r = 0; r < MQC_SG_R; ++r) {
         if (jb[r] < nB) {
             if (L) {
-                const size_t o = (size_t)(i - S.l_lo) * nB + jb[r];
+                const size_t o = (size_t)(i - S.l_lo) * pitch + jb[r];
                 if (gridDim.z > 1) mqc_sg_atomic(L + o, ar[r], ai[r]);
                 else if (S.accumulate) mqc_sg_add(L + o, ar[r], ai[r]);
                 else mqc_sg_store(L + o, ar[r], ai[r]);
             }
-            mqc_sg_dot(Cown[(size_t)(i - S.own_lo) * nB + jb[r]], ar[r], ai[r], er, ei);
+            mqc_sg_dot(Cown[(size_t)(i - S.own_lo) * pitch + jb[r]], ar[r], ai[r], er, ei);
         }
     }
 #pragma unroll

@@ -18,6 +18,8 @@ def main():
     n = int(sys.argv[1])
     energy_only = "energy" in sys.argv[2:]
     opts = [kv.split("=") for kv in sys.argv[2:] if "=" in kv]
+    reps_opt = [int(v) for k, v in opts if k == "reps"]
+    opts = [(k, v) for k, v in opts if k != "reps"]
     ne = n if n % 2 == 0 else n - 1
     t0 = time.perf_counter()
     tab = fragment_term_table(*random_fragment_integrals(n, 1234), 0, 0.0, 0.25)
@@ -35,7 +37,7 @@ def main():
     else:
         e, g = h.energy_grad(th)
     t3 = time.perf_counter()
-    reps = 1 if energy_only else 2
+    reps = reps_opt[0] if reps_opt else (1 if energy_only else 2)
     ph = np.zeros(4)
     for _ in range(reps):
         e2 = h.energy(th) if energy_only else h.energy_grad_resident()
@@ -45,13 +47,14 @@ def main():
     from math import comb
     ndet = comb(n, ne // 2) * comb(n, ne - ne // 2)
     info = h.cplan_info(0 if energy_only else 1)
+    ab = h.amplitude_bytes() or 16
     norm = h.expectation(np.zeros(1, np.uint64), np.zeros(1, np.uint64), np.ones(1)).real
     print(json.dumps({"n_qubits": 2 * n, "opts": dict(opts), "n_theta": F.n_theta, "n_terms": len(tab[0]), "n_det": ndet,
-                      "sector_MB": 16e-6 * ndet, "compact_passes": info["n_passes"], "passes": t["forward_passes"],
+                      "amplitude_bytes": ab, "sector_MB": ab * 1e-6 * ndet, "compact_passes": info["n_passes"], "passes": t["forward_passes"],
                       "host_tables_s": t1 - t0, "setup_s": t2 - t1, "first_eval_s": t3 - t2,
                       "fwd_ms": ph[0], "ham_ms": ph[1], "rev_ms": ph[2], "total_ms": ph[3], "energy": e, "dE_repeat": abs(e - e2),
-                      "fwd_GBps_per_pass": 2 * 16e-9 * ndet / (ph[0] * 1e-3 / max(1, t["forward_passes"])),
-                      "rev_GBps_per_pass": 4 * 16e-9 * ndet / (ph[2] * 1e-3 / max(1, t["reverse_passes"])) if ph[2] > 0 else None,
+                      "fwd_GBps_per_pass": 2 * ab * 1e-9 * ndet / (ph[0] * 1e-3 / max(1, t["forward_passes"])),
+                      "rev_GBps_per_pass": 4 * ab * 1e-9 * ndet / (ph[2] * 1e-3 / max(1, t["reverse_passes"])) if ph[2] > 0 else None,
                       "gnorm": float(np.linalg.norm(g)), "norm": norm, "what": "energy" if energy_only else "energy+gradient"}), flush=True)
     h.close()
 

@@ -157,7 +157,7 @@ def test_rdm_golden_vector(golden):
 
 def test_real_and_complex_storage_selection():
     """The compact matrix holds doubles when the Hamiltonian is real (include/mqc_b200.h, mqc_amplitude_bytes) and
-    goes back to complex storage by itself: option, odd row pitch, a Hamiltonian term with an odd number of Y,
+    goes back to complex storage by itself: option, a Hamiltonian term with an odd number of Y,
     a complex loaded state.  Results agree with the oracle in every case."""
     h, orc, F, tab, th = _setup(6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 8})
     assert h.amplitude_bytes() == 8
@@ -181,12 +181,20 @@ def test_real_and_complex_storage_selection():
     assert abs(e2 - e2_ref) < E_TOL and abs(g2 - g2_ref).max() < G_TOL
     assert abs(h.state(th) - orc2.state(th)).max() < S_TOL
     h.close()
-    # option and odd pitch
+    # option; odd number of columns
     h, orc, F, tab, th = _setup(6, 6, "blocked", {"real_amplitudes": 0})
     assert h.amplitude_bytes() == 16
     h.close()
-    h, orc, F, tab, th = _setup(7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 9})     # C(7, 3) = 35 columns
-    assert h.amplitude_bytes() == 16
+    h, orc, F, tab, th = _setup(7, 6, "blocked", {"tile_bits": 10, "grad_tile_bits": 9})     # C(7, 3) = 35 columns: padded row pitch
+    assert h.amplitude_bytes() == 8
+    e_ref, g_ref = orc.energy_grad(th)
+    e, g = h.energy_grad(th)
+    assert abs(e - e_ref) < E_TOL and abs(g - g_ref).max() < G_TOL
+    h.prepare(th)
+    r1, r2 = h.rdm12(7, 3, 3)
+    o1, o2 = ordm.get_rdm12(orc.state(th), 6, 7)
+    assert abs(r1 - o1).max() < R_TOL and abs(r2 - o2).max() < R_TOL
+    assert abs(h.state() - orc.state(th)).max() < S_TOL
     h.close()
     h, orc, F, tab, th = _setup(5, 4, "blocked", {"compact": 0})
     assert h.amplitude_bytes() == 0
