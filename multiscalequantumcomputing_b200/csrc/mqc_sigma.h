@@ -141,6 +141,47 @@ static inline void mqc_sg_strings(int n_orb, int k, std::vector<unsigned>& out, 
     }
 }
 
+// The order of a column's ELL entries is free (a sum).  Sixteen consecutive output columns are the lanes of one
+// shared-memory wavefront of 8-byte gathers: permute every column's entries so that, slot by slot, the sixteen
+// source columns fall into different bank pairs (col mod 16) and - for the alpha-beta table - so do the weight
+// indices (greedy; equal addresses are a broadcast, not a conflict).  key2 < 0: no second key.
+template <class Key2>
+static inline void mqc_sg_bank_order(std::vector<std::vector<unsigned>>& rows, Key2 key2) {
+    const size_t nb = rows.size();
+    for (size_t g0 = 0; g0 < nb; g0 += 16) {
+        const size_t g1 = std::min(nb, g0 + 16);
+        size_t emax = 0;
+        for (size_t j = g0; j < g1; ++j) emax = std::max(emax, rows[j].size());
+        std::vector<std::vector<unsigned>> out(g1 - g0);
+        std::vector<std::vector<char>> used(g1 - g0);
+        for (size_t j = g0; j < g1; ++j) { used[j - g0].assign(rows[j].size(), 0); out[j - g0].reserve(rows[j].size()); }
+        for (size_t e = 0; e < emax; ++e) {
+            int bank_col[16], bank_k2[16];
+            for (int b = 0; b < 16; ++b) { bank_col[b] = -1; bank_k2[b] = -1; }
+            for (size_t j = g0; j < g1; ++j) {
+                const std::vector<unsigned>& r = rows[j];
+                std::vector<char>& u = used[j - g0];
+                if (out[j - g0].size() >= r.size()) continue;
+                int best = -1, best_cost = 99;
+                for (size_t c = 0; c < r.size(); ++c) {
+                    if (u[c]) continue;
+                    const int col = (int)(r[c] & 0xffffu), k2 = key2(r[c]);
+                    int cost = 0;
+                    if (bank_col[col & 15] >= 0 && bank_col[col & 15] != col) cost += 2;
+                    if (k2 >= 0 && bank_k2[k2 & 15] >= 0 && bank_k2[k2 & 15] != k2) cost += 1;
+                    if (cost < best_cost) { best_cost = cost; best = (int)c; if (!cost) break; }
+                }
+                u[best] = 1;
+                const int col = (int)(r[best] & 0xffffu), k2 = key2(r[best]);
+                if (bank_col[col & 15] < 0) bank_col[col & 15] = col;
+                if (k2 >= 0 && bank_k2[k2 & 15] < 0) bank_k2[k2 & 15] = k2;
+                out[j - g0].push_back(r[best]);
+            }
+        }
+        for (size_t j = g0; j < g1; ++j) rows[j].swap(out[j - g0]);
+    }
+}
+
 // xq / zq: Pauli masks in QUBIT space (bit q = qubit q), c: coefficients.  Returns the tables;
 // terms that cannot take the fast path are listed in fallback_terms.
 static inline MqcSigmaHost mqc_sigma_build(int n_orb, int na, int nb, const std::vector<u64>& xq,
@@ -325,6 +366,7 @@ static inline MqcSigmaHost mqc_sigma_build(int n_orb, int na, int nb, const std:
             }
             emax = std::max(emax, rows[j].size());
         }
+        mqc_sg_bank_order(rows, [](unsigned en) { return (int)(((en >> 16) & 0xffu) * 2u + ((en >> 24) & 1u)); });
         S.cls_off[c + 1] = S.cls_off[c] + (int)emax;
         const size_t base = S.ell_b1.size();
         S.ell_b1.resize(base + emax * S.n_b, (unsigned)S.n_m2 << 16);
@@ -351,6 +393,7 @@ static inline MqcSigmaHost mqc_sigma_build(int n_orb, int na, int nb, const std:
             }
         }
         for (auto& r : rows) emax = std::max(emax, r.size());
+        mqc_sg_bank_order(rows, [](unsigned) { return -1; });
         S.e2b = (int)emax;
         S.ell_b2.assign(std::max<size_t>(1, emax * S.n_b), (unsigned)S.n_m4 << 16);
         for (unsigned j = 0; j < S.n_b; ++j)
