@@ -206,6 +206,8 @@ struct mqc_solver {
 
     HamHost ham, ham_fb;            // all terms / the terms the link-table kernel leaves to k_happly_sector
     SigmaTables sig;
+    int sigma_stage_one = 0;
+    int sigma_stage_bytes = 98304;                        // shared memory the staged source rows of K2 may take
     int sigma_split = -1;                                 // K2 row split: -1 auto, 0 off, k: part 0 takes the first k alpha single links
     int use_sigma = 1, sigma_stage = 1, sigma_ab = 0;     // sigma_ab: opposite-spin doubles through k_sigma_ab (measured: no faster, both are shared-memory-gather bound)
     // The launch sequence of an evaluation depends on theta only through device buffers, so a
@@ -357,6 +359,10 @@ static void require_gpu(mqc_solver* s) {
     CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma<true, MQC_SG_LB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
+    CK(cudaFuncSetAttribute(k_sigma<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     CK(cudaFuncSetAttribute(k_sigma<false, MQC_SG_LB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120000));
     s->gpu_ready = true;
 }
@@ -928,8 +934,15 @@ static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Co
     D.src_lo = src_lo; D.src_hi = src_hi; D.own_lo = own_lo; D.l_lo = l_lo; D.accumulate = accumulate;
     D.pitch = pitch ? pitch : nB;
     const int elem = real ? 8 : 16;
-    const bool stage = s->sigma_stage && (size_t)MQC_SG_LB * nB * elem <= 98304;
-    const size_t smem = mqc_sigma_smem_bytes(D, stage, MQC_SG_LB, elem);
+    // source rows staged in shared memory, four links at a time; longer rows two at a time (28 qubits with real
+    // amplitudes: K2 36.2 -> 32.9 ms); one at a time is slower than unstaged gathers from L1 / L2 (30 qubits: 171
+    // against 151 ms) and only kept for tests (sigma_stage_one = 1)
+    int lb = MQC_SG_LB;
+    const size_t cap = (size_t)s->sigma_stage_bytes;
+    while (lb > (s->sigma_stage_one ? 1 : 2) && (size_t)lb * nB * elem > cap) lb >>= 1;
+    const bool stage = s->sigma_stage && (size_t)lb * nB * elem <= cap;
+    if (!stage) lb = MQC_SG_LB;
+    const size_t smem = mqc_sigma_smem_bytes(D, stage, lb, elem);
     dim3 grid(r1 - r0, (nB + MQC_SG_THREADS * MQC_SG_R - 1) / (MQC_SG_THREADS * MQC_SG_R));
     // Few CTAs per SM (924 rows on 444 slots at 24 qubits: the third wave is 8 % full): halve the work per CTA.
     // sigma_split: -1 auto, 0 off, k > 0: part 0 takes the first k alpha single links.
@@ -944,13 +957,13 @@ static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Co
             if (Lp) CK(cudaMemsetAsync(Lp, 0, (size_t)(r1 - r0) * D.pitch * elem, s->stream));
         }
     }
-    if (real) {
-        const double* co = reinterpret_cast<const double*>(Cown);
-        const double* cs = reinterpret_cast<const double*>(Csrc);
-        double* lp = reinterpret_cast<double*>(Lp);
-        if (stage) k_sigma<true, MQC_SG_LB, true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(co, cs, lp, D, s->scalars_p());
-        else k_sigma<false, MQC_SG_LB, true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(co, cs, lp, D, s->scalars_p());
-    } else if (stage) k_sigma<true, MQC_SG_LB, false><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p());
+#define MQC_SG_LAUNCH(LB_) do { \
+        if (real) k_sigma<true, LB_, true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(reinterpret_cast<const double*>(Cown), \
+                      reinterpret_cast<const double*>(Csrc), reinterpret_cast<double*>(Lp), D, s->scalars_p()); \
+        else k_sigma<true, LB_, false><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p()); } while (0)
+    if (stage) { if (lb == 4) MQC_SG_LAUNCH(4); else if (lb == 2) MQC_SG_LAUNCH(2); else MQC_SG_LAUNCH(1); }
+    else if (real) k_sigma<false, MQC_SG_LB, true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(reinterpret_cast<const double*>(Cown),
+                       reinterpret_cast<const double*>(Csrc), reinterpret_cast<double*>(Lp), D, s->scalars_p());
     else k_sigma<false, MQC_SG_LB, false><<<grid, MQC_SG_THREADS, smem, s->stream>>>(Cown, Csrc, Lp, D, s->scalars_p());
     s->counters[0]++;
 }
@@ -1339,6 +1352,8 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sigma") s->use_sigma = (int)value;
     else if (k == "sigma_stage") s->sigma_stage = (int)value;
     else if (k == "sigma_split") s->sigma_split = (int)value;
+    else if (k == "sigma_stage_one") s->sigma_stage_one = (int)value;
+    else if (k == "sigma_stage_bytes") { if (value < 0 || value > 98304) throw MqcError("sigma_stage_bytes must be 0 .. 98304"); s->sigma_stage_bytes = (int)value; }
     else if (k == "real_amplitudes") s->real_amplitudes = (int)value;
     else if (k == "csweep_adj_threads") s->csweep_adj_threads = (int)value;
     else if (k == "sigma_ab") s->sigma_ab = (int)value;

@@ -54,6 +54,9 @@ CASES = [
     (6, 6, "lex", {"tile_bits": 9, "grad_tile_bits": 8, "real_amplitudes": 0}),      # complex compact storage (default here: real)
     (8, 8, "blocked", {"real_amplitudes": 0, "sigma_split": 0}),
     (8, 8, "blocked", {"sigma_split": 8, "csweep_adj_threads": 128}),
+    (8, 8, "blocked", {"sigma_stage_bytes": 1200}),                                # K2 stages two source rows at a time
+    (8, 8, "lex", {"sigma_stage_bytes": 600, "real_amplitudes": 0}),               # complex: 1120-byte rows do not fit: unstaged
+    (8, 8, "lex", {"sigma_stage_bytes": 600, "sigma_stage_one": 1}),               # ... one 560-byte row at a time
     (6, 4, "blocked", {"tile_bits": 8, "grad_tile_bits": 8, "csweep_adj_threads": 32}),   # real rows starting on odd columns, one warp per tile
     (4, 4, "blocked", {"compact": 0}),
     (4, 4, "lex", {"mode": 0}),                                  # one factor per pass
