@@ -495,9 +495,12 @@ def run_ours(args):
             cpu = {"value": None, "unit": "evals/s", "cores": 0, "kind": "port", "sample": "reported at N=1 only" if world > 1 else "skipped (--quick)"}
         else:
             try:
-                dt, cores, e_cpu, g_cpu, ph_cpu = cpu_full_evaluation(table, factors, theta)
+                # two full evaluations, the faster one counts (the first pays the page faults of the port's buffers
+                # and the OpenMP thread start-up; `--impl reference` does the same with its warm-up step)
+                runs = [cpu_full_evaluation(table, factors, theta) for _ in range(2)]
+                dt, cores, e_cpu, g_cpu, ph_cpu = min(runs, key=lambda r: r[0])
                 cpu = {"value": 1.0 / dt, "unit": "evals/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE,
-                       "seconds": dt, "phase_s": {"forward": ph_cpu[0], "hamiltonian": ph_cpu[1], "reverse": ph_cpu[2]},
+                       "seconds": dt, "seconds_all_runs": [r[0] for r in runs], "phase_s": {"forward": ph_cpu[0], "hamiltonian": ph_cpu[1], "reverse": ph_cpu[2]},
                        "gpu_vs_cpu_dE": abs(e_cpu - e_ref), "gpu_vs_cpu_max_dg": float(np.abs(g_cpu - g_ref).max()),
                        "dense_sweep_variant": cpu_dense_sample(table, factors, theta)}
             except Exception as exc:  # the checker could not be built on this box
