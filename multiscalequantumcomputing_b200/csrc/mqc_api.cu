@@ -1384,7 +1384,7 @@ int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value) {
     if (!s || !key) throw MqcError("null argument");
     // options that shape the schedules, layouts, plans and uploaded tables are frozen by mqc_set_ansatz
     static const char* frozen[] = {"tile_bits", "low_bits", "grad_tile_bits", "mode", "sector", "sparse_tiles", "sp2", "compact",
-                                   "sigma_blocked", "csweep_snake", nullptr};
+                                   "sigma_blocked", "csweep_snake", "real_amplitudes", nullptr};
     if (s->have_ansatz)
         for (const char** f = frozen; *f; ++f)
             if (std::string(key) == *f)

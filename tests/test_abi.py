@@ -68,9 +68,23 @@ def test_schedule_options_are_frozen_by_set_ansatz():
     h = _lib.Handle(8)
     h.set_option("tile_bits", 6)
     h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
-    for key in ("mode", "sector", "sparse_tiles", "sp2", "tile_bits", "grad_tile_bits", "low_bits", "compact"):
+    assert h.amplitude_bytes() == 8            # real compact storage is decided by mqc_set_ansatz (no Hamiltonian yet: real)
+    for key in ("mode", "sector", "sparse_tiles", "sp2", "tile_bits", "grad_tile_bits", "low_bits", "compact", "real_amplitudes"):
         with pytest.raises(_lib.MqcError):
             h.set_option(key, 0 if key != "tile_bits" else 7)
     h.set_option("csweep_threads", 64)
+    h.set_option("csweep_adj_threads", 32)
     h.set_option("sigma_stage", 0)
+    h.set_option("sigma_split", 0)
+    h.close()
+    # the storage form is a set_ansatz-time choice: option, and the dense register for non-conserving / compact = 0
+    h = _lib.Handle(8)
+    h.set_option("real_amplitudes", 0)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    assert h.amplitude_bytes() == 16
+    h.close()
+    h = _lib.Handle(8)
+    h.set_option("compact", 0)
+    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+    assert h.amplitude_bytes() == 0
     h.close()

@@ -23,20 +23,28 @@ EMPTY = (np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.complex1
     (8, 8, 10, "blocked", 0),
 ])
 def test_cplan_reproduces_oracle_state(n, ne, kb, order, which):
+    """Both layouts of the class programs: 8-byte amplitudes (even row stride with spare slots, sixteen-lane bank
+    order; the default) and 16-byte amplitudes (odd row stride)."""
     F = uccsd_factors(n, ne, order)
-    h = _lib.Handle(2 * n)
-    h.set_option("tile_bits", kb)
-    h.set_option("grad_tile_bits", kb)
-    h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
-    info = h.cplan_info(which)
-    assert info["n_passes"] == len(h.schedule(which)["passes"])
-    from math import comb
-    assert (info["n_rows"], info["n_cols"]) == (comb(n, ne // 2), comb(n, ne - ne // 2))
     th = np.random.default_rng(5).normal(0, 0.2, F.n_theta)
-    psi = h.cplan_host_state(th, which)
     ref = UCCSDOracle(2 * n, F.as_tuples(), F.theta_index, F.ref_index, EMPTY).state(th)
-    assert abs(psi - ref).max() < 1e-14
-    h.close()
+    smem = {}
+    for real in (1, 0):
+        h = _lib.Handle(2 * n)
+        h.set_option("tile_bits", kb)
+        h.set_option("grad_tile_bits", kb)
+        h.set_option("real_amplitudes", real)
+        h.set_ansatz(F.kind, F.idx, F.theta_index, F.n_theta, F.ref_index)
+        assert h.amplitude_bytes() == (8 if real else 16)
+        info = h.cplan_info(which)
+        assert info["n_passes"] == len(h.schedule(which)["passes"])
+        from math import comb
+        assert (info["n_rows"], info["n_cols"]) == (comb(n, ne // 2), comb(n, ne - ne // 2))
+        psi = h.cplan_host_state(th, which)
+        assert abs(psi - ref).max() < 1e-14
+        smem[real] = info["smem_adjoint"]
+        h.close()
+    assert smem[1] <= smem[0]
 
 
 def test_cplan_generalized_factors_and_tied_parameters():
