@@ -139,6 +139,9 @@ __device__ __forceinline__ double mqc_rotate_pair2(double* __restrict__ sp, doub
     return g;
 }
 
+#ifndef MQC_CS_FWD_UNROLL
+#define MQC_CS_FWD_UNROLL 2
+#endif
 template <bool REAL> struct MqcAmp { typedef double2 T; };
 template <> struct MqcAmp<true> { typedef double T; };
 
@@ -269,10 +272,11 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
             uint2 hc = shdr[step(0)];
             wait_chunks((hc.y >> WSH) & 3u);
             uint32_t wc = ring[(hc.x + (uint32_t)tid) & RMASK];
-            for (int i0 = 0; i0 < n_live; i0 += 8) {
+            constexpr int UN = ADJ ? 8 : MQC_CS_FWD_UNROLL;            // the adjoint reduces the partials of eight steps together
+            for (int i0 = 0; i0 < n_live; i0 += UN) {
                 double acc8[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < UN; ++j) {
                     acc8[j] = 0.0;
                     const int i = i0 + j;
                     if (i < n_live) {                                   // uniform over the CTA
