@@ -184,6 +184,24 @@ def test_real_and_complex_storage_selection():
     assert abs(e2 - e2_ref) < E_TOL and abs(g2 - g2_ref).max() < G_TOL
     assert abs(h.state(th) - orc2.state(th)).max() < S_TOL
     h.close()
+    # real Hamiltonians with extra terms: X0 Z1 Z2 X4 (the JW string misses qubit 3: still a link-table group, stays
+    # real) and a six-qubit flip X0 X2 X4 X6 X8 X10 (three-body: only the X-group kernel takes it, which works on
+    # complex amplitudes: decided when the tables are built, at the first evaluation)
+    for xs, zs2, want in ((bit(0) | bit(4), bit(1) | bit(2), 8),
+                          (bit(0) | bit(2) | bit(4) | bit(6) | bit(8) | bit(10), np.uint64(0), 16)):
+        h, orc, F, tab, th = _setup(6, 6, "blocked", {"tile_bits": 8, "grad_tile_bits": 8})
+        x3 = np.concatenate([tab[0], [xs]]).astype(np.uint64)
+        z3 = np.concatenate([tab[1], [zs2]]).astype(np.uint64)
+        c3 = np.concatenate([tab[2], [0.2]])
+        h.set_hamiltonian(x3, z3, c3)
+        assert h.amplitude_bytes() == 8
+        orc3 = UCCSDOracle(n, F.as_tuples(), F.theta_index, F.ref_index, (x3, z3, c3))
+        e3_ref, g3_ref = orc3.energy_grad(th)
+        e3, g3 = h.energy_grad(th)
+        assert abs(e3 - e3_ref) < E_TOL and abs(g3 - g3_ref).max() < G_TOL
+        assert abs(e3 - e_ref) > 1e-6                      # the extra term does contribute
+        assert h.amplitude_bytes() == want
+        h.close()
     # option; odd number of columns
     h, orc, F, tab, th = _setup(6, 6, "blocked", {"real_amplitudes": 0})
     assert h.amplitude_bytes() == 16
