@@ -181,7 +181,7 @@ static inline size_t mqc_c_smem_bytes(const MqcCPassDev& P, bool adj, int n_warp
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
     size_t b = 0;
     b += (size_t)(adj ? 2 : 1) * al((size_t)P.capA * P.strideB * elem);
-    b += al((size_t)P.max_live * 8);              // class program headers
+    b += al(((size_t)P.max_live + 9) * 8);        // class program headers + sentinel slots
     b += (size_t)MQC_C_RING_SLOTS * chunk * 4;    // pair-word ring
     b += (size_t)P.nf * 16;                       // cos / sin
     b += al((size_t)P.nf);                        // per-tile factor signs

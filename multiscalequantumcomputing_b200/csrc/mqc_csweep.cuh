@@ -139,6 +139,27 @@ __device__ __forceinline__ double mqc_rotate_pair2(double* __restrict__ sp, doub
     return g;
 }
 
+// transposed butterfly: eight per-lane partials -> one total per lane group (9 double shuffles instead of 40);
+// lane L with (L & 3) == 0 ends up with the total of step j = 4 * bit4(L) + 2 * bit3(L) + bit2(L) in OUT
+#define MQC_CS_BUTTERFLY(ACC, LANE, OUT) \
+    double OUT; \
+    { \
+        double w4_[4], w2_[2]; \
+        { const bool hi_ = ((LANE) & 16) != 0; \
+          _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) { \
+              const double send_ = hi_ ? ACC[j_] : ACC[j_ + 4], keep_ = hi_ ? ACC[j_ + 4] : ACC[j_]; \
+              w4_[j_] = keep_ + __shfl_xor_sync(0xffffffffu, send_, 16); } } \
+        { const bool hi_ = ((LANE) & 8) != 0; \
+          _Pragma("unroll") for (int j_ = 0; j_ < 2; ++j_) { \
+              const double send_ = hi_ ? w4_[j_] : w4_[j_ + 2], keep_ = hi_ ? w4_[j_ + 2] : w4_[j_]; \
+              w2_[j_] = keep_ + __shfl_xor_sync(0xffffffffu, send_, 8); } } \
+        { const bool hi_ = ((LANE) & 4) != 0; \
+          const double send_ = hi_ ? w2_[0] : w2_[1], keep_ = hi_ ? w2_[1] : w2_[0]; \
+          OUT = keep_ + __shfl_xor_sync(0xffffffffu, send_, 4); } \
+        OUT += __shfl_xor_sync(0xffffffffu, OUT, 2); \
+        OUT += __shfl_xor_sync(0xffffffffu, OUT, 1); \
+    }
+
 #ifndef MQC_CS_FWD_UNROLL
 #define MQC_CS_FWD_UNROLL 2
 #endif
@@ -165,7 +186,7 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
     const size_t tile_bytes = ((size_t)capA * strideB * ES + 15) & ~(size_t)15;
     AT* sp0 = reinterpret_cast<AT*>(q);                       q += tile_bytes;
     AT* sl0 = reinterpret_cast<AT*>(q);                       if (ADJ) q += tile_bytes;
-    uint2* shdr = reinterpret_cast<uint2*>(q);                q += ((size_t)P->max_live * 8 + 15) & ~(size_t)15;
+    uint2* shdr = reinterpret_cast<uint2*>(q) + 8;            q += (((size_t)P->max_live + 9) * 8 + 15) & ~(size_t)15;   // [-8 .. -1] and [n_live]: empty sentinel steps
     uint32_t* ring = reinterpret_cast<uint32_t*>(q);          q += (size_t)MQC_C_RING_SLOTS * CH * 4;
     double2* hcs = reinterpret_cast<double2*>(q);             q += (size_t)nf * 16;
     unsigned char* hsg = q;                                   q += ((size_t)nf + 15) & ~(size_t)15;
@@ -259,6 +280,8 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
             }
             mqc_cp_async_wait_all();
         }
+        if (ADJ) { if (tid < 8) shdr[-1 - tid] = make_uint2(0u, 0u); }
+        else if (tid == 0 && !(n_live & 1)) shdr[n_live] = make_uint2(0u, 0u);   // odd n_live: the bulk copy brings the list's zero pad entry
         mqc_mbar_wait(bar, phase);
         phase ^= 1u;
         __syncthreads();
@@ -266,7 +289,87 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
         // ---- factors: step i of the class program = header (first word, pairs | factor << 16) + its
         //      pair words in the ring; the thread's first word of step i + 1 is read before the barrier
         //      that ends step i, so between two barriers a thread only rotates ----------------------------
-        if (n_live > 0) {
+        if (!ADJ && REAL && n_live > 0) {
+            // forward sweep, lean step loop: the header after the last step is an empty sentinel (no pairs, no
+            // flags), waits and refills sit behind one uniform flag test each
+            uint2 hc = shdr[0];
+            wait_chunks((hc.y >> 23) & 3u);
+            uint32_t wc = ring[(hc.x + (uint32_t)tid) & RMASK];
+            const uint2* ph = shdr + 1;
+#pragma unroll 1
+            for (int i = n_live; i > 0; --i, ++ph) {
+                const uint2 hn = *ph;
+                const uint32_t npairs = MQC_C_NP(hc.y);
+                if (hn.y & (3u << 23)) wait_chunks((hn.y >> 23) & 3u);
+                if ((uint32_t)(warp * 32) < npairs) {
+                    const double2 csv = hcs[MQC_C_F(hc.y)];
+                    uint32_t u = (uint32_t)tid;
+                    uint32_t w0 = wc;
+                    for (; u + NT < npairs; u += 2 * NT) {
+                        mqc_rotate_pair2<false>(reinterpret_cast<double*>(sp), reinterpret_cast<double*>(sl), w0,
+                                                ring[(hc.x + u + NT) & RMASK], csv.x, csv.y);
+                        w0 = ring[(hc.x + u + 2 * NT) & RMASK];
+                    }
+                    if (u < npairs) mqc_rotate_pair<false>(sp, sl, w0, csv.x, csv.y);
+                }
+                const uint32_t wn = ring[(hn.x + (uint32_t)tid) & RMASK];
+                if (NT == 32) __syncwarp(); else __syncthreads();
+                if (hc.y & (3u << 27)) {                                // uniform: some ring slots are free now
+                    if (tid == 0) {
+                        mqc_fence_async();
+                        for (uint32_t cnt_is = (hc.y >> 27) & 3u; cnt_is; --cnt_is) issue_chunk(issued++);
+                    }
+                }
+                hc = hn; wc = wn;
+            }
+        } else if (ADJ && REAL && n_live > 0) {
+            // adjoint sweep, same lean loop in groups of eight steps (the gradient partials of a group are reduced
+            // together); the group may run past the first step into the empty sentinel headers below it
+            const uint2* ph = shdr + (n_live - 1);
+            uint2 hc = *ph;
+            wait_chunks((hc.y >> 25) & 3u);
+            uint32_t wc = ring[(hc.x + (uint32_t)tid) & RMASK];
+#pragma unroll 1
+            for (int i0 = 0; i0 < n_live; i0 += 8) {
+                const uint2* pg = ph;                                   // header of step i0 (adjoint order: descending)
+                double acc8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    --ph;
+                    const uint2 hn = *ph;
+                    const uint32_t npairs = MQC_C_NP(hc.y);
+                    if (hn.y & (3u << 25)) wait_chunks((hn.y >> 25) & 3u);
+                    double gacc = 0.0;
+                    if ((uint32_t)(warp * 32) < npairs) {
+                        const double2 csv = hcs[MQC_C_F(hc.y)];
+                        uint32_t u = (uint32_t)tid;
+                        uint32_t w0 = wc;
+                        for (; u + NT < npairs; u += 2 * NT) {
+                            gacc += mqc_rotate_pair2<true>(reinterpret_cast<double*>(sp), reinterpret_cast<double*>(sl), w0,
+                                                           ring[(hc.x + u + NT) & RMASK], csv.x, csv.y);
+                            w0 = ring[(hc.x + u + 2 * NT) & RMASK];
+                        }
+                        if (u < npairs) gacc += mqc_rotate_pair<true>(sp, sl, w0, csv.x, csv.y);
+                    }
+                    const uint32_t wn = ring[(hn.x + (uint32_t)tid) & RMASK];
+                    acc8[j] = gacc;
+                    if (NT == 32) __syncwarp(); else __syncthreads();
+                    if (hc.y & (3u << 29)) {
+                        if (tid == 0) {
+                            mqc_fence_async();
+                            for (uint32_t cnt_is = (hc.y >> 29) & 3u; cnt_is; --cnt_is) issue_chunk(issued++);
+                        }
+                    }
+                    hc = hn; wc = wn;
+                }
+                MQC_CS_BUTTERFLY(acc8, lane, w1r)
+                const int j = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                if ((lane & 3) == 0 && i0 + j < n_live && w1r != 0.0) {
+                    const int f = (int)MQC_C_F(pg[-j].y);
+                    gw[(size_t)warp * gw_stride + f] += hsg[f] ? -w1r : w1r;
+                }
+            }
+        } else if (n_live > 0) {
             auto step = [&](int i) -> int { return ADJ ? n_live - 1 - i : i; };
             constexpr int WSH = ADJ ? 25 : 23, ISH = ADJ ? 29 : 27;
             uint2 hc = shdr[step(0)];
@@ -319,33 +422,7 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
                     }
                 }
                 if (ADJ) {
-                    // transposed butterfly: eight per-lane partials -> one total per lane group
-                    // (9 double shuffles instead of 40); lane L with (L & 3) == 0 ends up with
-                    // the total of factor j = 4 * bit4(L) + 2 * bit3(L) + bit2(L)
-                    double w4[4], w2r[2], w1r;
-                    {
-                        const bool hi = (lane & 16) != 0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const double send = hi ? acc8[j] : acc8[j + 4], keep = hi ? acc8[j + 4] : acc8[j];
-                            w4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                        }
-                    }
-                    {
-                        const bool hi = (lane & 8) != 0;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const double send = hi ? w4[j] : w4[j + 2], keep = hi ? w4[j + 2] : w4[j];
-                            w2r[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                        }
-                    }
-                    {
-                        const bool hi = (lane & 4) != 0;
-                        const double send = hi ? w2r[0] : w2r[1], keep = hi ? w2r[1] : w2r[0];
-                        w1r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    w1r += __shfl_xor_sync(0xffffffffu, w1r, 2);
-                    w1r += __shfl_xor_sync(0xffffffffu, w1r, 1);
+                    MQC_CS_BUTTERFLY(acc8, lane, w1r)
                     const int j = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
                     if ((lane & 3) == 0 && i0 + j < n_live && w1r != 0.0) {
                         const int f = (int)MQC_C_F(shdr[step(i0 + j)].y);
