@@ -7,12 +7,14 @@
 //                    gradient partials: gather through the maps (cp.async), factors, rows
 //                    leave by bulk copies shared -> global.
 //
-// One CTA owns a tile (persistent over the pass's tile list, heaviest first).  The tile's class
-// program (mqc_cplan.h) tells every thread which pair of slots to rotate for each live factor:
-// the program headers arrive with the same mbarrier transaction as the rows, the 32-bit pair
-// words are fetched coalesced from L2 three factors ahead, so that between two barriers a
-// thread only reads its two amplitudes, rotates and writes them back.  Algorithmic bytes per launch: 2 * 16 * N_det (forward),
-// 4 * 16 * N_det (adjoint) - the state is read once and written once, nothing else is touched.
+// One CTA owns a tile (one CTA per tile, or persistent over the pass's tile list, heaviest first).  The
+// tile's class program (mqc_cplan.h) tells every thread which pair of slots to rotate for each live
+// factor: the program headers arrive with the same mbarrier transaction as the rows, the 32-bit pair
+// words stream through a shared-memory ring of four chunks that thread 0 refills with further bulk
+// copies, so that between two barriers a thread only reads its two amplitudes, rotates and writes them
+// back.  Amplitudes are complex (16 bytes) or, template parameter REAL, real (8 bytes: real Hamiltonian,
+// DESIGN.md section 2).  Algorithmic bytes per launch: 2 * b * N_det (forward), 4 * b * N_det (adjoint),
+// b = bytes per amplitude - the state is read once and written once, nothing else is touched.
 #pragma once
 #include <cuda_runtime.h>
 
