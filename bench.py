@@ -160,7 +160,8 @@ def cpu_dense_sample(table, factors, theta, n_fac=16, n_terms=600):
 
 
 CPU_SAMPLE = ("one FULL evaluation per step (not extrapolated): sector-aware C/OpenMP port, forward sweep over all 1818 "
-              "factors, H|psi> over all 15169 Pauli terms, adjoint reverse sweep; determinants of the (6,6) sector only")
+              "factors, H|psi> over all 15169 Pauli terms, adjoint reverse sweep; determinants of the (6,6) sector only; "
+              "complex128 amplitudes as in the reference's libraries (the CUDA path stores this real problem in 8-byte amplitudes)")
 
 
 def run_reference(args):
