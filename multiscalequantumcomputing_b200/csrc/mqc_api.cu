@@ -185,6 +185,8 @@ struct mqc_solver {
     // compact sector storage (mqc_cplan.h): the state is the matrix C[alpha string][beta string];
     // cpsi / clam ping-pong between the layouts of consecutive passes
     int compact = 1, csweep_threads = 128, csweep_ctas = 0, csweep_snake = 1;
+    int csweep_pdl = 0;              // programmatic dependent launch of the sweep passes: measured slower (0.71 / 1.30 -> 0.86 / 1.49 ms:
+                                     // the early CTAs land on whichever SMs drain first and the next pass is unbalanced), kept as an option
     int csweep_adj_threads = 0;      // threads per tile of the adjoint sweep; 0: 64 with real amplitudes (measured), else csweep_threads
     bool use_compact = false;
     // Real amplitudes: every ansatz factor is a real rotation, so with a real Hamiltonian (even number of Y per
@@ -827,9 +829,18 @@ static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     unsigned grid = (unsigned)std::min<u64>(P.n_tiles, std::max<u64>((u64)s->n_sm * per_sm, 2048));
     if (s->csweep_ctas > 0) grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->csweep_ctas);
     CK(cudaSetDevice(s->device));
+    // programmatic dependent launch: the CTAs of this pass may start (and set up their tables) while the previous
+    // kernel of the stream drains; k_csweep waits (griddepcontrol.wait) before it touches the state
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = smem; cfg.stream = s->stream;
+    cfg.attrs = pdl_attr; cfg.numAttrs = s->csweep_pdl ? 1 : 0;
+#define MQC_CS_LAUNCH3(ADJ_, NT_, CH_, REAL_) do { cfg.blockDim = dim3(NT_); CK(cudaLaunchKernelEx(&cfg, k_csweep<ADJ_, NT_, CH_, REAL_>, A)); } while (0)
 #define MQC_CS_LAUNCH2(NT_, CH_) do { \
-        if (real) { if (adj) k_csweep<true, NT_, CH_, true><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_, CH_, true><<<grid, NT_, smem, s->stream>>>(A); } \
-        else { if (adj) k_csweep<true, NT_, CH_, false><<<grid, NT_, smem, s->stream>>>(A); else k_csweep<false, NT_, CH_, false><<<grid, NT_, smem, s->stream>>>(A); } } while (0)
+        if (real) { if (adj) MQC_CS_LAUNCH3(true, NT_, CH_, true); else MQC_CS_LAUNCH3(false, NT_, CH_, true); } \
+        else { if (adj) MQC_CS_LAUNCH3(true, NT_, CH_, false); else MQC_CS_LAUNCH3(false, NT_, CH_, false); } } while (0)
 #define MQC_CS_LAUNCH(NT_) do { if (PL.chunk == 256) MQC_CS_LAUNCH2(NT_, 256); else MQC_CS_LAUNCH2(NT_, 1024); } while (0)
     if (nt >= 512) MQC_CS_LAUNCH(512); else if (nt >= 256) MQC_CS_LAUNCH(256); else if (nt >= 128) MQC_CS_LAUNCH(128);
     else if (nt >= 64) MQC_CS_LAUNCH(64); else MQC_CS_LAUNCH(32);
@@ -1356,6 +1367,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "sigma_stage_bytes") { if (value < 0 || value > 98304) throw MqcError("sigma_stage_bytes must be 0 .. 98304"); s->sigma_stage_bytes = (int)value; }
     else if (k == "real_amplitudes") s->real_amplitudes = (int)value;
     else if (k == "csweep_adj_threads") s->csweep_adj_threads = (int)value;
+    else if (k == "csweep_pdl") s->csweep_pdl = (int)value;
     else if (k == "sigma_ab") s->sigma_ab = (int)value;
     else if (k == "graph") s->use_graph = (int)value;
     else if (k == "sigma_blocked") s->sigma_blocked = (int)value;

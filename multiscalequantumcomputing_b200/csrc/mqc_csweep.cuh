@@ -73,6 +73,8 @@ __device__ __forceinline__ void mqc_cp_async8(void* smem_dst, const void* gsrc) 
 }
 __device__ __forceinline__ void mqc_cp_async_amp(double2* d, const double2* g) { mqc_cp_async16(d, g); }
 __device__ __forceinline__ void mqc_cp_async_amp(double* d, const double* g) { mqc_cp_async8(d, g); }
+// no-op unless the kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization
+__device__ __forceinline__ void mqc_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void mqc_cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 // one pair rotation on psi (and lambda, with the gradient partial): w = slot0 | slot1 << 14 | parity << 28
@@ -199,6 +201,10 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
     uint64_t* rbar = bar + 1;
     constexpr uint32_t RMASK = MQC_C_RING_SLOTS * CH - 1;
 
+    // Programmatic dependent launch (the host launches the passes of a sweep with the attribute): the next pass may
+    // start its CTAs as soon as SM resources free up and set up everything that does not depend on the state (program
+    // headers, pair-word ring, cos / sin table, maps); it reads the state only after mqc_grid_dependency_wait().
+    asm volatile("griddepcontrol.launch_dependents;");
     if (tid == 0) {
         for (int i = 0; i <= MQC_C_RING_SLOTS; ++i) mqc_mbar_init(bar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -255,6 +261,7 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
             __syncwarp();
             if (lane == 31 && bH) mqc_bulk_g2s(shdr, A.prog_hdr + lt4.x, bH, bar);
             if (lane == 0) { for (; issued < NC && issued < MQC_C_RING_SLOTS; ++issued) issue_chunk(issued); }
+            if (!ADJ) mqc_grid_dependency_wait();               // the previous pass (or whatever wrote psi_in) is complete
             if (!ADJ)
                 for (int ja = lane; ja < nAl; ja += 32)
                     mqc_bulk_g2s(sp0 + (size_t)ja * strideB, static_cast<const AT*>(A.psi_in) + (size_t)(row0 + ja) * nB + col0 - shift,
@@ -274,6 +281,7 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
                               : (P->col_identity ? col0 + (i - nAl) : __ldg(A.maps + P->map_col_off + col0 + (i - nAl)));
         if (ADJ) {
             __syncthreads();
+            mqc_grid_dependency_wait();
             for (int e = tid; e < cnt; e += NT) {
                 const int ja = (nBl == 1) ? e : (int)__umulhi((uint32_t)e, magicB), jb = e - ja * nBl;
                 const size_t g = (size_t)smap[ja] * nB + smap[nAl + jb];
