@@ -569,9 +569,10 @@ def test_update_hamiltonian_coeffs_and_handle_cache():
     assert S.STATS["handle_reuses"] == run.n_solves - len(cl) and S.STATS["handle_reuses"] > 0
     ref = DMETRun(ints, cl, solver=lambda *a: solve(*a))
     e_ref = ref.run()
-    # re-used handles run the same arithmetic as fresh ones; two FRESH runs already differ by a few 1e-9 (the
-    # order of the gradient atomics is not fixed, the chemical-potential secant search amplifies the last digits)
-    assert abs(e_cached - e_ref) < 2e-8
+    # re-used handles run the same arithmetic as fresh ones; two FRESH runs of a five-fragment chain already differ by
+    # up to 2.5e-8 (8 runs, H10 chain: the order of the gradient atomics is not fixed, BFGS stops at gtol-different
+    # points and the chemical-potential secant search, tolerance 1e-8 on mu, amplifies the last digits)
+    assert abs(e_cached - e_ref) < 1e-7
     # with the per-fragment warm start the optimiser stops at a (gtol-)different point of the same minimum
     warm = DMETRun(ints, cl, batch_solver=lambda ps: solve_fragments(ps, devices=[0], fragment_ids=True))
     assert abs(warm.run() - e_ref) < 1e-6
