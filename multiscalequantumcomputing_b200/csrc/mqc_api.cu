@@ -185,6 +185,16 @@ struct mqc_solver {
     // compact sector storage (mqc_cplan.h): the state is the matrix C[alpha string][beta string];
     // cpsi / clam ping-pong between the layouts of consecutive passes
     int compact = 1, csweep_threads = 128, csweep_ctas = 0, csweep_snake = 1;
+    // Reproducible sums (default): the adjoint sweep leaves per-(CTA, factor) gradient partials that are added in a fixed
+    // order, K2 adds its per-CTA energy partials in a fixed order - two evaluations with the same input give the same
+    // bits, so an optimiser or a chemical-potential search on top takes the same path every time.  0: atomics.
+    int deterministic = 1;
+    DevBuf<double> cgpart, e_part;
+    DevBuf<uint4> cgwhere;
+    DevBuf<int> th_ptr, th_fac;      // factors of every parameter (CSR, factor order)
+    DevBuf<unsigned> e_ticket;
+    std::vector<size_t> gp_off;
+    bool gpart_ready = false;
     int csweep_pdl = 0;              // programmatic dependent launch of the sweep passes: measured slower (0.71 / 1.30 -> 0.86 / 1.49 ms:
                                      // the early CTAs land on whichever SMs drain first and the next pass is unbalanced), kept as an option
     int csweep_adj_threads = 0;      // threads per tile of the adjoint sweep; 0: 64 with real amplitudes (measured), else csweep_threads
@@ -665,6 +675,7 @@ static void ensure_layout_ready(mqc_solver* s, int which) {
 // ranks wherever one reads or writes another's shard.
 // ---------------------------------------------------------------------------------------
 static void invalidate_graphs(mqc_solver* s) {
+    s->gpart_ready = false;          // grids of the adjoint passes may change with the options / plans
     for (int w = 0; w < 2; ++w) {
         if (s->gexec[w]) { cudaGraphExecDestroy(s->gexec[w]); s->gexec[w] = nullptr; }
         s->eager_done[w] = 0;
@@ -804,6 +815,49 @@ static void launch_tile(mqc_solver* s, int which, int pass, bool adj, int revers
 }
 
 // ---- compact sector storage: one launch per pass over the matrix C[alpha][beta] ---------------
+static void csweep_dims(const mqc_solver* s, int which, int pass, bool adj, int& nt, unsigned& grid, size_t& smem) {
+    const MqcCPlan& PL = s->cplan[which];
+    const MqcCPassDev& P = PL.pass[pass];
+    nt = s->csweep_threads;
+    if (adj) nt = s->csweep_adj_threads > 0 ? s->csweep_adj_threads : (s->creal ? std::min(64, s->csweep_threads) : s->csweep_threads);
+    // small tiles do not feed many threads: most factor visits of a tile couple <= capA * capB / 4 pairs
+    while (nt > 128 && P.capA * P.capB < 2 * nt) nt >>= 1;
+    smem = mqc_c_smem_bytes(P, adj, nt / 32, PL.chunk, PL.elem);
+    if (smem > 232448) throw MqcError("compact tile does not fit shared memory");
+    int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / (smem + 1024));
+    per_sm = std::max(1, std::min(per_sm, std::min(32, 2048 / nt)));
+    // a few thousand tiles: one CTA per tile, the hardware deals them out as SM slots free up (measured 1-3 % better
+    // than persistent CTAs striding over the list); more: persistent CTAs (one gradient flush per CTA, not per tile)
+    grid = (unsigned)std::min<u64>(P.n_tiles, std::max<u64>((u64)s->n_sm * per_sm, 2048));
+    if (s->csweep_ctas > 0) grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->csweep_ctas);
+}
+// per-(CTA, factor) gradient partials of the adjoint passes of schedule 1 and where k_grad_combine_parts finds them
+static void ensure_gpart(mqc_solver* s) {
+    if (s->gpart_ready || !s->deterministic) return;
+    const MqcCPlan& PL = s->cplan[1];
+    const int np = (int)PL.pass.size();
+    const size_t nfac = s->fac.size();
+    std::vector<uint4> where(std::max<size_t>(1, nfac), make_uint4(0u, 0u, 1u, 0u));
+    s->gp_off.assign(std::max(1, np), 0);
+    size_t total = 0;
+    for (int p = 0; p < np; ++p) {
+        int nt; unsigned grid; size_t smem;
+        csweep_dims(s, 1, p, true, nt, grid, smem);
+        const MqcCPassDev& P = PL.pass[p];
+        s->gp_off[p] = total;
+        for (int f = 0; f < P.nf; ++f) {
+            const size_t slot = (size_t)(PL.fac[P.fac_off + f].theta_sign & 0x7fffffff);
+            const unsigned long long o = total + (size_t)f;
+            if (slot < nfac) where[slot] = make_uint4((unsigned)(o & 0xffffffffull), (unsigned)(o >> 32), (unsigned)P.nf, grid);
+        }
+        total += (size_t)grid * P.nf;
+    }
+    CK(cudaSetDevice(s->device));
+    if (s->cgpart.n < std::max<size_t>(1, total)) s->cgpart.alloc(std::max<size_t>(1, total));
+    s->cgwhere.upload(where, s->stream);
+    CK(cudaStreamSynchronize(s->stream));
+    s->gpart_ready = true;
+}
 static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     const MqcCPlan& PL = s->cplan[which];
     const MqcCPassDev& P = PL.pass[pass];
@@ -815,19 +869,13 @@ static void launch_csweep(mqc_solver* s, int which, int pass, bool adj) {
     A.lam_in = adj ? (const void*)s->clam[s->clcur].p : nullptr; A.lam_out = adj ? (void*)s->clam[s->clcur ^ 1].p : nullptr;
     A.grad = adj ? s->grad_p() : nullptr;
     A.nB = PL.pitch;                                   // the kernel only uses it as the row pitch
-    int nt = s->csweep_threads;
-    if (adj) nt = s->csweep_adj_threads > 0 ? s->csweep_adj_threads : (s->creal ? std::min(64, s->csweep_threads) : s->csweep_threads);
-    // small tiles do not feed many threads: most factor visits of a tile couple <= capA * capB / 4 pairs
-    while (nt > 128 && P.capA * P.capB < 2 * nt) nt >>= 1;
-    const size_t smem = mqc_c_smem_bytes(P, adj, nt / 32, PL.chunk, PL.elem);
-    if (smem > 232448) throw MqcError("compact tile does not fit shared memory");
+    int nt; unsigned grid; size_t smem;
+    csweep_dims(s, which, pass, adj, nt, grid, smem);
     const bool real = s->creal;
-    int per_sm = (int)std::min<size_t>(32, (size_t)(227 * 1024) / (smem + 1024));
-    per_sm = std::max(1, std::min(per_sm, std::min(32, 2048 / nt)));
-    // a few thousand tiles: one CTA per tile, the hardware deals them out as SM slots free up (measured 1-3 % better
-    // than persistent CTAs striding over the list); more: persistent CTAs (one gradient flush per CTA, not per tile)
-    unsigned grid = (unsigned)std::min<u64>(P.n_tiles, std::max<u64>((u64)s->n_sm * per_sm, 2048));
-    if (s->csweep_ctas > 0) grid = (unsigned)std::min<u64>(P.n_tiles, (u64)s->csweep_ctas);
+    if (adj && s->deterministic) {
+        if (!s->gpart_ready) throw MqcError("internal: gradient partial buffers are not set up");
+        A.gpart = s->cgpart.p + s->gp_off[pass];
+    }
     CK(cudaSetDevice(s->device));
     // programmatic dependent launch: the CTAs of this pass may start (and set up their tables) while the previous
     // kernel of the stream drains; k_csweep waits (griddepcontrol.wait) before it touches the state
@@ -967,6 +1015,13 @@ static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Co
             grid.z = 2;
             if (Lp) CK(cudaMemsetAsync(Lp, 0, (size_t)(r1 - r0) * D.pitch * elem, s->stream));
         }
+    }
+    D.e_part = nullptr; D.ticket = nullptr;
+    if (s->deterministic) {
+        const size_t ctas = (size_t)grid.x * grid.y * grid.z;
+        if (s->e_part.n < 2 * ctas) s->e_part.alloc(2 * ctas);
+        if (!s->e_ticket.p) { s->e_ticket.alloc(1); CK(cudaMemsetAsync(s->e_ticket.p, 0, sizeof(unsigned), s->stream)); }
+        D.e_part = s->e_part.p; D.ticket = s->e_ticket.p;
     }
 #define MQC_SG_LAUNCH(LB_) do { \
         if (real) k_sigma<true, LB_, true><<<grid, MQC_SG_THREADS, smem, s->stream>>>(reinterpret_cast<const double*>(Cown), \
@@ -1145,6 +1200,7 @@ static void reverse_sweep(mqc_solver* L, int which) {
     const int nfac = (int)L->fac.size();
     if (L->use_compact) {
         const int np = (int)L->cplan[which].pass.size();
+        ensure_gpart(L);
         for (int p = np - 1; p >= 0; --p) launch_csweep(L, which, p, true);
         L->counters[2] += np;
         L->cvalid = false;
@@ -1368,6 +1424,7 @@ static void set_option_rank(mqc_solver* s, const std::string& k, int64_t value) 
     else if (k == "real_amplitudes") s->real_amplitudes = (int)value;
     else if (k == "csweep_adj_threads") s->csweep_adj_threads = (int)value;
     else if (k == "csweep_pdl") s->csweep_pdl = (int)value;
+    else if (k == "deterministic") s->deterministic = (int)value;
     else if (k == "sigma_ab") s->sigma_ab = (int)value;
     else if (k == "graph") s->use_graph = (int)value;
     else if (k == "sigma_blocked") s->sigma_blocked = (int)value;
@@ -1618,6 +1675,15 @@ static void set_ansatz_rank(mqc_solver* s, int32_t n_factors, const int32_t* kin
         std::vector<int> ti(n_factors);
         for (int k = 0; k < n_factors; ++k) ti[k] = theta_index[k];
         s->theta_index.upload(ti.empty() ? std::vector<int>(1, 0) : ti, s->stream);
+        {
+            std::vector<int> ptr(std::max(1, n_theta) + 1, 0), lst(std::max(1, n_factors), 0);
+            for (int k = 0; k < n_factors; ++k) ptr[ti[k] + 1]++;
+            for (int t = 0; t < n_theta; ++t) ptr[t + 1] += ptr[t];
+            std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+            for (int k = 0; k < n_factors; ++k) lst[pos[ti[k]]++] = k;
+            s->th_ptr.upload(ptr, s->stream);
+            s->th_fac.upload(lst, s->stream);
+        }
         std::vector<double> sc(std::max(1, n_factors), 1.0);
         if (theta_scale) for (int k = 0; k < n_factors; ++k) sc[k] = theta_scale[k];
         s->theta_scale.upload(sc, s->stream);
@@ -1793,7 +1859,11 @@ static void evaluation_body(mqc_solver* s, int which, const double* theta) {
             CK(cudaSetDevice(s->device));
             CK(cudaMemsetAsync(s->gtheta.p, 0, sizeof(double) * std::max(1, s->n_theta), s->stream));
             const int nfac = (int)s->fac.size();
-            if (nfac) { k_grad_combine<<<(nfac + 255) / 256, 256, 0, s->stream>>>(reduced_grad(s), s->theta_index.p, s->theta_scale.p, s->gtheta.p, nfac); s->counters[0]++; }
+            if (nfac && s->use_compact && s->deterministic) {
+                k_grad_combine_parts<<<(unsigned)(((size_t)std::max(1, s->n_theta) * 32 + 255) / 256), 256, 0, s->stream>>>(
+                    s->cgpart.p, s->cgwhere.p, s->th_ptr.p, s->th_fac.p, s->theta_scale.p, s->gtheta.p, s->n_theta);
+                s->counters[0]++;
+            } else if (nfac) { k_grad_combine<<<(nfac + 255) / 256, 256, 0, s->stream>>>(reduced_grad(s), s->theta_index.p, s->theta_scale.p, s->gtheta.p, nfac); s->counters[0]++; }
         }
         record_ev(s, 3);
     }

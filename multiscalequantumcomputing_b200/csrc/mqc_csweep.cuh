@@ -36,6 +36,8 @@ struct MqcCArgs {
     const void* lam_in;
     void* lam_out;
     double* grad;
+    double* gpart;                   // [gridDim.x][nf] per-CTA gradient partials of this pass (summed in a fixed order
+                                     // by k_grad_combine_parts: reproducible gradients); NULL: atomics into grad
     uint32_t nB;
 };
 
@@ -481,7 +483,8 @@ k_csweep(const __grid_constant__ MqcCArgs A) {
             double g = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) g += gw[(size_t)w * gw_stride + f];
-            if (g != 0.0) atomicAdd(A.grad + (A.fac[P->fac_off + f].theta_sign & 0x7fffffff), 2.0 * g);
+            if (A.gpart) A.gpart[(size_t)blockIdx.x * nf + f] = 2.0 * g;
+            else if (g != 0.0) atomicAdd(A.grad + (A.fac[P->fac_off + f].theta_sign & 0x7fffffff), 2.0 * g);
         }
     }
 }

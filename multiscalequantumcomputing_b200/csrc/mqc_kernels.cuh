@@ -91,6 +91,28 @@ __global__ void k_grad_combine(const double* __restrict__ g_factor, const int* _
     }
 }
 
+// Reproducible variant: the adjoint sweep left one partial per (CTA, factor); a warp per PARAMETER walks the
+// parameter's factors (th_ptr / th_fac: CSR lists in factor order) and adds each factor's partials in a fixed order
+// (lane-strided, then a fixed shuffle tree): no atomics, the same bits every time, tied parameters included.
+// where[f] = {offset of the factor's first partial (lo, hi), stride between CTAs, number of CTAs}.
+__global__ void k_grad_combine_parts(const double* __restrict__ gpart, const uint4* __restrict__ where, const int* __restrict__ th_ptr,
+                                     const int* __restrict__ th_fac, const double* __restrict__ scale, double* __restrict__ g_theta, int n_theta) {
+    const int t = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= n_theta) return;
+    double gt = 0.0;
+    for (int i = th_ptr[t]; i < th_ptr[t + 1]; ++i) {
+        const int f = th_fac[i];
+        const uint4 w = where[f];
+        const double* __restrict__ src = gpart + (((unsigned long long)w.y << 32) | w.x);
+        double g = 0.0;
+        for (unsigned c = lane; c < w.w; c += 32) g += src[(size_t)c * w.z];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        gt += scale[f] * g;
+    }
+    if (lane == 0) g_theta[t] = gt;
+}
+
 __global__ void k_set_amplitude(double2* psi, u64 index, double re, double im) {
     if (blockIdx.x == 0 && threadIdx.x == 0) psi[index] = make_double2(re, im);
 }

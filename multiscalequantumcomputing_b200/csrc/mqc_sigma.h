@@ -78,6 +78,10 @@ struct MqcSigmaDev {
     unsigned src_lo, src_hi, own_lo, l_lo;
     int accumulate;                // L += instead of L =  (rounds after the first)
     unsigned pitch;                // elements between consecutive rows of Cown / Csrc / L (0: n_b)
+    // reproducible energy: every CTA leaves its partial in e_part[2 * cta], the last CTA to finish (ticket) adds them
+    // in a fixed order into e_out; NULL: one atomicAdd per CTA
+    double* e_part;
+    unsigned* ticket;
     // Row split (replicated matrix only): gridDim.z == 2, part z = 0 does phase 0 and the alpha single
     // links [0, split_l), part 1 the remaining links and phase 2; both ADD into a zeroed L with
     // atomics (two addends per element: the sum does not depend on their order).  0: one CTA per row.
@@ -845,9 +849,33 @@ k_sigma(const typename MqcSgAmp<REAL>::T* __restrict__ Cown, const typename MqcS
         double vi = (lane < MQC_SG_THREADS / 32) ? red[1][lane] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { vr += __shfl_xor_sync(0xffffffffu, vr, o); vi += __shfl_xor_sync(0xffffffffu, vi, o); }
-        if (lane == 0) {
-            if (vr != 0.0) atomicAdd(e_out, vr);
-            if (vi != 0.0) atomicAdd(e_out + 1, vi);
+        if (!S.e_part) {
+            if (lane == 0) {
+                if (vr != 0.0) atomicAdd(e_out, vr);
+                if (vi != 0.0) atomicAdd(e_out + 1, vi);
+            }
+        } else {
+            const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+            const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            unsigned last = 0u;
+            if (lane == 0) {
+                S.e_part[2 * (size_t)cta] = vr; S.e_part[2 * (size_t)cta + 1] = vi;
+                __threadfence();
+                last = atomicAdd(S.ticket, 1u) == total - 1u ? 1u : 0u;
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {                                               // every other CTA's partial is visible (fence + ticket)
+                __threadfence();
+                double sr = 0.0, si = 0.0;
+                for (unsigned c = lane; c < total; c += 32) { sr += __ldcg(S.e_part + 2 * (size_t)c); si += __ldcg(S.e_part + 2 * (size_t)c + 1); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+                if (lane == 0) {
+                    if (sr != 0.0) atomicAdd(e_out, sr);
+                    if (si != 0.0) atomicAdd(e_out + 1, si);
+                    *S.ticket = 0u;                                   // ready for the next launch on this stream
+                }
+            }
         }
     }
 }

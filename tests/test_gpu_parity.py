@@ -240,6 +240,43 @@ def test_real_and_complex_storage_selection():
     h.close(); h2.close()
 
 
+def test_reproducible_energy_and_gradient():
+    """Default option deterministic = 1: the gradient partials of the adjoint sweep and the energy partials of K2 are
+    added in a fixed order, so the same input gives the same bits - on the same handle, on a fresh handle, and with
+    tied parameters (several factors per parameter).  An optimiser or a chemical-potential search on top then takes the
+    same path every run (scripts/dmet_adapt_spread.py: one value in every run; with deterministic = 0: 1e-9 ... 4e-8)."""
+    for n, ne in ((6, 6), (8, 8)):
+        h, orc, F, tab, th = _setup(n, ne, "blocked", {})
+        e0, g0 = h.energy_grad(th)
+        for _ in range(3):
+            e1, g1 = h.energy_grad(th)
+            assert e1 == e0 and np.array_equal(g1, g0)
+        assert h.energy(th) == e0
+        h2, *_ = _setup(n, ne, "blocked", {})
+        e2, g2 = h2.energy_grad(th)
+        assert e2 == e0 and np.array_equal(g2, g0)
+        h.close(); h2.close()
+    # tied parameters: every parameter drives three consecutive factors
+    h1, eri = random_fragment_integrals(6, 1234)
+    tab = fragment_term_table(h1, eri, 0, 0.0, 0.25)
+    F = uccsd_factors(6, 6, "blocked")
+    tied = (np.arange(len(F.theta_index)) // 3).astype(np.int32)
+    n_theta = int(tied.max()) + 1
+    th = np.random.default_rng(7).normal(0, 0.05, n_theta)
+    res = []
+    for _ in range(2):
+        h = _lib.Handle(12)
+        h.set_hamiltonian(*tab)
+        h.set_ansatz(F.kind, F.idx, tied, n_theta, F.ref_index)
+        res.append(h.energy_grad(th)); res.append(h.energy_grad(th))
+        h.close()
+    orc = UCCSDOracle(12, F.as_tuples(), tied, F.ref_index, tab)
+    e_ref, g_ref = orc.energy_grad(th)
+    assert abs(res[0][0] - e_ref) < E_TOL and abs(res[0][1] - g_ref).max() < G_TOL
+    for e, g in res[1:]:
+        assert e == res[0][0] and np.array_equal(g, res[0][1])
+
+
 def _c_oracle_check(tab, F, th, e, g):
     from oracle.cref import CRefUCCSD, use_all_cores
     use_all_cores()
@@ -391,12 +428,12 @@ def test_dmet_with_adapt_matches_reference_fci_log(golden):
 def test_dmet_with_tight_adapt_matches_reference_fci_log_to_1e8(golden):
     """BASELINE.json: 'DMET energies matching the reference to 1e-8 Ha'.  With tight ADAPT / optimiser thresholds the
     whole DMET loop on the GPU reproduces the reference's FCI-solver log (test/testlog_fci:438,
-    E = -5.373292466490414) at the 1e-8 Ha level: 16 runs each (scripts/dmet_adapt_spread.py,
-    profiles/dmet_adapt_spread_r02.jsonl) gave 1.0e-9 ... 4.2e-8 (median 9.5e-9) with the spin-orbital pool and
-    1.5e-9 ... 3.7e-8 with the spin-adapted pool in product form.  The run-to-run spread is the tolerance of the
-    chemical-potential secant search (1e-8 on mu, qcdmet.py:232 - the reference's own criterion) times dE/dmu: the
-    unordered floating-point atomics of the gradient and energy sums (1e-16 relative) decide which way the last
-    secant steps and the last BFGS line searches go.  The bounds leave a factor 2.5 / 8 over the largest value seen."""
+    E = -5.373292466490414) at the 1e-8 Ha level: 7.5e-9 with the spin-orbital pool, 2.0e-8 with the spin-adapted
+    pool in product form, the same value in every run (scripts/dmet_adapt_spread.py, profiles/dmet_adapt_spread_r02c.jsonl)
+    now that the gradient and energy sums are reproducible.  With atomics (option deterministic = 0) 16 runs each gave
+    1.0e-9 ... 4.2e-8 and 1.5e-9 ... 3.7e-8 (profiles/dmet_adapt_spread_r02.jsonl): the tolerance of the chemical-
+    potential secant search (1e-8 on mu, qcdmet.py:232 - the reference's own criterion) times dE/dmu, steered by the last
+    bits of the sums.  The bounds cover that spread with a factor 2.5 / 8."""
     ints = local_integrals(hydrogen_ring(10, 1.0))
     opts = {"ansatz": "adapt", "adapt": {"eps": 1e-8, "nu": 10, "pool": "generalized"}, "opt": {"gtol": 1e-10}}
     import warnings
