@@ -83,7 +83,18 @@ int mqc_shard_read(mqc_solver_t* s, const double* theta, int32_t member, double*
  * "sector" (1 = exploit particle-number/S_z conservation of the ansatz in H|psi>),
  * "sparse_tiles" (1 = compressed-sector tiles when the ansatz conserves N_alpha, N_beta),
  * "tile_threads" (256), "sparse_threads" (128), "sigma" (1 = link-table kernel for the sector
- * form of H|psi>, 0 = first-generation X-group kernel). */
+ * form of H|psi>, 0 = first-generation X-group kernel).
+ * Compact sector storage (round 2): "compact" (1 = the state is the matrix C[alpha string][beta string] whenever the
+ * ansatz conserves N_alpha, N_beta and the handle is unsharded), "real_amplitudes" (1 = 8-byte amplitudes when the
+ * Hamiltonian is real, see mqc_amplitude_bytes; 0 = always complex128), "csweep_threads" (128: threads per tile of
+ * the forward sweep), "csweep_adj_threads" (0 = automatic: 64 with real amplitudes), "csweep_ctas" (0 = one CTA per
+ * tile up to a few thousand, else persistent CTAs), "csweep_snake" (1 = boustrophedon tile order), "csweep_pdl"
+ * (0; 1 = programmatic dependent launch of the passes), "rdm_gram" (1 = Gram-matrix RDM kernel), "sigma_split"
+ * (-1 = automatic: a row of H|psi> is split over two CTAs when there are few rows), "sigma_stage_bytes" (98304),
+ * "sigma_ab" (0), "deterministic" (1 = gradient and energy partial sums are added in a fixed order: the same input
+ * gives the same bits; 0 = floating-point atomics).  Options that shape schedules, plans or uploaded tables
+ * ("tile_bits", "grad_tile_bits", "low_bits", "mode", "sector", "sparse_tiles", "sp2", "compact", "real_amplitudes",
+ * "sigma_blocked", "csweep_snake") are refused after mqc_set_ansatz. */
 int mqc_set_option(mqc_solver_t* s, const char* key, int64_t value);
 
 /* Replaces: `mapping(fermi_ham,'JW',...)` + `get_sparse_operator(qubit_ham)`,
