@@ -1019,7 +1019,11 @@ static void launch_sigma(mqc_solver* s, const SigmaTables* SG, const double2* Co
     D.e_part = nullptr; D.ticket = nullptr;
     if (s->deterministic) {
         const size_t ctas = (size_t)grid.x * grid.y * grid.z;
-        if (s->e_part.n < 2 * ctas) s->e_part.alloc(2 * ctas);
+        if (s->e_part.n < 2 * ctas) {
+            if (s->capturing) throw MqcError("internal: energy partial buffer grows during graph capture");
+            invalidate_graphs(s);                        // captured launches hold the old pointer
+            s->e_part.alloc(2 * ctas);
+        }
         if (!s->e_ticket.p) { s->e_ticket.alloc(1); CK(cudaMemsetAsync(s->e_ticket.p, 0, sizeof(unsigned), s->stream)); }
         D.e_part = s->e_part.p; D.ticket = s->e_ticket.p;
     }
